@@ -1,0 +1,339 @@
+// layer_kernels.cu -- generic (any n / segments / widths / kind) single-layer kernels.
+//
+// These back the drop-in nn.Modules returned by high_order_fc_layers(...) and every network the
+// fused whole-network kernel (fused_mlp.cu) has no instantiation for.  One CTA handles a tile of
+// TB samples: phase 1 evaluates, once per (sample, input), the node window and the n basis
+// values (+ derivatives in backward) into shared memory; phase 2 contracts them with the
+// gathered weights w[out][in][window].  Algorithm: SURVEY.md A.3-A.5 / oracle/hol_oracle.py.
+#include "hoir_common.cuh"
+
+namespace {
+
+struct LayerParams {
+  int kind, n, segments, in_f, out_f, nodes, stride;
+  float length, half, rescale, periodicity, segf, inv_segf;
+  int pow2, odd_is_sin;
+  LagrangeTable lag;
+  FourierTable fou;
+};
+
+// record layout per (sample, input): [0]=window base (int bits) [1]=d x_in/dx  [2..2+n) values
+// [2+n..2+2n) derivatives wrt x_in (backward only)
+__device__ __forceinline__ void eval_record(const LayerParams& p, float x, float* rec, bool with_der) {
+  float psign = 1.f;
+  if (p.periodicity > 0.f) x = hoir::make_periodic(x, p.periodicity, &psign);
+  float* val = rec + 2;
+  float* der = with_der ? rec + 2 + p.n : nullptr;
+  int base = 0;
+  float slope = 1.f;
+  if (p.kind == HOIR_CONTINUOUS || p.kind == HOIR_DISCONTINUOUS) {
+    int id = hoir::segment_index(x, p.half, p.length, p.segf, p.segments);
+    float xi;
+    if (p.pow2) {
+      xi = hoir::local_coordinate<true>(x, id, p.half, p.length, p.segf, p.inv_segf);
+      slope = hoir::local_slope<true>(id, p.length, p.segf);
+    } else {
+      xi = hoir::local_coordinate<false>(x, id, p.half, p.length, p.segf, p.inv_segf);
+      slope = hoir::local_slope<false>(id, p.length, p.segf);
+    }
+    base = id * p.stride;
+    hoir::lagrange_rt(p.n, p.lag.X, p.lag.D, xi, val, der);
+  } else if (p.kind == HOIR_POLYNOMIAL) {
+    hoir::lagrange_rt(p.n, p.lag.X, p.lag.D, x, val, der);
+  } else {
+    hoir::fourier_rt(p.n, p.fou.c, x, p.length, p.odd_is_sin, val, der);
+  }
+  rec[0] = __int_as_float(base);
+  rec[1] = slope * psign;
+}
+
+__global__ void __launch_bounds__(256)
+layer_fwd_kernel(LayerParams p, long long B, int TB, const float* __restrict__ x,
+                 const float* __restrict__ w, float* __restrict__ y) {
+  extern __shared__ float smem[];
+  const int recw = p.n + 2;
+  for (long long tile = blockIdx.x; tile * TB < B; tile += gridDim.x) {
+    const long long b0 = tile * TB;
+    const int nb = (int)min((long long)TB, B - b0);
+    for (int it = threadIdx.x; it < nb * p.in_f; it += blockDim.x)
+      eval_record(p, x[b0 * p.in_f + it], smem + (size_t)it * recw, false);
+    __syncthreads();
+    for (int it = threadIdx.x; it < nb * p.out_f; it += blockDim.x) {
+      const int bl = it / p.out_f, o = it - bl * p.out_f;
+      const float* rec = smem + (size_t)bl * p.in_f * recw;
+      const float* wo = w + (size_t)o * p.in_f * p.nodes;
+      float acc = 0.f;
+      for (int i = 0; i < p.in_f; ++i, rec += recw, wo += p.nodes) {
+        const float* wi = wo + __float_as_int(rec[0]);
+        for (int j = 0; j < p.n; ++j) acc = fmaf(rec[2 + j], __ldg(wi + j), acc);
+      }
+      y[(b0 + bl) * p.out_f + o] = acc * p.rescale;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layer_bwd_kernel(LayerParams p, long long B, int TB, const float* __restrict__ x,
+                 const float* __restrict__ w, const float* __restrict__ gy,
+                 float* __restrict__ gx, float* __restrict__ gw) {
+  extern __shared__ float smem[];
+  const int recw = 2 * p.n + 2;
+  for (long long tile = blockIdx.x; tile * TB < B; tile += gridDim.x) {
+    const long long b0 = tile * TB;
+    const int nb = (int)min((long long)TB, B - b0);
+    for (int it = threadIdx.x; it < nb * p.in_f; it += blockDim.x)
+      eval_record(p, x[b0 * p.in_f + it], smem + (size_t)it * recw, true);
+    __syncthreads();
+    if (gx != nullptr) {
+      for (int it = threadIdx.x; it < nb * p.in_f; it += blockDim.x) {
+        const int bl = it / p.in_f, i = it - bl * p.in_f;
+        const float* rec = smem + (size_t)it * recw;
+        const int base = __float_as_int(rec[0]);
+        const float* g = gy + (b0 + bl) * p.out_f;
+        float acc = 0.f;
+        for (int o = 0; o < p.out_f; ++o) {
+          const float* wi = w + ((size_t)o * p.in_f + i) * p.nodes + base;
+          float t = 0.f;
+          for (int j = 0; j < p.n; ++j) t = fmaf(rec[2 + p.n + j], __ldg(wi + j), t);
+          acc = fmaf(__ldg(g + o), t, acc);
+        }
+        gx[(b0 + bl) * p.in_f + i] = acc * rec[1] * p.rescale;
+      }
+    }
+    if (gw != nullptr) {
+      const int per_b = p.in_f * p.out_f;
+      for (int it = threadIdx.x; it < nb * per_b; it += blockDim.x) {
+        const int bl = it / per_b, r = it - bl * per_b;
+        const int o = r / p.in_f, i = r - o * p.in_f;
+        const float* rec = smem + ((size_t)bl * p.in_f + i) * recw;
+        const int base = __float_as_int(rec[0]);
+        const float g = __ldg(gy + (b0 + bl) * p.out_f + o) * p.rescale;
+        if (g != 0.f) {
+          float* dst = gw + ((size_t)o * p.in_f + i) * p.nodes + base;
+          for (int j = 0; j < p.n; ++j) atomicAdd(dst + j, rec[2 + j] * g);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void segment_index_kernel(LayerParams p, long long total, const float* __restrict__ x,
+                                     int* __restrict__ id_min, int* __restrict__ wid_min,
+                                     float* __restrict__ x_local) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total;
+       k += (long long)gridDim.x * blockDim.x) {
+    float xv = x[k], ps;
+    if (p.periodicity > 0.f) xv = hoir::make_periodic(xv, p.periodicity, &ps);
+    int id = hoir::segment_index(xv, p.half, p.length, p.segf, p.segments);
+    id_min[k] = id;
+    wid_min[k] = id * p.stride;
+    if (x_local)
+      x_local[k] = p.pow2 ? hoir::local_coordinate<true>(xv, id, p.half, p.length, p.segf, p.inv_segf)
+                          : hoir::local_coordinate<false>(xv, id, p.half, p.length, p.segf, p.inv_segf);
+  }
+}
+
+// MaxAbsNormalization: one warp per row; first index wins ties (torch.max(dim) on CPU).
+__global__ void __launch_bounds__(256)
+maxabs_kernel(long long B, int width, float eps, const float* __restrict__ x,
+              const float* __restrict__ gy, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long b = warp0; b < B; b += nwarps) {
+    const float* xr = x + b * width;
+    float m = -1.f;
+    int k = 0x7fffffff;
+    for (int i = lane; i < width; i += 32) {
+      float a = fabsf(xr[i]);
+      if (a > m || (a != a && m == m)) { m = a; k = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      int k2 = __shfl_xor_sync(0xffffffffu, k, o);
+      if (m2 > m || (m2 == m && k2 < k)) { m = m2; k = k2; }
+    }
+    const float d = __fadd_rn(m, eps);
+    if (gy == nullptr) {
+      for (int i = lane; i < width; i += 32) out[b * width + i] = __fdiv_rn(xr[i], d);
+    } else {
+      const float* gr = gy + b * width;
+      float dot = 0.f;
+      for (int i = lane; i < width; i += 32) dot = fmaf(gr[i], __fdiv_rn(xr[i], d), dot);
+      dot = hoir::warp_sum(dot);
+      const float xk = xr[k];
+      const float sgn = xk > 0.f ? 1.f : (xk < 0.f ? -1.f : 0.f);
+      for (int i = lane; i < width; i += 32) {
+        float g = gr[i];
+        if (i == k) g -= sgn * dot;
+        out[b * width + i] = __fdiv_rn(g, d);
+      }
+    }
+  }
+}
+
+__global__ void mesh_positions_kernel(hoir_mesh_desc m, long long B, float* __restrict__ x) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < B;
+       k += (long long)gridDim.x * blockDim.x) {
+    float c[2 * HOIR_MAX_ROTATIONS];
+    hoir::mesh_position(m, m.first_pixel + k, c, HOIR_MAX_ROTATIONS);
+    for (int r = 0; r < 2 * m.rotations; ++r) x[k * 2 * m.rotations + r] = c[r];
+  }
+}
+
+int make_params(const hoir_layer_desc* d, LayerParams* p) {
+  if (d == nullptr) return hoir_set_error(HOIR_EINVAL, "null layer descriptor", "make_params");
+  if (d->kind < HOIR_CONTINUOUS || d->kind > HOIR_FOURIER)
+    return hoir_set_error(HOIR_EINVAL, "layer kind not recognized", "make_params");
+  if (d->n < 1 || d->n > HOIR_MAX_N)
+    return hoir_set_error(HOIR_EINVAL, "n must be in [1, 32]", "make_params");
+  if (d->in_features < 1 || d->out_features < 1)
+    return hoir_set_error(HOIR_EINVAL, "in_features/out_features must be >= 1", "make_params");
+  const bool piecewise = d->kind == HOIR_CONTINUOUS || d->kind == HOIR_DISCONTINUOUS;
+  if (piecewise && d->segments < 1)
+    return hoir_set_error(HOIR_EINVAL, "segments must be >= 1", "make_params");
+  if (d->kind == HOIR_CONTINUOUS && d->n < 2)
+    return hoir_set_error(HOIR_EINVAL, "continuous layers need n >= 2", "make_params");
+  if (!(d->length > 0.f))
+    return hoir_set_error(HOIR_EINVAL, "length must be > 0", "make_params");
+  p->kind = d->kind;
+  p->n = d->n;
+  p->segments = piecewise ? d->segments : 1;
+  p->in_f = d->in_features;
+  p->out_f = d->out_features;
+  p->nodes = hoir_layer_nodes(d);
+  p->stride = piecewise ? hoir::piecewise_stride(d->kind, d->n) : 0;
+  p->length = d->length;
+  p->half = 0.5f * d->length;
+  p->rescale = d->rescale == 0.f ? 1.f : d->rescale;
+  p->periodicity = d->periodicity;
+  p->segf = (float)p->segments;
+  p->inv_segf = 1.f / (float)p->segments;
+  p->pow2 = hoir::is_pow2(p->segments) && d->length == 2.f;
+  p->odd_is_sin = d->fourier_odd_is_sin;
+  // piecewise layers interpolate on the unit nodes; Polynomial on (length/2) * nodes
+  hoir_make_lagrange_table(d->n, d->kind == HOIR_POLYNOMIAL ? 0.5f * d->length : 1.f, &p->lag);
+  hoir_make_fourier_table(d->n, d->fourier_arg_scale == 0.f ? 2.f : d->fourier_arg_scale, &p->fou);
+  return HOIR_OK;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+constexpr int kSmemBudget = 96 * 1024;
+
+}  // namespace
+
+extern "C" int hoir_layer_nodes(const hoir_layer_desc* d) {
+  if (d == nullptr) return -1;
+  switch (d->kind) {
+    case HOIR_CONTINUOUS: return (d->n - 1) * d->segments + 1;
+    case HOIR_DISCONTINUOUS: return d->n * d->segments;
+    case HOIR_POLYNOMIAL:
+    case HOIR_FOURIER: return d->n;
+    default: return -1;
+  }
+}
+
+extern "C" int hoir_layer_forward(const hoir_layer_desc* d, long long B, const float* x,
+                                  const float* w, float* y, void* stream) {
+  LayerParams p;
+  if (int e = make_params(d, &p)) return e;
+  if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_layer_forward");
+  if (B == 0) return HOIR_OK;
+  if (!x || !w || !y) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_layer_forward");
+  const size_t per_sample = (size_t)p.in_f * (p.n + 2) * sizeof(float);
+  if (per_sample > (size_t)kSmemBudget)
+    return hoir_set_error(HOIR_EUNSUPPORTED, "in_features*(n+2) exceeds the shared-memory tile", "hoir_layer_forward");
+  int TB = (int)min((size_t)64, (size_t)kSmemBudget / per_sample);
+  if ((long long)TB > B) TB = (int)B;
+  const size_t smem = per_sample * TB;
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  long long tiles = (B + TB - 1) / TB;
+  int grid = (int)min(tiles, (long long)num_sms() * 4);
+  layer_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, B, TB, x, w, y);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+extern "C" int hoir_layer_backward(const hoir_layer_desc* d, long long B, const float* x,
+                                   const float* w, const float* gy, float* gx, float* gw,
+                                   void* stream) {
+  LayerParams p;
+  if (int e = make_params(d, &p)) return e;
+  if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_layer_backward");
+  if (B == 0 || (gx == nullptr && gw == nullptr)) return HOIR_OK;
+  if (!x || !w || !gy) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_layer_backward");
+  const size_t per_sample = (size_t)p.in_f * (2 * p.n + 2) * sizeof(float);
+  if (per_sample > (size_t)kSmemBudget)
+    return hoir_set_error(HOIR_EUNSUPPORTED, "in_features*(2n+2) exceeds the shared-memory tile", "hoir_layer_backward");
+  int TB = (int)min((size_t)64, (size_t)kSmemBudget / per_sample);
+  if ((long long)TB > B) TB = (int)B;
+  const size_t smem = per_sample * TB;
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  long long tiles = (B + TB - 1) / TB;
+  int grid = (int)min(tiles, (long long)num_sms() * 4);
+  layer_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, B, TB, x, w, gy, gx, gw);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+extern "C" int hoir_segment_index(const hoir_layer_desc* d, long long B, const float* x,
+                                  int* id_min, int* wid_min, float* x_local, void* stream) {
+  LayerParams p;
+  if (int e = make_params(d, &p)) return e;
+  if (d->kind != HOIR_CONTINUOUS && d->kind != HOIR_DISCONTINUOUS)
+    return hoir_set_error(HOIR_EINVAL, "segment index is defined for piecewise layers only", "hoir_segment_index");
+  if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_segment_index");
+  if (B == 0) return HOIR_OK;
+  if (!x || !id_min || !wid_min) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_segment_index");
+  const long long total = B * p.in_f;
+  int grid = (int)min((total + 255) / 256, (long long)num_sms() * 8);
+  segment_index_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, total, x, id_min, wid_min, x_local);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+static int maxabs_launch(long long B, int width, float eps, const float* x, const float* gy,
+                         float* out, void* stream, const char* where) {
+  if (B < 0 || width < 1) return hoir_set_error(HOIR_EINVAL, "bad shape", where);
+  if (B == 0) return HOIR_OK;
+  if (!x || !out) return hoir_set_error(HOIR_EINVAL, "null device pointer", where);
+  int grid = (int)min((B + 7) / 8, (long long)num_sms() * 8);
+  maxabs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, width, eps, x, gy, out);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+extern "C" int hoir_maxabs_forward(long long B, int width, float eps, const float* x, float* y,
+                                   void* stream) {
+  return maxabs_launch(B, width, eps, x, nullptr, y, stream, "hoir_maxabs_forward");
+}
+extern "C" int hoir_maxabs_backward(long long B, int width, float eps, const float* x,
+                                    const float* gy, float* gx, void* stream) {
+  if (B > 0 && !gy) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_maxabs_backward");
+  return maxabs_launch(B, width, eps, x, gy, gx, stream, "hoir_maxabs_backward");
+}
+
+extern "C" int hoir_mesh_positions(const hoir_mesh_desc* mesh, long long B, float* x, void* stream) {
+  if (!mesh || mesh->rotations < 1 || mesh->rotations > HOIR_MAX_ROTATIONS || mesh->rows < 1 ||
+      mesh->cols < 1 || mesh->normalize_mode < 0 || mesh->normalize_mode > 2)
+    return hoir_set_error(HOIR_EINVAL, "bad mesh descriptor", "hoir_mesh_positions");
+  if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_mesh_positions");
+  if (B == 0) return HOIR_OK;
+  if (!x) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_mesh_positions");
+  int grid = (int)min((B + 255) / 256, (long long)num_sms() * 8);
+  mesh_positions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*mesh, B, x);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}

@@ -1,0 +1,158 @@
+/* hoir.h -- C ABI of libhoir_b200.so (hand-written CUDA for sm_100a).
+ *
+ * The reference (jloveric/high-order-implicit-representation) has no native code and no FFI:
+ * its hot path sits behind the Python constructors of the un-vendored package
+ * high-order-layers-torch (star-imported at
+ * /root/reference/high_order_implicit_representation/networks.py:7-8).  The drop-in boundary is
+ * therefore (a) this C ABI -- plain pointers and sizes, no torch types -- and (b) the Python
+ * mirror of the package's constructors in high-order-implicit-representation_b200/, which binds
+ * these entry points with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer named x, w, y, g*, target, ... is a DEVICE pointer owned by the caller,
+ *     row-major contiguous fp32 unless stated; the library never allocates or frees user memory;
+ *   - `stream` is a cudaStream_t passed as void*; all launches are asynchronous on it;
+ *   - return 0 on success; otherwise a HOIR_E* code, message via hoir_last_error() (thread local);
+ *   - B == 0 is legal everywhere (the reference render loops feed one empty batch,
+ *     /root/reference/high_order_implicit_representation/rendering.py:200);
+ *   - weight layout at this boundary is the package's  w[out_features][in_features][nodes];
+ *   - there is NO CPU fallback: a host pointer is a caller error.
+ */
+#ifndef HOIR_H
+#define HOIR_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOIR_VERSION 100
+#define HOIR_MAX_LAYERS 8
+#define HOIR_MAX_N 32          /* max basis functions per segment / Fourier terms          */
+#define HOIR_MAX_ROTATIONS 8
+
+enum hoir_error {
+  HOIR_OK = 0,
+  HOIR_EINVAL = 1,             /* bad descriptor / shape / null pointer -> ValueError       */
+  HOIR_EUNSUPPORTED = 2,       /* no fused instantiation for this network -> use per-layer   */
+  HOIR_ECUDA = 3               /* CUDA runtime error -> RuntimeError                         */
+};
+
+/* layer_type strings of high_order_fc_layers(...),
+ * /root/reference/high_order_implicit_representation/networks.py:148-161 */
+enum hoir_kind {
+  HOIR_CONTINUOUS = 0,         /* PiecewisePolynomial: nodes = (n-1)*segments+1             */
+  HOIR_DISCONTINUOUS = 1,      /* PiecewiseDiscontinuousPolynomial: nodes = n*segments      */
+  HOIR_POLYNOMIAL = 2,         /* Polynomial: nodes = n, no segment map                      */
+  HOIR_FOURIER = 3             /* FourierSeries: nodes = n (1/2, then sin/cos pairs)         */
+};
+
+/* One high-order layer.  Replaces the kwargs of high_order_fc_layers as forwarded by
+ * HighOrderMLP (/root/reference/high_order_implicit_representation/networks.py:41-55). */
+typedef struct hoir_layer_desc {
+  int kind;                    /* enum hoir_kind                                             */
+  int n;                       /* basis functions per segment (Fourier: number of terms)     */
+  int segments;                /* piecewise kinds only; >= 1                                  */
+  int in_features;
+  int out_features;
+  float length;                /* `scale` kwarg, 2.0 through Net                             */
+  float rescale;               /* output multiplier: 1/in_features if rescale_output else 1  */
+  float periodicity;           /* <= 0: none                                                  */
+  float fourier_arg_scale;     /* basis argument = fourier_arg_scale*pi*i*x/length           */
+  int fourier_odd_is_sin;      /* 1: odd j -> sin, even j -> cos                             */
+} hoir_layer_desc;
+
+/* HighOrderMLP = L_0, (MaxAbs, L_k) x hidden_layers, MaxAbs, L_last. */
+typedef struct hoir_mlp_desc {
+  int num_layers;              /* hidden_layers + 2                                          */
+  hoir_layer_desc layers[HOIR_MAX_LAYERS];
+  int normalize;               /* 1: MaxAbsNormalization between layers, 0: none             */
+  float norm_eps;              /* 1e-6                                                        */
+} hoir_mlp_desc;
+
+/* In-kernel coordinate source: positions_from_mesh(width=rows, height=cols, rotations,
+ * normalize) followed by stack(dim=2).reshape(-1, 2*rotations)
+ * (/root/reference/high_order_implicit_representation/single_image_dataset.py:39-47).
+ * Sample k of a call is pixel first_pixel + k in row-major (row, col) order. */
+typedef struct hoir_mesh_desc {
+  int rows, cols;
+  int rotations;               /* in_features of layer 0 must equal 2*rotations              */
+  int normalize_mode;          /* 0: raw integers; 1: (v/max(rows,cols)-0.5)*2;
+                                  2: v/(size-1)*2-1                                           */
+  long long first_pixel;
+  float rot_x[HOIR_MAX_ROTATIONS], rot_y[HOIR_MAX_ROTATIONS], rot_sum[HOIR_MAX_ROTATIONS];
+} hoir_mesh_desc;
+
+/* Target source for the fused training step. */
+enum hoir_target_kind {
+  HOIR_TARGET_F32 = 0,         /* float target[B][out]                                        */
+  HOIR_TARGET_U8_IMAGE = 1     /* uint8 image[rows*cols][3], indexed by pixel; the kernel
+                                  applies  u*2/255-1  (single_image_dataset.py:49)            */
+};
+
+const char* hoir_last_error(void);
+int hoir_version(void);
+/* number of weight nodes per (out, in) link for a layer descriptor, or -1 */
+int hoir_layer_nodes(const hoir_layer_desc* d);
+
+/* ---- single layer (replaces <layer>.forward / autograd backward of the package) -------- */
+int hoir_layer_forward(const hoir_layer_desc* d, long long B, const float* x, const float* w,
+                       float* y, void* stream);
+/* gx may be NULL (no input gradient); gw may be NULL; gw is ACCUMULATED into. */
+int hoir_layer_backward(const hoir_layer_desc* d, long long B, const float* x, const float* w,
+                        const float* gy, float* gx, float* gw, void* stream);
+/* Debug/parity entry: the integer part of the path.  id_min[B*in], wid_min[B*in] (first node
+ * of the gathered window), x_local[B*in] (may be NULL).  Piecewise kinds only. */
+int hoir_segment_index(const hoir_layer_desc* d, long long B, const float* x, int* id_min,
+                       int* wid_min, float* x_local, void* stream);
+
+/* ---- MaxAbsNormalization over dim 1 ------------------------------------------------------ */
+int hoir_maxabs_forward(long long B, int width, float eps, const float* x, float* y, void* stream);
+int hoir_maxabs_backward(long long B, int width, float eps, const float* x, const float* gy,
+                         float* gx, void* stream);
+
+/* ---- coordinates --------------------------------------------------------------------------*/
+/* x[B][2*rotations] for pixels first_pixel .. first_pixel+B-1 (bit-identical to the host mesh) */
+int hoir_mesh_positions(const hoir_mesh_desc* mesh, long long B, float* x, void* stream);
+
+/* ---- fused whole-network path ---------------------------------------------------------------
+ * Packed weights: one flat fp32 buffer, layer l at float offset hoir_mlp_packed_offset(l) with
+ * layout [in][node][out_padded] (out_padded = out rounded up to 4).  hoir_mlp_pack fills it from
+ * the boundary-layout tensors; it must be refreshed whenever a w changes. */
+int hoir_mlp_fused_supported(const hoir_mlp_desc* m);           /* 1 / 0 */
+long long hoir_mlp_packed_size(const hoir_mlp_desc* m);         /* floats, or -1 */
+long long hoir_mlp_packed_offset(const hoir_mlp_desc* m, int layer);
+int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, float* packed, void* stream);
+
+/* y[B][out] = MLP(x).  Exactly one of x / mesh is non-NULL.  post_scale: 0 -> y, 1 -> 0.5*(y+1)
+ * (the render loop, /root/reference/high_order_implicit_representation/rendering.py:213). */
+int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float* x,
+                     const hoir_mesh_desc* mesh, const float* packed, float* y, int post_scale,
+                     void* stream);
+
+/* One fused forward + MSE + backward pass (Net.eval_step + loss.backward(),
+ * /root/reference/high_order_implicit_representation/networks.py:64-70):
+ *   loss_sum[0] += sum_b sum_o (y_hat - target)^2 * loss_scale       (loss_scale = 1/(B_global*out))
+ *   gw[l]       += dL/dw_l   in boundary layout [out][in][nodes], with L = MSE(mean) over B_global
+ * Exactly one of x / mesh non-NULL; target per target_kind.  If gy_ext != NULL it is used as
+ * dL/dy_hat[B][out] instead of the MSE (autograd backward) and target/loss_sum are ignored. */
+int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const float* x,
+                        const hoir_mesh_desc* mesh, int target_kind, const void* target,
+                        const float* gy_ext, const float* packed, float* const* gw,
+                        float* loss_sum, float loss_scale, void* stream);
+
+/* ---- optimizers on flat fp32 vectors --------------------------------------------------------
+ * torch.optim.Adam (networks.py:94-97) and SparseLion (networks.py:99-102). */
+int hoir_adam_step(long long n, float* w, const float* g, float* exp_avg, float* exp_avg_sq,
+                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                   long long step, void* stream);
+int hoir_sparse_lion_step(long long n, float* w, const float* g, float* exp_avg, float lr,
+                          float beta1, float beta2, float weight_decay, void* stream);
+
+/* FFMA-only micro-kernel: runs `iters` dependent-free FFMA rounds on every SM and returns the
+ * elapsed milliseconds in *ms (the measured FP32 roofline denominator of bench.py). */
+int hoir_ffma_peak(int iters, float* ms, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOIR_H */
