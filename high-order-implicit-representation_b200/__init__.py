@@ -1,0 +1,16 @@
+"""hoir_b200 -- B200-native (sm_100a) drop-in for the high-order layer path of
+jloveric/high-order-implicit-representation.  Importable as ``hoir_b200`` (see the shim
+``hoir_b200.py`` at the repository root; the directory name carries hyphens)."""
+from . import _lib, config, spec  # noqa: F401
+from ._lib import HoirUnsupported, build  # noqa: F401
+from .config import Config, apply_overrides, images_config, to_cfg  # noqa: F401
+from .engine import FusedTrainer, HostBatchStepper  # noqa: F401
+from .layers import (FourierSeries, HighOrderLayer, MaxAbsNormalization,  # noqa: F401
+                     PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial,
+                     high_order_fc_layers, segment_index)
+from .networks import (Adam, HighOrderMLP, Net, initialize_network_polynomial_layers,  # noqa: F401
+                       node_positions)
+from .sparse_optimizers import SparseLion  # noqa: F401
+from .utils import positions_from_mesh  # noqa: F401
+
+__version__ = "0.1.0"

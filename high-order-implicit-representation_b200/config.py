@@ -1,0 +1,102 @@
+"""Minimal stand-in for the Hydra/OmegaConf ``DictConfig`` the reference passes to ``Net``
+(/root/reference/config/images_config.yaml, neighborhood_config.yaml): attribute and item access
+over a nested dict, ``key=value`` overrides.  Hydra itself is out of scope."""
+from __future__ import annotations
+
+import copy
+from typing import Any, Iterable, Mapping
+
+
+class Config(dict):
+    """dict with attribute access, recursively (``cfg.mlp.hidden.width``)."""
+
+    def __init__(self, data: Mapping = (), **kw):
+        super().__init__()
+        for k, v in dict(data, **kw).items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        if isinstance(v, Mapping) and not isinstance(v, Config):
+            v = Config(v)
+        super().__setitem__(k, v)
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def to_dict(self) -> dict:
+        return {k: (v.to_dict() if isinstance(v, Config) else copy.deepcopy(v)) for k, v in self.items()}
+
+    def __deepcopy__(self, memo):
+        return Config(self.to_dict())
+
+
+def to_cfg(obj: Any) -> Any:
+    """dict -> Config; objects that already offer attribute access (DictConfig, Config) pass."""
+    if isinstance(obj, Config):
+        return obj
+    if isinstance(obj, Mapping):
+        return Config(obj)
+    return obj
+
+
+def cfg_to_dict(cfg: Any) -> dict:
+    if isinstance(cfg, Config):
+        return cfg.to_dict()
+    if isinstance(cfg, Mapping):
+        return {k: cfg_to_dict(v) if isinstance(v, Mapping) else v for k, v in cfg.items()}
+    try:  # OmegaConf, if it is ever installed
+        from omegaconf import OmegaConf
+        return OmegaConf.to_container(cfg, resolve=True)
+    except Exception:
+        return dict(cfg)
+
+
+def apply_overrides(cfg: Config, overrides: Iterable[str]) -> Config:
+    """Hydra-style ``a.b.c=value`` overrides (ints, floats, bools, null, strings)."""
+    for ov in overrides:
+        key, _, raw = ov.partition("=")
+        node = cfg
+        parts = key.split(".")
+        for p in parts[:-1]:
+            if p not in node:
+                node[p] = Config()
+            node = node[p]
+        node[parts[-1]] = _parse(raw)
+    return cfg
+
+
+def _parse(raw: str):
+    low = raw.strip().lower()
+    if low in ("true", "false"):
+        return low == "true"
+    if low in ("null", "none"):
+        return None
+    for cast in (int, float):
+        try:
+            return cast(raw)
+        except ValueError:
+            pass
+    return raw
+
+
+def images_config(**overrides) -> Config:
+    """Defaults of /root/reference/config/images_config.yaml + optimizer/sparse_lion.yaml (keys that
+    reach the hot path)."""
+    cfg = Config(
+        images=["images/newt.jpg"],
+        mlp=dict(layer_type="polynomial", n=3, n_in=None, n_out=None, n_hidden=None,
+                 periodicity=2.0, rescale_output=False, scale=2.0,
+                 input=dict(segments=100, width=4), output=dict(segments=2, width=3),
+                 hidden=dict(segments=2, layers=2, width=10)),
+        max_epochs=50, gpus=1, accelerator="cuda", lr=1e-3, batch_size=256, rotations=2,
+        train=True, checkpoint=None,
+        optimizer=dict(name="sparse_lion", lr=1e-4, scheduler="plateau", patience=10, factor=0.1))
+    for k, v in overrides.items():
+        cfg[k] = v
+    return cfg

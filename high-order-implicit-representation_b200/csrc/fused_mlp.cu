@@ -1,0 +1,722 @@
+// fused_mlp.cu -- whole-network kernels for the coordinate -> RGB implicit MLP
+// (HighOrderMLP of piecewise-Lagrange layers with MaxAbsNormalization in between, as built at
+// /root/reference/high_order_implicit_representation/networks.py:41-55).
+//
+// One CTA = 256 threads = one tile of 256 samples; the grid is persistent (one CTA per SM).
+//   forward : thread-per-sample.  Layer-0 inputs come from x[B][IN] or are generated from the
+//             pixel index (positions_from_mesh semantics); hidden/output weights live in shared
+//             memory as [in][node][out_pad] so a thread reads the n*out_pad floats of its node
+//             window with LDS.128; activations go layer to layer through registers and
+//             thread-private shared-memory columns -- never through HBM.
+//   backward: thread-per-sample for dL/dx (basis recomputed from the saved layer inputs);
+//             dL/dw as a block-level contraction over the tile's samples: sample threads stage
+//             the densified basis rows and dL/dy rows in shared memory, then "owner" threads
+//             (input, output group, sample phase) accumulate in registers, reduce the sample
+//             phases with warp shuffles and add into shared-memory accumulators that are
+//             flushed to HBM once per CTA.  Layer 0 (many segments) merges runs of equal
+//             segment and flushes with global atomics.
+// Algorithm: oracle/hol_oracle.py.
+#include "hoir_common.cuh"
+
+namespace {
+
+constexpr int BT = 256;  // samples per tile == threads per CTA
+constexpr int CI = 4;    // inputs per dL/dw chunk
+constexpr int RECW = 8;  // floats per densified basis row
+
+template <int KIND_, int N_, int IN_, int HID_, int OUT_, int NH_, int SEGH_, int SEGO_>
+struct Shape {
+  static constexpr int KIND = KIND_, N = N_, IN = IN_, HID = HID_, OUT = OUT_, NH = NH_;
+  static constexpr int SEGH = SEGH_, SEGO = SEGO_;
+  static constexpr bool CONT = KIND_ == HOIR_CONTINUOUS;
+  static constexpr int STRIDE = CONT ? N_ - 1 : N_;
+  static constexpr int NODES_H = STRIDE * SEGH_ + (CONT ? 1 : 0);
+  static constexpr int NODES_O = STRIDE * SEGO_ + (CONT ? 1 : 0);
+  static constexpr int HP = (HID_ + 3) & ~3;
+  static constexpr int OP = (OUT_ + 3) & ~3;
+  static constexpr int GP = (HID_ > OUT_ ? HID_ : OUT_) | 1;  // odd row stride of the dL/dy tile
+  static constexpr int WH = HID_ * NODES_H * HP;               // floats of one hidden layer
+  static constexpr int WO = HID_ * NODES_O * OP;
+  static_assert(N_ >= 2 && N_ <= 3, "fused kernel: n in {2,3}");
+  static_assert(NODES_H <= RECW && NODES_O <= RECW, "densified row too wide");
+  static_assert(IN_ <= 8 && IN_ <= CI * 2, "layer-0 inputs are kept in registers");
+  static_assert(IN_ * HID_ <= BT, "layer-0 dL/dw owners: one thread per (in, out) link");
+  // shared-memory plan (floats)
+  static constexpr int S_W = NH_ * WH + WO;                    // weights of layers 1..NH+1
+  static constexpr int S_A = (NH_ + 1) * HID_ * BT;            // saved layer inputs (train only)
+  static constexpr int S_G = BT * GP;
+  static constexpr int S_REC = CI * BT * RECW;
+  static constexpr int S_TRAIN_NOACC = S_W + S_A + S_G + S_REC;
+  static constexpr bool ACC_SMEM = (size_t)(S_TRAIN_NOACC + S_W) * 4 <= 227 * 1024;
+  static constexpr int S_TRAIN = S_TRAIN_NOACC + (ACC_SMEM ? S_W : 0);
+  static constexpr int S_FWD = S_W + HID_ * BT;
+};
+
+struct FusedParams {
+  long long B;
+  const float* x;            // [B][IN] or nullptr (mesh)
+  hoir_mesh_desc mesh;
+  int target_kind;
+  const void* target;
+  const float* gy_ext;
+  const float* packed;
+  long long off[HOIR_MAX_LAYERS];
+  float* gw[HOIR_MAX_LAYERS];
+  float* loss_sum;
+  float loss_scale;
+  float* y;
+  int post_scale;
+  int seg0, nodes0, pow2_0;
+  int normalize;
+  float norm_eps;
+  LagrangeTable lag;
+};
+
+struct SegConst {
+  int segments, stride;
+  float segf, inv_segf;
+};
+
+template <bool POW2>
+__device__ __forceinline__ void locate(float x, const SegConst& sc, int& id, float& xi) {
+  id = hoir::segment_index(x, 1.f, 2.f, sc.segf, sc.segments);
+  xi = hoir::local_coordinate<POW2>(x, id, 1.f, 2.f, sc.segf, sc.inv_segf);
+}
+
+// y[O] += sum_j l[j] * W[(base + j)][0..OP)   (W row-major, OP floats per node, 16B aligned)
+template <int N, int O, int OPAD, bool GLOBAL>
+__device__ __forceinline__ void contract_fwd(const float* __restrict__ wrow, const float* l,
+                                             float* __restrict__ acc) {
+  const float4* wp = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+#pragma unroll
+    for (int q = 0; q < OPAD / 4; ++q) {
+      float4 w = GLOBAL ? __ldg(wp + j * (OPAD / 4) + q) : wp[j * (OPAD / 4) + q];
+      if (4 * q + 0 < O) acc[4 * q + 0] = fmaf(l[j], w.x, acc[4 * q + 0]);
+      if (4 * q + 1 < O) acc[4 * q + 1] = fmaf(l[j], w.y, acc[4 * q + 1]);
+      if (4 * q + 2 < O) acc[4 * q + 2] = fmaf(l[j], w.z, acc[4 * q + 2]);
+      if (4 * q + 3 < O) acc[4 * q + 3] = fmaf(l[j], w.w, acc[4 * q + 3]);
+    }
+  }
+}
+
+// t[j] = sum_o g[o] * W[(base + j)][o]
+template <int N, int O, int OPAD>
+__device__ __forceinline__ void contract_bwd(const float* __restrict__ wrow, const float* g,
+                                             float* __restrict__ t) {
+  const float4* wp = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < OPAD / 4; ++q) {
+      float4 w = wp[j * (OPAD / 4) + q];
+      if (4 * q + 0 < O) s0 = fmaf(g[4 * q + 0], w.x, s0);
+      if (4 * q + 1 < O) s1 = fmaf(g[4 * q + 1], w.y, s1);
+      if (4 * q + 2 < O) s0 = fmaf(g[4 * q + 2], w.z, s0);
+      if (4 * q + 3 < O) s1 = fmaf(g[4 * q + 3], w.w, s1);
+    }
+    t[j] = s0 + s1;
+  }
+}
+
+// MaxAbsNormalization over the thread's W registers; first index wins ties.
+template <int W>
+__device__ __forceinline__ void maxabs_fwd(float* v, float eps, float& inv_d, int& kidx) {
+  float m = -1.f, vk = 0.f;
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    float a = fabsf(v[i]);
+    if (a > m) { m = a; k = i; vk = v[i]; }
+  }
+  const float d = __fadd_rn(m, eps);
+  const float sgn = vk > 0.f ? 1.f : (vk < 0.f ? -1.f : 0.f);
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] = __fdiv_rn(v[i], d);
+  inv_d = 1.f / d;
+  kidx = sgn > 0.f ? k : (sgn < 0.f ? (k | 0x10000) : (k | 0x20000));
+}
+
+// One hidden/output layer forward for this thread's sample: inputs from the smem column a[i*BT].
+template <int N, int I, int O, int OPAD, int NODES, bool POW2>
+__device__ __forceinline__ void layer_fwd(const float* __restrict__ a, const float* __restrict__ w,
+                                          const SegConst& sc, const LagrangeTable& lag,
+                                          float* __restrict__ acc) {
+#pragma unroll
+  for (int o = 0; o < O; ++o) acc[o] = 0.f;
+#pragma unroll 2
+  for (int i = 0; i < I; ++i) {
+    const float x = a[i * BT];
+    int id;
+    float xi, l[N];
+    locate<POW2>(x, sc, id, xi);
+    hoir::lagrange<N>(lag.X, lag.D, xi, l);
+    contract_fwd<N, O, OPAD, false>(w + ((size_t)i * NODES + id * sc.stride) * OPAD, l, acc);
+  }
+}
+
+// dL/dx of one hidden/output layer for this thread's sample.  Overwrites a[i*BT] with dL/dx_i and
+// returns sum_i dL/dx_i * x_i (needed by the MaxAbs backward).
+template <int N, int I, int O, int OPAD, int NODES, bool POW2>
+__device__ __forceinline__ float layer_bwd_x(float* __restrict__ a, const float* __restrict__ w,
+                                             const SegConst& sc, const LagrangeTable& lag,
+                                             const float* __restrict__ g) {
+  float dot = 0.f;
+#pragma unroll 2
+  for (int i = 0; i < I; ++i) {
+    const float x = a[i * BT];
+    int id;
+    float xi, l[N], d[N], t[N];
+    locate<POW2>(x, sc, id, xi);
+    hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
+    contract_bwd<N, O, OPAD>(w + ((size_t)i * NODES + id * sc.stride) * OPAD, g, t);
+    float gx = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) gx = fmaf(d[j], t[j], gx);
+    gx *= hoir::local_slope<POW2>(id, 2.f, sc.segf);
+    dot = fmaf(gx, x, dot);
+    a[i * BT] = gx;
+  }
+  return dot;
+}
+
+// dL/dw of a hidden/output layer for one tile: chunks of CI inputs.  Sample threads write the
+// densified basis row (NODES coefficients, zeros outside the active window) of their sample;
+// owner threads (il, og, bph) contract it with dL/dy over the samples b = bph (mod BPH).
+template <int N, int STRIDE, int I, int O, int OPAD, int NODES, bool POW2, bool ACC_SMEM>
+__device__ __forceinline__ void layer_bwd_w(const float* __restrict__ a, const float* __restrict__ G,
+                                            int GP, float* __restrict__ rec,
+                                            float* __restrict__ gws, float* __restrict__ gwg,
+                                            const SegConst& sc, const LagrangeTable& lag) {
+  constexpr int OGRP = O <= 8 ? 1 : (O <= 16 ? 2 : (O <= 32 ? 4 : 8));
+  constexpr int OG = (O + OGRP - 1) / OGRP;
+  static_assert(OG <= 8, "output group too wide");
+  constexpr int BPH = (64 / OGRP) < 32 ? (64 / OGRP) : 32;
+  constexpr int ACTIVE = CI * OGRP * BPH;
+  const int tid = threadIdx.x;
+  const int bph = tid % BPH, og = (tid / BPH) % OGRP, il = tid / (BPH * OGRP);
+  for (int c = 0; c < (I + CI - 1) / CI; ++c) {
+    // ---- stage densified rows of inputs c*CI .. c*CI+CI-1
+#pragma unroll
+    for (int k = 0; k < CI; ++k) {
+      const int i = c * CI + k;
+      float row[RECW];
+#pragma unroll
+      for (int q = 0; q < RECW; ++q) row[q] = 0.f;
+      if (i < I) {
+        const float x = a[i * BT + tid];
+        int id;
+        float xi, l[N];
+        locate<POW2>(x, sc, id, xi);
+        hoir::lagrange<N>(lag.X, lag.D, xi, l);
+        const int base = id * STRIDE;
+#pragma unroll
+        for (int q = 0; q < NODES; ++q) {
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            if (q - j >= 0 && (q - j) % STRIDE == 0)  // window starts are multiples of STRIDE
+              row[q] = (base + j == q) ? l[j] : row[q];
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(rec + ((size_t)k * BT + tid) * RECW);
+      dst[0] = make_float4(row[0], row[1], row[2], row[3]);
+      dst[1] = make_float4(row[4], row[5], row[6], row[7]);
+    }
+    __syncthreads();
+    // ---- owners
+    if (tid < ACTIVE) {
+      const int i = c * CI + il;
+      float acc[NODES][OG];
+#pragma unroll
+      for (int q = 0; q < NODES; ++q)
+#pragma unroll
+        for (int m = 0; m < OG; ++m) acc[q][m] = 0.f;
+#pragma unroll 2
+      for (int b = bph; b < BT; b += BPH) {
+        const float4* rp = reinterpret_cast<const float4*>(rec + ((size_t)il * BT + b) * RECW);
+        const float4 r0 = rp[0];
+        float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NODES > 4) r1 = rp[1];
+        const float cf[RECW] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        float gv[OG];
+#pragma unroll
+        for (int m = 0; m < OG; ++m) {
+          const int o = og + OGRP * m;
+          gv[m] = (o < O) ? G[b * GP + o] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < NODES; ++q)
+#pragma unroll
+          for (int m = 0; m < OG; ++m) acc[q][m] = fmaf(cf[q], gv[m], acc[q][m]);
+      }
+#pragma unroll
+      for (int q = 0; q < NODES; ++q)
+#pragma unroll
+        for (int m = 0; m < OG; ++m) {
+          float v = acc[q][m];
+#pragma unroll
+          for (int s = BPH / 2; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+          acc[q][m] = v;
+        }
+      if (bph == 0 && i < I) {
+#pragma unroll
+        for (int q = 0; q < NODES; ++q)
+#pragma unroll
+          for (int m = 0; m < OG; ++m) {
+            const int o = og + OGRP * m;
+            if (o < O) {
+              if (ACC_SMEM) gws[((size_t)i * NODES + q) * OPAD + o] += acc[q][m];
+              else if (acc[q][m] != 0.f) atomicAdd(gwg + ((size_t)o * I + i) * NODES + q, acc[q][m]);
+            }
+          }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dL/dw of layer 0 (many segments): owner (i, o) walks the tile's samples in order, merges runs
+// of equal node window and flushes each run with global atomics (boundary layout).
+template <int N, int IN, int HID>
+__device__ __forceinline__ void layer0_bwd_w(const float* __restrict__ rec0,
+                                             const float* __restrict__ G, int GP,
+                                             float* __restrict__ gw0, int nodes0) {
+  constexpr int PAIRS = IN * HID;
+  constexpr int BPH0 = PAIRS > 128 ? 1 : (PAIRS > 64 ? 2 : (PAIRS > 32 ? 4 : (PAIRS > 16 ? 8 : 16)));
+  constexpr int SPAN = BT / BPH0;
+  const int tid = threadIdx.x;
+  const int p = tid / BPH0, bp = tid % BPH0;
+  if (p >= PAIRS) return;
+  const int i = p / HID, o = p - i * HID;
+  float* dst = gw0 + ((size_t)o * IN + i) * nodes0;
+  int cur = -1;
+  float a[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) a[j] = 0.f;
+  const float4* rp = reinterpret_cast<const float4*>(rec0) + (size_t)i * BT + bp * SPAN;
+  const float* gp = G + (size_t)(bp * SPAN) * GP + o;
+#pragma unroll 4
+  for (int b = 0; b < SPAN; ++b) {
+    const float4 r = rp[b];
+    const float gv = gp[b * GP];
+    const int base = __float_as_int(r.x);
+    if (base != cur) {
+      if (cur >= 0) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          if (a[j] != 0.f) atomicAdd(dst + cur + j, a[j]);
+      }
+      cur = base;
+#pragma unroll
+      for (int j = 0; j < N; ++j) a[j] = 0.f;
+    }
+    const float l[3] = {r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[j] = fmaf(l[j], gv, a[j]);
+  }
+  if (cur >= 0) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (a[j] != 0.f) atomicAdd(dst + cur + j, a[j]);
+  }
+}
+
+template <class S, bool TRAIN>
+__global__ void __launch_bounds__(BT, 1) fused_mlp_kernel(const FusedParams p) {
+  constexpr int N = S::N, IN = S::IN, HID = S::HID, OUT = S::OUT, NH = S::NH;
+  constexpr int HP = S::HP, OP = S::OP, GP = S::GP;
+  constexpr bool POW2H = (S::SEGH & (S::SEGH - 1)) == 0, POW2O = (S::SEGO & (S::SEGO - 1)) == 0;
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;                                  // hidden layers then output layer
+  float* sA = sW + S::S_W;                           // [(NH+1)][HID][BT]   (TRAIN) / [HID][BT]
+  float* sG = sA + S::S_A;                           // [BT][GP]            (TRAIN)
+  float* sRec = sG + S::S_G;                         // [CI][BT][RECW]      (TRAIN)
+  float* sAcc = sRec + S::S_REC;                     // like sW             (TRAIN && ACC_SMEM)
+  const int tid = threadIdx.x;
+
+  // ---- stage weights of layers 1..NH+1 (contiguous in the packed buffer) -----------------
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.packed + p.off[1]);
+    float4* dst = reinterpret_cast<float4*>(sW);
+    for (int k = tid; k < S::S_W / 4; k += BT) dst[k] = __ldg(src + k);
+    if (TRAIN && S::ACC_SMEM)
+      for (int k = tid; k < S::S_W; k += BT) sAcc[k] = 0.f;
+  }
+  __syncthreads();
+
+  const SegConst sc0 = {p.seg0, S::STRIDE, (float)p.seg0, 1.f / (float)p.seg0};
+  const SegConst sch = {S::SEGH, S::STRIDE, (float)S::SEGH, 1.f / (float)S::SEGH};
+  const SegConst sco = {S::SEGO, S::STRIDE, (float)S::SEGO, 1.f / (float)S::SEGO};
+  const float* w0 = p.packed + p.off[0];
+  const LagrangeTable& lag = p.lag;
+  float loss_local = 0.f;
+
+  const long long tiles = (p.B + BT - 1) / BT;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long b = tile * BT + tid;
+    const bool live = b < p.B;
+    // ---- layer-0 inputs
+    float x0[IN];
+#pragma unroll
+    for (int i = 0; i < IN; ++i) x0[i] = 0.f;
+    if (live) {
+      if (p.x != nullptr) {
+#pragma unroll
+        for (int i = 0; i < IN; ++i) x0[i] = __ldg(p.x + b * IN + i);
+      } else {
+        hoir::mesh_position(p.mesh, p.mesh.first_pixel + b, x0, IN / 2);
+      }
+    }
+    // ---- forward
+    float h[HID];
+    float inv_d[NH + 1];
+    int kidx[NH + 1];
+    float4 rec0[IN];  // layer-0 (node window, basis) rows, consumed by its dL/dw pass
+    {
+#pragma unroll
+      for (int o = 0; o < HID; ++o) h[o] = 0.f;
+#pragma unroll
+      for (int i = 0; i < IN; ++i) {
+        int id;
+        float xi, l[N];
+        if (p.pow2_0) locate<true>(x0[i], sc0, id, xi);
+        else locate<false>(x0[i], sc0, id, xi);
+        hoir::lagrange<N>(lag.X, lag.D, xi, l);
+        const int base0 = id * S::STRIDE;
+        contract_fwd<N, HID, HP, true>(w0 + ((size_t)i * p.nodes0 + base0) * HP, l, h);
+        rec0[i] = make_float4(__int_as_float(base0), l[0], l[1], N > 2 ? l[2] : 0.f);
+      }
+    }
+    float* aT = sA + tid;
+#pragma unroll
+    for (int l = 0; l < NH; ++l) {
+      if (p.normalize) maxabs_fwd<HID>(h, p.norm_eps, inv_d[l], kidx[l]);
+      float* a = aT + (TRAIN ? (size_t)l * HID * BT : 0);
+#pragma unroll
+      for (int i = 0; i < HID; ++i) a[i * BT] = h[i];
+      layer_fwd<N, HID, HID, HP, S::NODES_H, POW2H>(a, sW + (size_t)l * S::WH, sch, lag, h);
+    }
+    if (p.normalize) maxabs_fwd<HID>(h, p.norm_eps, inv_d[NH], kidx[NH]);
+    float yo[OUT];
+    {
+      float* a = aT + (TRAIN ? (size_t)NH * HID * BT : 0);
+#pragma unroll
+      for (int i = 0; i < HID; ++i) a[i * BT] = h[i];
+      layer_fwd<N, HID, OUT, OP, S::NODES_O, POW2O>(a, sW + (size_t)NH * S::WH, sco, lag, yo);
+    }
+    if (!TRAIN) {
+      if (live) {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o)
+          p.y[b * OUT + o] = p.post_scale ? 0.5f * (yo[o] + 1.f) : yo[o];
+      }
+      continue;
+    }
+    // ---- loss and dL/dy
+    float g[HID];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) g[o] = 0.f;
+    if (live) {
+      if (p.gy_ext != nullptr) {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) g[o] = __ldg(p.gy_ext + b * OUT + o);
+      } else {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+          float t;
+          if (p.target_kind == HOIR_TARGET_U8_IMAGE) {
+            const unsigned char* img = static_cast<const unsigned char*>(p.target);
+            const float u = (float)img[(p.mesh.first_pixel + b) * OUT + o];
+            t = __fsub_rn(__fdiv_rn(__fmul_rn(u, 2.f), 255.f), 1.f);
+          } else {
+            t = __ldg(static_cast<const float*>(p.target) + b * OUT + o);
+          }
+          const float diff = yo[o] - t;
+          loss_local = fmaf(diff, diff, loss_local);
+          g[o] = 2.f * diff * p.loss_scale;
+        }
+      }
+    }
+    // ---- output layer backward
+    {
+      float* a = aT + (size_t)NH * HID * BT;
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) sG[tid * GP + o] = g[o];
+      __syncthreads();
+      layer_bwd_w<N, S::STRIDE, HID, OUT, OP, S::NODES_O, POW2O, S::ACC_SMEM>(
+          sA + (size_t)NH * HID * BT, sG, GP, sRec, sAcc + (size_t)NH * S::WH, p.gw[NH + 1], sco, lag);
+      float dot = layer_bwd_x<N, HID, OUT, OP, S::NODES_O, POW2O>(a, sW + (size_t)NH * S::WH, sco, lag, g);
+      // MaxAbs backward -> g[HID] = dL/d(hidden output NH-1 .. )
+      if (p.normalize) {
+        const int k = kidx[NH] & 0xffff;
+        const float sgn = (kidx[NH] & 0x10000) ? -1.f : ((kidx[NH] & 0x20000) ? 0.f : 1.f);
+#pragma unroll
+        for (int i = 0; i < HID; ++i) {
+          float gi = a[i * BT];
+          if (i == k) gi -= sgn * dot;
+          g[i] = gi * inv_d[NH];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < HID; ++i) g[i] = a[i * BT];
+      }
+      // ---- hidden layers, last to first
+#pragma unroll
+      for (int l = NH - 1; l >= 0; --l) {
+        float* al = aT + (size_t)l * HID * BT;
+#pragma unroll
+        for (int o = 0; o < HID; ++o) sG[tid * GP + o] = g[o];
+        __syncthreads();
+        layer_bwd_w<N, S::STRIDE, HID, HID, HP, S::NODES_H, POW2H, S::ACC_SMEM>(
+            sA + (size_t)l * HID * BT, sG, GP, sRec, sAcc + (size_t)l * S::WH, p.gw[l + 1], sch, lag);
+        dot = layer_bwd_x<N, HID, HID, HP, S::NODES_H, POW2H>(al, sW + (size_t)l * S::WH, sch, lag, g);
+        if (p.normalize) {
+          const int k = kidx[l] & 0xffff;
+          const float sgn = (kidx[l] & 0x10000) ? -1.f : ((kidx[l] & 0x20000) ? 0.f : 1.f);
+#pragma unroll
+          for (int i = 0; i < HID; ++i) {
+            float gi = al[i * BT];
+            if (i == k) gi -= sgn * dot;
+            g[i] = gi * inv_d[l];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < HID; ++i) g[i] = al[i * BT];
+        }
+      }
+      // ---- layer 0: dL/dw only
+#pragma unroll
+      for (int o = 0; o < HID; ++o) sG[tid * GP + o] = g[o];
+#pragma unroll
+      for (int i = 0; i < IN; ++i) reinterpret_cast<float4*>(sRec)[(size_t)i * BT + tid] = rec0[i];
+      __syncthreads();
+      layer0_bwd_w<N, IN, HID>(sRec, sG, GP, p.gw[0], p.nodes0);
+      __syncthreads();
+    }
+  }
+  if (!TRAIN) return;
+  // ---- flush: loss and the shared-memory dL/dw accumulators (boundary layout [out][in][nodes])
+  if (p.gy_ext == nullptr) {
+    float s = hoir::warp_sum(loss_local) * p.loss_scale;
+    if ((tid & 31) == 0 && s != 0.f) atomicAdd(p.loss_sum, s);
+  }
+  if (S::ACC_SMEM) {
+    __syncthreads();
+    for (int l = 0; l < NH; ++l) {
+      const float* acc = sAcc + (size_t)l * S::WH;
+      for (int k = tid; k < HID * S::NODES_H * HID; k += BT) {
+        const int o = k % HID, r = k / HID, q = r % S::NODES_H, i = r / S::NODES_H;
+        const float v = acc[((size_t)i * S::NODES_H + q) * HP + o];
+        if (v != 0.f) atomicAdd(p.gw[l + 1] + ((size_t)o * HID + i) * S::NODES_H + q, v);
+      }
+    }
+    const float* acc = sAcc + (size_t)NH * S::WH;
+    for (int k = tid; k < HID * S::NODES_O * OUT; k += BT) {
+      const int o = k % OUT, r = k / OUT, q = r % S::NODES_O, i = r / S::NODES_O;
+      const float v = acc[((size_t)i * S::NODES_O + q) * OP + o];
+      if (v != 0.f) atomicAdd(p.gw[NH + 1] + ((size_t)o * HID + i) * S::NODES_O + q, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const float* __restrict__ w, float* __restrict__ packed, int in_f,
+                            int out_f, int nodes, int out_pad) {
+  const long long total = (long long)in_f * nodes * out_pad;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total;
+       k += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(k % out_pad);
+    const long long r = k / out_pad;
+    const int q = (int)(r % nodes), i = (int)(r / nodes);
+    packed[k] = o < out_f ? w[((size_t)o * in_f + i) * nodes + q] : 0.f;
+  }
+}
+
+bool mlp_desc_ok(const hoir_mlp_desc* m) {
+  if (!m || m->num_layers < 2 || m->num_layers > HOIR_MAX_LAYERS) return false;
+  for (int l = 0; l < m->num_layers; ++l) {
+    if (hoir_layer_nodes(&m->layers[l]) < 1) return false;
+    if (m->layers[l].in_features < 1 || m->layers[l].out_features < 1) return false;
+    if (l > 0 && m->layers[l].in_features != m->layers[l - 1].out_features) return false;
+  }
+  return true;
+}
+
+struct FusedEntry {
+  int kind, n, in, hid, out, nh, segh, sego;
+  void (*fwd)(const FusedParams);
+  void (*train)(const FusedParams);
+  size_t smem_fwd, smem_train;
+};
+
+template <class S>
+constexpr FusedEntry make_entry() {
+  return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
+                    fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
+                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4};
+}
+
+// Instantiations: BASELINE.json configs C2/C3 (40-wide, 1 hidden layer, rotations 1 and 2) and
+// C1 (10-wide, 2 hidden layers), continuous and discontinuous, n = 3; plus n = 2 variants.
+const FusedEntry kEntries[] = {
+    make_entry<Shape<HOIR_CONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
+    make_entry<Shape<HOIR_DISCONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
+    make_entry<Shape<HOIR_CONTINUOUS, 3, 2, 40, 3, 1, 2, 2>>(),
+    make_entry<Shape<HOIR_CONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),
+    make_entry<Shape<HOIR_DISCONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),
+    make_entry<Shape<HOIR_CONTINUOUS, 2, 2, 10, 3, 2, 2, 2>>(),
+    make_entry<Shape<HOIR_DISCONTINUOUS, 2, 2, 10, 3, 2, 2, 2>>(),
+};
+
+const FusedEntry* find_entry(const hoir_mlp_desc* m) {
+  if (!mlp_desc_ok(m) || m->num_layers < 3) return nullptr;
+  const int L = m->num_layers;
+  const hoir_layer_desc& l0 = m->layers[0];
+  const hoir_layer_desc& lo = m->layers[L - 1];
+  for (int l = 0; l < L; ++l) {
+    const hoir_layer_desc& d = m->layers[l];
+    if (d.kind != l0.kind || d.n != l0.n || d.length != 2.f || d.periodicity > 0.f) return nullptr;
+    if (d.rescale != 0.f && d.rescale != 1.f) return nullptr;
+    if (l > 0 && l < L - 1 && (d.segments != m->layers[1].segments || d.out_features != l0.out_features))
+      return nullptr;
+  }
+  if (l0.kind != HOIR_CONTINUOUS && l0.kind != HOIR_DISCONTINUOUS) return nullptr;
+  for (const FusedEntry& e : kEntries)
+    if (e.kind == l0.kind && e.n == l0.n && e.in == l0.in_features && e.hid == l0.out_features &&
+        e.out == lo.out_features && e.nh == L - 2 && e.segh == m->layers[1].segments &&
+        e.sego == lo.segments)
+      return &e;
+  return nullptr;
+}
+
+int fill_params(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
+                const float* packed, FusedParams* p, const char* where) {
+  memset(p, 0, sizeof(*p));
+  if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", where);
+  if ((x == nullptr) == (mesh == nullptr) && B > 0)
+    return hoir_set_error(HOIR_EINVAL, "exactly one of x / mesh must be given", where);
+  if (!packed && B > 0) return hoir_set_error(HOIR_EINVAL, "null packed weights", where);
+  p->B = B;
+  p->x = x;
+  if (mesh) {
+    if (mesh->rotations * 2 != m->layers[0].in_features || mesh->rows < 1 || mesh->cols < 1 ||
+        mesh->normalize_mode < 0 || mesh->normalize_mode > 2 || mesh->first_pixel < 0 ||
+        mesh->first_pixel + B > (long long)mesh->rows * mesh->cols)
+      return hoir_set_error(HOIR_EINVAL, "mesh descriptor does not match the network / batch", where);
+    p->mesh = *mesh;
+  }
+  p->packed = packed;
+  for (int l = 0; l < m->num_layers; ++l) p->off[l] = hoir_mlp_packed_offset(m, l);
+  p->seg0 = m->layers[0].segments;
+  p->nodes0 = hoir_layer_nodes(&m->layers[0]);
+  p->pow2_0 = hoir::is_pow2(p->seg0);
+  p->normalize = m->normalize;
+  p->norm_eps = m->norm_eps;
+  hoir_make_lagrange_table(m->layers[0].n, 1.f, &p->lag);
+  return HOIR_OK;
+}
+
+int num_sms_fused() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace
+
+extern "C" int hoir_mlp_fused_supported(const hoir_mlp_desc* m) { return find_entry(m) != nullptr; }
+
+extern "C" long long hoir_mlp_packed_offset(const hoir_mlp_desc* m, int layer) {
+  if (!mlp_desc_ok(m) || layer < 0 || layer > m->num_layers) return -1;
+  long long off = 0;
+  for (int l = 0; l < layer; ++l) {
+    const hoir_layer_desc& d = m->layers[l];
+    off += (long long)d.in_features * hoir_layer_nodes(&d) * ((d.out_features + 3) & ~3);
+  }
+  return off;
+}
+
+extern "C" long long hoir_mlp_packed_size(const hoir_mlp_desc* m) {
+  if (!mlp_desc_ok(m)) return -1;
+  return hoir_mlp_packed_offset(m, m->num_layers);
+}
+
+extern "C" int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, float* packed,
+                             void* stream) {
+  if (!mlp_desc_ok(m)) return hoir_set_error(HOIR_EINVAL, "bad network descriptor", "hoir_mlp_pack");
+  if (!w || !packed) return hoir_set_error(HOIR_EINVAL, "null pointer", "hoir_mlp_pack");
+  for (int l = 0; l < m->num_layers; ++l) {
+    const hoir_layer_desc& d = m->layers[l];
+    if (!w[l]) return hoir_set_error(HOIR_EINVAL, "null weight pointer", "hoir_mlp_pack");
+    const int nodes = hoir_layer_nodes(&d), op = (d.out_features + 3) & ~3;
+    const long long total = (long long)d.in_features * nodes * op;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w[l], packed + hoir_mlp_packed_offset(m, l),
+                                                        d.in_features, d.out_features, nodes, op);
+  }
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float* x,
+                                const hoir_mesh_desc* mesh, const float* packed, float* y,
+                                int post_scale, void* stream) {
+  const FusedEntry* e = find_entry(m);
+  if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", "hoir_mlp_forward");
+  FusedParams p;
+  if (int err = fill_params(m, B, x, mesh, packed, &p, "hoir_mlp_forward")) return err;
+  if (B == 0) return HOIR_OK;
+  if (!y) return hoir_set_error(HOIR_EINVAL, "null output pointer", "hoir_mlp_forward");
+  p.y = y;
+  p.post_scale = post_scale;
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
+  const long long tiles = (B + BT - 1) / BT;
+  const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
+  e->fwd<<<grid, BT, e->smem_fwd, (cudaStream_t)stream>>>(p);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+extern "C" int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const float* x,
+                                   const hoir_mesh_desc* mesh, int target_kind, const void* target,
+                                   const float* gy_ext, const float* packed, float* const* gw,
+                                   float* loss_sum, float loss_scale, void* stream) {
+  const FusedEntry* e = find_entry(m);
+  if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", "hoir_mlp_train_step");
+  FusedParams p;
+  if (int err = fill_params(m, B, x, mesh, packed, &p, "hoir_mlp_train_step")) return err;
+  if (B == 0) return HOIR_OK;
+  if (!gw) return hoir_set_error(HOIR_EINVAL, "null gradient pointer table", "hoir_mlp_train_step");
+  for (int l = 0; l < m->num_layers; ++l) {
+    if (!gw[l]) return hoir_set_error(HOIR_EINVAL, "null gradient pointer", "hoir_mlp_train_step");
+    p.gw[l] = gw[l];
+  }
+  if (gy_ext == nullptr) {
+    if (!target || !loss_sum) return hoir_set_error(HOIR_EINVAL, "target / loss_sum required", "hoir_mlp_train_step");
+    if (target_kind != HOIR_TARGET_F32 && target_kind != HOIR_TARGET_U8_IMAGE)
+      return hoir_set_error(HOIR_EINVAL, "unknown target kind", "hoir_mlp_train_step");
+    if (target_kind == HOIR_TARGET_U8_IMAGE && (mesh == nullptr || m->layers[m->num_layers - 1].out_features != 3))
+      return hoir_set_error(HOIR_EINVAL, "uint8 image targets need a mesh and 3 outputs", "hoir_mlp_train_step");
+  }
+  p.target_kind = target_kind;
+  p.target = target;
+  p.gy_ext = gy_ext;
+  p.loss_sum = loss_sum;
+  p.loss_scale = loss_scale;
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_train));
+  const long long tiles = (B + BT - 1) / BT;
+  const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
+  e->train<<<grid, BT, e->smem_train, (cudaStream_t)stream>>>(p);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}

@@ -1,0 +1,173 @@
+// hoir_common.cu -- error state, basis tables, optimizers and the FFMA peak micro-kernel.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include "hoir_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+int hoir_set_error(int code, const char* msg, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where ? where : "hoir", msg ? msg : "error");
+  return code;
+}
+
+extern "C" const char* hoir_last_error(void) { return g_err; }
+extern "C" int hoir_version(void) { return HOIR_VERSION; }
+
+// Chebyshev-Lobatto nodes the way the package builds them: -cos(k*pi/(n-1))
+// evaluated in fp32, |X| < 1e-15 snapped to 0.  D_j = 1 / prod_{m != j} (X_j - X_m).
+void hoir_make_lagrange_table(int n, float half_length, LagrangeTable* t) {
+  memset(t, 0, sizeof(*t));
+  if (n < 1 || n > HOIR_MAX_N) return;
+  if (n == 1) {
+    t->X[0] = 0.f;
+    t->D[0] = 1.f;
+    return;
+  }
+  for (int k = 0; k < n; ++k) {
+    float arg = (float)((double)k * M_PI / (double)(n - 1));
+    float x = -cosf(arg);
+    if (fabsf(x) < 1e-15f) x = 0.f;
+    t->X[k] = half_length * x;
+  }
+  for (int j = 0; j < n; ++j) {
+    double d = 1.0;
+    for (int m = 0; m < n; ++m)
+      if (m != j) d *= (double)t->X[j] - (double)t->X[m];
+    t->D[j] = (float)(1.0 / d);
+  }
+}
+
+void hoir_make_fourier_table(int n, float arg_scale, FourierTable* t) {
+  memset(t, 0, sizeof(*t));
+  for (int j = 1; j < n && j < HOIR_MAX_N; ++j)
+    t->c[j] = (float)((double)arg_scale * M_PI * (double)((j + 1) / 2));
+}
+
+// ------------------------------------------------------------------------------------------
+// Optimizers on flat fp32 vectors.
+// torch.optim.Adam defaults as used at /root/reference/high_order_implicit_representation/
+// networks.py:94-97 (no amsgrad, L2 weight decay added to the gradient).
+// ------------------------------------------------------------------------------------------
+__global__ void adam_kernel(long long n, float* __restrict__ w, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v, float lr, float b1,
+                            float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x) {
+    float gk = g[k];
+    float wk = w[k];
+    if (wd != 0.f) gk = fmaf(wd, wk, gk);
+    float mk = m[k] + (1.f - b1) * (gk - m[k]);          // lerp, as torch does
+    float vk = b2 * v[k] + (1.f - b2) * gk * gk;
+    m[k] = mk;
+    v[k] = vk;
+    float denom = sqrtf(vk) / bc2_sqrt + eps;
+    w[k] = wk - (lr / bc1) * (mk / denom);
+  }
+}
+
+// SparseLion: Lion restricted to entries whose gradient is non-zero.
+__global__ void sparse_lion_kernel(long long n, float* __restrict__ w, const float* __restrict__ g,
+                                   float* __restrict__ ea, float lr, float b1, float b2, float wd) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x) {
+    float gk = g[k];
+    if (gk != 0.f) {
+      float e = ea[k];
+      float wk = w[k] * (1.f - lr * wd);
+      float u = e * b1 + gk * (1.f - b1);
+      float s = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+      w[k] = wk - lr * s;
+      ea[k] = e * b2 + gk * (1.f - b2);
+    }
+  }
+}
+
+static int flat_grid(long long n) {
+  long long g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  return (int)g;
+}
+
+extern "C" int hoir_adam_step(long long n, float* w, const float* g, float* exp_avg,
+                              float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, long long step, void* stream) {
+  if (n < 0 || step < 1) return hoir_set_error(HOIR_EINVAL, "bad n/step", "hoir_adam_step");
+  if (n == 0) return HOIR_OK;
+  if (!w || !g || !exp_avg || !exp_avg_sq)
+    return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_adam_step");
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(
+      n, w, g, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+      (float)sqrt(bc2));
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+extern "C" int hoir_sparse_lion_step(long long n, float* w, const float* g, float* exp_avg,
+                                     float lr, float beta1, float beta2, float weight_decay,
+                                     void* stream) {
+  if (n < 0) return hoir_set_error(HOIR_EINVAL, "bad n", "hoir_sparse_lion_step");
+  if (n == 0) return HOIR_OK;
+  if (!w || !g || !exp_avg)
+    return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_sparse_lion_step");
+  sparse_lion_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, w, g, exp_avg, lr, beta1,
+                                                                     beta2, weight_decay);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FFMA-only micro-kernel: the measured FP32 roofline denominator.  16 independent
+// register-register FFMA chains per thread, 1024 threads per SM-resident CTA pair.
+// ------------------------------------------------------------------------------------------
+template <bool REG_FORM>
+__global__ void __launch_bounds__(512, 2)
+ffma_peak_kernel(int iters, float a, float b, float* __restrict__ sink) {
+  if (REG_FORM) {  // force a, b into registers: FFMA R, R, R, R (what a weight-from-LDS kernel issues)
+    a += 1e-9f * (float)threadIdx.x;
+    b += 1e-9f * (float)threadIdx.x;
+  }
+  float r[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) r[k] = (float)(threadIdx.x + k);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) r[k] = fmaf(r[k], a, b);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += r[k];
+  if (s == 123.456f) sink[0] = s;
+}
+
+extern "C" int hoir_ffma_peak(int iters, int reg_form, float* ms, double* flops, void* stream) {
+  if (iters < 1 || !ms || !flops) return hoir_set_error(HOIR_EINVAL, "bad arguments", "hoir_ffma_peak");
+  int dev = 0, sms = 0;
+  HOIR_CHECK_CUDA(cudaGetDevice(&dev));
+  HOIR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  float* sink = nullptr;
+  HOIR_CHECK_CUDA(cudaMalloc(&sink, sizeof(float)));
+  cudaEvent_t e0, e1;
+  HOIR_CHECK_CUDA(cudaEventCreate(&e0));
+  HOIR_CHECK_CUDA(cudaEventCreate(&e1));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = sms * 2 * 4;
+  auto kern = reg_form ? ffma_peak_kernel<true> : ffma_peak_kernel<false>;
+  kern<<<grid, 512, 0, s>>>(iters / 8 + 1, 1.0001f, 0.5f, sink);  // warm-up
+  HOIR_CHECK_CUDA(cudaEventRecord(e0, s));
+  kern<<<grid, 512, 0, s>>>(iters, 1.0001f, 0.5f, sink);
+  HOIR_CHECK_CUDA(cudaEventRecord(e1, s));
+  HOIR_CHECK_CUDA(cudaEventSynchronize(e1));
+  HOIR_CHECK_CUDA(cudaEventElapsedTime(ms, e0, e1));
+  *flops = 2.0 * 16.0 * 8.0 * (double)iters * 512.0 * (double)grid;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}

@@ -1,0 +1,202 @@
+"""Fused training / rendering engine over the whole-network sm_100a kernels.
+
+This is the fast path behind ``Net``: all ``w`` tensors of a ``HighOrderMLP`` become views into
+ONE flat fp32 parameter vector (boundary layout ``[out][in][nodes]`` per layer, so
+``state_dict`` is unchanged), gradients and the scalar loss live in one flat vector that is
+zeroed with a single memset, reduced across ranks with a single NCCL all-reduce (data-parallel
+over disjoint pixel tiles) and consumed by a single fused Adam / SparseLion
+launch.  One training step of ``Net.eval_step`` + ``backward`` + ``optimizer.step``
+(/root/reference/high_order_implicit_representation/networks.py:64-70, 93-102) is
+``memset, pack, hoir_mlp_train_step, [all_reduce], optimizer`` -- no PyTorch autograd, no
+per-layer tensors in HBM.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _lib
+from .networks import HighOrderMLP
+
+
+class FusedTrainer:
+    def __init__(self, mlp: HighOrderMLP, optimizer: str = "adam", lr: float = 1e-4,
+                 betas: Optional[tuple] = None, eps: float = 1e-8, weight_decay: float = 0.0,
+                 process_group=None):
+        self.lib = _lib.lib()
+        self.mlp = mlp
+        self.layers = mlp.high_order_layers()
+        self.desc = mlp.mlp_desc()
+        if self.desc is None or not self.lib.hoir_mlp_fused_supported(self.desc):
+            raise _lib.HoirUnsupported("no fused instantiation for this network; train it through "
+                                       "the per-layer autograd path (Net.training_step)")
+        if optimizer not in ("adam", "sparse_lion"):
+            raise ValueError(f"Optimizer {optimizer} not recognized")
+        dev = self.layers[0].w.device
+        if dev.type != "cuda":
+            raise RuntimeError("hoir_b200 has no CPU path: move the network to a CUDA device first")
+        self.device = dev
+        self.optimizer = optimizer
+        self.lr = float(lr)
+        self.betas = tuple(betas) if betas is not None else ((0.9, 0.999) if optimizer == "adam" else (0.9, 0.99))
+        self.eps = float(eps)
+        self.weight_decay = float(weight_decay)
+        self.step_count = 0
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.out_features = self.layers[-1].out_features
+        self.in_features = self.layers[0].in_features
+        sizes = [l.w.numel() for l in self.layers]
+        self.n_params = sum(sizes)
+        self.flat_w = torch.empty(self.n_params, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(self.n_params + 1, device=dev, dtype=torch.float32)  # [-1] = loss
+        self.w_views, self.g_views = [], []
+        off = 0
+        with torch.no_grad():
+            for l, sz in zip(self.layers, sizes):
+                view = self.flat_w[off:off + sz].view_as(l.w)
+                view.copy_(l.w)
+                l.w.data = view                       # state_dict / checkpoints keep working
+                self.w_views.append(view)
+                self.g_views.append(self.flat_g[off:off + sz].view_as(l.w))
+                off += sz
+        self.exp_avg = torch.zeros(self.n_params, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(self.n_params, device=dev, dtype=torch.float32) if optimizer == "adam" else None
+        self.packed = torch.empty(self.lib.hoir_mlp_packed_size(self.desc), device=dev, dtype=torch.float32)
+        self._w_table = _lib.ptr_table(self.w_views)
+        self._g_table = _lib.ptr_table(self.g_views)
+        self._loss_ptr = _lib.C.c_void_p(self.flat_g.data_ptr() + 4 * self.n_params)
+        self._packed_fresh = False
+        #: kernels launched by the last train step (memset excluded)
+        self.launches_per_step = len(self.layers) + 2
+        #: set to a list to collect (start, end) CUDA events around the fused training kernel
+        self.kernel_events = None
+
+    # ------------------------------------------------------------------------------------------
+    def pack(self) -> None:
+        _lib.check(self.lib.hoir_mlp_pack(self.desc, self._w_table, _lib.dptr(self.packed),
+                                          _lib.stream_ptr(self.device)))
+        self._packed_fresh = True
+
+    def _train_kernel(self, *args) -> None:
+        if self.kernel_events is None:
+            _lib.check(self.lib.hoir_mlp_train_step(*args))
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(self.lib.hoir_mlp_train_step(*args))
+        e1.record()
+        self.kernel_events.append((e0, e1))
+
+    def _loss_scale(self, B: int, global_batch: Optional[int]) -> float:
+        gb = global_batch if global_batch is not None else B * self.world
+        return 1.0 / (gb * self.out_features) if gb > 0 else 0.0
+
+    def _finish(self) -> Tensor:
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        self.step_count += 1
+        st = _lib.stream_ptr(self.device)
+        if self.optimizer == "adam":
+            _lib.check(self.lib.hoir_adam_step(
+                self.n_params, _lib.dptr(self.flat_w), _lib.dptr(self.flat_g), _lib.dptr(self.exp_avg),
+                _lib.dptr(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, self.step_count, st))
+        else:
+            _lib.check(self.lib.hoir_sparse_lion_step(
+                self.n_params, _lib.dptr(self.flat_w), _lib.dptr(self.flat_g), _lib.dptr(self.exp_avg),
+                self.lr, self.betas[0], self.betas[1], self.weight_decay, st))
+        self._packed_fresh = False
+        return self.flat_g[self.n_params:]  # 1-element view: MSE(mean) of this step (all ranks)
+
+    def train_step(self, x: Tensor, y: Tensor, global_batch: Optional[int] = None) -> Tensor:
+        """One optimisation step on explicit samples x[B, in], y[B, out] (the reference's batch).
+        Returns a 1-element device tensor holding the loss; valid until the next step."""
+        x2 = x.reshape(x.shape[0], -1)
+        y2 = y.reshape(y.shape[0], -1)
+        if x2.shape[1] != self.in_features or y2.shape[1] != self.out_features:
+            raise ValueError(f"expected x[B,{self.in_features}] / y[B,{self.out_features}], got "
+                             f"{tuple(x.shape)} / {tuple(y.shape)}")
+        B = x2.shape[0]
+        with torch.cuda.device(self.device):
+            self.flat_g.zero_()
+            self.pack()
+            self._train_kernel(
+                self.desc, B, _lib.dptr(x2), None, _lib.TARGET_F32, _lib.dptr(y2), None,
+                _lib.dptr(self.packed), self._g_table, self._loss_ptr,
+                self._loss_scale(B, global_batch), _lib.stream_ptr(self.device))
+            return self._finish()
+
+    def train_step_mesh(self, image_u8: Tensor, rotations: int, first_pixel: int, B: int,
+                        global_batch: Optional[int] = None) -> Tensor:
+        """One optimisation step on pixels first_pixel .. first_pixel+B-1 (row-major) of a uint8
+        image [rows, cols, 3] resident in HBM: coordinates (positions_from_mesh) and targets
+        (u*2/255-1) are produced in-kernel -- image_to_dataset of the reference,
+        /root/reference/high_order_implicit_representation/single_image_dataset.py:22-51."""
+        if image_u8.dtype != torch.uint8 or image_u8.dim() != 3 or image_u8.shape[2] != 3:
+            raise ValueError("expected a uint8 image [rows, cols, 3]")
+        mesh = _lib.make_mesh_desc(image_u8.shape[0], image_u8.shape[1], rotations, True, first_pixel)
+        with torch.cuda.device(self.device):
+            self.flat_g.zero_()
+            self.pack()
+            self._train_kernel(
+                self.desc, B, None, mesh, _lib.TARGET_U8_IMAGE, _lib.dptr(image_u8, torch.uint8), None,
+                _lib.dptr(self.packed), self._g_table, self._loss_ptr,
+                self._loss_scale(B, global_batch), _lib.stream_ptr(self.device))
+            return self._finish()
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x: Tensor) -> Tensor:
+        x2 = x.reshape(x.shape[0], -1).contiguous()
+        y = torch.empty((x2.shape[0], self.out_features), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            if not self._packed_fresh:
+                self.pack()
+            _lib.check(self.lib.hoir_mlp_forward(self.desc, x2.shape[0], _lib.dptr(x2), None,
+                                                 _lib.dptr(self.packed), _lib.dptr(y), 0,
+                                                 _lib.stream_ptr(self.device)))
+        return y
+
+    def render(self, rows: int, cols: int, rotations: int, first_pixel: int = 0,
+               count: Optional[int] = None, out: Optional[Tensor] = None,
+               post_scale: bool = True) -> Tensor:
+        """Forward over pixels first_pixel .. first_pixel+count-1 of a rows x cols mesh; with
+        post_scale the 0.5*(y+1) of /root/reference/.../rendering.py:213 is applied in-kernel.
+        Tile-sharded rendering = each rank calls this with its own pixel range (no collective)."""
+        count = rows * cols - first_pixel if count is None else count
+        if out is None:
+            out = torch.empty((count, self.out_features), device=self.device, dtype=torch.float32)
+        mesh = _lib.make_mesh_desc(rows, cols, rotations, True, first_pixel)
+        with torch.cuda.device(self.device):
+            if not self._packed_fresh:
+                self.pack()
+            _lib.check(self.lib.hoir_mlp_forward(self.desc, count, None, mesh, _lib.dptr(self.packed),
+                                                 _lib.dptr(out), 1 if post_scale else 0,
+                                                 _lib.stream_ptr(self.device)))
+        return out
+
+
+class HostBatchStepper:
+    """End-to-end step through host memory: pinned host (x, y) -> H2D -> fused step -> loss D2H.
+    This is the reference-facing shape of a training step (a DataLoader batch arriving from host
+    memory, /root/reference/high_order_implicit_representation/single_image_dataset.py:312-320)."""
+
+    def __init__(self, trainer: FusedTrainer, batch: int):
+        self.trainer = trainer
+        dev = trainer.device
+        self.x_dev = torch.empty((batch, trainer.in_features), device=dev, dtype=torch.float32)
+        self.y_dev = torch.empty((batch, trainer.out_features), device=dev, dtype=torch.float32)
+        self.loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = self.x_dev.numel() * 4 + self.y_dev.numel() * 4
+        self.d2h_bytes = 4
+
+    def step(self, x_host: Tensor, y_host: Tensor) -> float:
+        self.x_dev.copy_(x_host, non_blocking=True)
+        self.y_dev.copy_(y_host, non_blocking=True)
+        loss = self.trainer.train_step(self.x_dev, self.y_dev)
+        self.loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream(self.trainer.device).synchronize()
+        return float(self.loss_host[0])

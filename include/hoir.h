@@ -148,9 +148,11 @@ int hoir_adam_step(long long n, float* w, const float* g, float* exp_avg, float*
 int hoir_sparse_lion_step(long long n, float* w, const float* g, float* exp_avg, float lr,
                           float beta1, float beta2, float weight_decay, void* stream);
 
-/* FFMA-only micro-kernel: runs `iters` dependent-free FFMA rounds on every SM and returns the
- * elapsed milliseconds in *ms (the measured FP32 roofline denominator of bench.py). */
-int hoir_ffma_peak(int iters, float* ms, double* flops, void* stream);
+/* FFMA-only micro-kernel: runs `iters` rounds of 128 independent FFMAs per thread on every SM and
+ * returns the elapsed milliseconds in *ms and the FLOPs executed in *flops (the measured FP32
+ * roofline denominator of bench.py).  reg_form 1: FFMA with three register sources (what a
+ * kernel whose weights come from shared memory issues); 0: constant-bank multiplier/addend. */
+int hoir_ffma_peak(int iters, int reg_form, float* ms, double* flops, void* stream);
 
 #ifdef __cplusplus
 }

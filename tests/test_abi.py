@@ -1,0 +1,99 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/hoir.h declares,
+and its argument validation / error mapping works without touching a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import hoir_b200 as H
+from hoir_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hoir.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hoir_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), f"libhoir_b200.so does not export {name}"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS)
+    assert lib.hoir_version() == 100
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.LayerDesc) == 40
+    assert C.sizeof(_lib.MlpDesc) == 4 + 8 * 40 + 8
+    assert C.sizeof(_lib.MeshDesc) == 16 + 8 + 3 * 8 * 4
+
+
+@pytest.mark.parametrize("kind,n,seg,nodes", [("continuous", 3, 100, 201), ("discontinuous", 3, 100, 300),
+                                              ("polynomial", 5, 7, 5), ("fourier", 31, 1, 31),
+                                              ("continuous", 2, 50, 51)])
+def test_layer_nodes(kind, n, seg, nodes):
+    d = _lib.make_layer_desc(kind, n, seg, 4, 40)
+    assert _lib.lib().hoir_layer_nodes(d) == nodes
+
+
+def test_packed_layout_sizes_c2():
+    net = H.HighOrderMLP(layer_type="continuous", n=3, in_width=4, out_width=3, hidden_layers=1,
+                         hidden_width=40, in_segments=100, out_segments=2, hidden_segments=2,
+                         normalization=H.MaxAbsNormalization)
+    assert sum(p.numel() for p in net.parameters()) == 40760          # README.md:35
+    desc = net.mlp_desc()
+    lib = _lib.lib()
+    assert lib.hoir_mlp_packed_offset(desc, 0) == 0
+    assert lib.hoir_mlp_packed_offset(desc, 1) == 4 * 201 * 40
+    assert lib.hoir_mlp_packed_offset(desc, 2) == 4 * 201 * 40 + 40 * 5 * 40
+    assert lib.hoir_mlp_packed_size(desc) == 4 * 201 * 40 + 40 * 5 * 40 + 40 * 5 * 4
+    assert lib.hoir_mlp_fused_supported(desc) == 1
+
+
+def test_fused_supported_matrix():
+    def sup(**kw):
+        base = dict(layer_type="continuous", n=3, in_width=4, out_width=3, hidden_layers=1, hidden_width=40,
+                    in_segments=100, out_segments=2, hidden_segments=2, normalization=H.MaxAbsNormalization)
+        base.update(kw)
+        return H.HighOrderMLP(**base).fused_supported()
+    assert sup()
+    assert sup(layer_type="discontinuous")
+    assert sup(in_width=2, hidden_width=10, hidden_layers=2)
+    assert sup(in_segments=37)                      # layer-0 segments are a runtime value
+    assert not sup(layer_type="fourier")
+    assert not sup(hidden_width=41)
+    assert not sup(hidden_segments=3)
+    assert not sup(periodicity=2.0)
+
+
+def test_errors_map_to_python_exceptions():
+    lib = _lib.lib()
+    bad = _lib.LayerDesc(7, 3, 2, 4, 4, 2.0, 1.0, 0.0, 2.0, 1)
+    with pytest.raises(ValueError):
+        _lib.check(lib.hoir_layer_forward(bad, 0, None, None, None, None))
+    ok = _lib.make_layer_desc("continuous", 3, 2, 4, 4)
+    with pytest.raises(ValueError):
+        _lib.check(lib.hoir_layer_forward(ok, -1, None, None, None, None))
+    # B == 0 is legal and touches no pointer (the reference's render loops feed an empty batch)
+    _lib.check(lib.hoir_layer_forward(ok, 0, None, None, None, None))
+    _lib.check(lib.hoir_layer_backward(ok, 0, None, None, None, None, None, None))
+    _lib.check(lib.hoir_maxabs_forward(0, 4, 1e-6, None, None, None))
+    with pytest.raises(ValueError, match="not recognized"):
+        H.high_order_fc_layers("no_such_layer", n=3, in_features=2, out_features=2)
+    fourier = H.HighOrderMLP(layer_type="fourier", n=3, in_width=4, out_width=3, hidden_layers=1,
+                             hidden_width=40, normalization=H.MaxAbsNormalization)
+    with pytest.raises(H.HoirUnsupported):
+        _lib.check(lib.hoir_mlp_forward(fourier.mlp_desc(), 0, None, None, None, None, 0, None))
+
+
+def test_no_cpu_fallback():
+    import torch
+    layer = H.high_order_fc_layers("continuous", n=3, in_features=2, out_features=2, segments=4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer(torch.zeros(3, 2))

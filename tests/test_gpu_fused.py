@@ -1,0 +1,187 @@
+"""GPU parity of the fused whole-network kernels and of the training engine against the CPU
+oracle (copied weights, same seeded inputs): forward, dL/dw through autograd and through the
+fused MSE step, optimizers, rendering, the Net drop-in and its checkpoints."""
+import math
+
+import pytest
+import torch
+
+import hoir_b200 as H
+from oracle import hol_oracle as O
+from helpers import MLP_KW, make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FUSED = ["C1", "C1d", "C1n2", "C2", "C2r1", "C3d"]
+UNFUSED = ["C3f", "C4s", "poly"]
+
+
+def batch(name, B, seed=0):
+    kw = MLP_KW[name]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, kw["in_width"], generator=g) * 2.2 - 1.1
+    y = torch.rand(B, kw["out_width"], generator=g) * 2 - 1
+    return x, y
+
+
+@pytest.mark.parametrize("name", FUSED + UNFUSED)
+@pytest.mark.parametrize("B", [1, 255, 1000])
+def test_mlp_forward_backward_parity(name, B):
+    ref, net = make_pair(name)
+    assert net.fused_supported() == (name in FUSED)
+    x, y = batch(name, B)
+    loss_ref = O.mse_training_step(ref, x, y)
+    loss_ref.backward()
+    y_hat = net(x.cuda())
+    loss = torch.nn.functional.mse_loss(y_hat.flatten(), y.cuda().flatten())
+    loss.backward()
+    tol = 1e-4 if name == "C3f" else 1e-5
+    assert rel_err(y_hat, ref(x)) <= tol
+    assert abs(loss.item() - loss_ref.item()) <= tol * abs(loss_ref.item())
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad, q.grad) <= 2 * tol, k
+
+
+@pytest.mark.parametrize("name", FUSED)
+def test_fused_matches_per_layer_kernels(name):
+    _, net = make_pair(name)
+    x, _ = batch(name, 777, seed=5)
+    y_fused = net(x.cuda())
+    net.use_fused = False
+    y_layers = net(x.cuda())
+    assert rel_err(y_fused, y_layers) <= 2e-6
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3d"])
+@pytest.mark.parametrize("opt", ["adam", "sparse_lion"])
+def test_trainer_steps_match_oracle_training(name, opt):
+    ref, net = make_pair(name)
+    tr = H.FusedTrainer(net, optimizer=opt, lr=1e-3)
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-3) if opt == "adam" else O.SparseLion(ref.parameters(), lr=1e-3)
+    for step in range(3):
+        x, y = batch(name, 600, seed=step)
+        ref_opt.zero_grad()
+        loss_ref = O.mse_training_step(ref, x, y)
+        loss_ref.backward()
+        ref_opt.step()
+        loss = tr.train_step(x.cuda(), y.cuda())
+        assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+        if step == 0:
+            for gv, q in zip(tr.g_views, ref.parameters()):
+                assert rel_err(gv, q.grad) <= 2e-5
+    # sign-based Lion updates can flip on round-off-sized momenta: compare in absolute lr units
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        if opt == "adam":
+            assert (p.detach().cpu() - q.detach()).abs().max().item() <= 2e-5, k
+        else:
+            frac_off = ((p.detach().cpu() - q.detach()).abs() > 1e-6).float().mean().item()
+            assert frac_off <= 1e-3, k
+    # state_dict still reads the live (flat-buffer) weights
+    sd = net.state_dict()
+    assert rel_err(sd["model.0.w"], ref.state_dict()["model.0.w"]) <= 1e-4
+
+
+@pytest.mark.parametrize("rows,cols,rot,name", [(37, 53, 2, "C2"), (64, 48, 1, "C1"), (40, 40, 2, "C3d")])
+def test_mesh_mode_training_and_render(rows, cols, rot, name):
+    ref, net = make_pair(name)
+    g = torch.Generator().manual_seed(11)
+    img = torch.randint(0, 256, (rows, cols, 3), generator=g, dtype=torch.uint8)
+    y_flat, x_flat, _ = O.image_to_dataset(img, rotations=rot)
+    tr = H.FusedTrainer(net, optimizer="adam", lr=0.0)      # lr 0: weights stay put, grads visible
+    first, count = 5, rows * cols - 9
+    loss_ref = O.mse_training_step(ref, x_flat[first:first + count], y_flat[first:first + count])
+    loss_ref.backward()
+    loss = tr.train_step_mesh(img.cuda(), rot, first, count)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    for gv, q in zip(tr.g_views, ref.parameters()):
+        assert rel_err(gv, q.grad) <= 2e-5
+    # rendering.py:195-213 -- including the empty trailing batch when N % bs == 0
+    want = O.render_image(ref, x_flat, (rows, cols, 3), batch_size=rows)
+    got = tr.render(rows, cols, rot).reshape(rows, cols, 3)
+    assert rel_err(got, want) <= 1e-5
+    part = tr.render(rows, cols, rot, first_pixel=first, count=count, post_scale=False)
+    assert rel_err(part, ref(x_flat[first:first + count])) <= 1e-5
+
+
+def test_fused_empty_and_edge_batches():
+    ref, net = make_pair("C2")
+    assert net(torch.empty(0, 4, device="cuda")).shape == (0, 3)
+    tr = H.FusedTrainer(net, lr=0.0)
+    assert tr.render(8, 8, 2, first_pixel=64, count=0).shape == (0, 3)
+    for B in (1, 256, 257, 148 * 256 + 3):
+        x, _ = batch("C2", B, seed=B)
+        assert rel_err(tr.forward(x.cuda()), ref(x)) <= 1e-5
+
+
+def test_large_batch_linearity_of_gradients():
+    """Full-size property check (2^20 samples, too big for the oracle): dL/dw over the batch equals
+    the sum over its halves, and the loss is the mean of the halves' losses."""
+    _, net = make_pair("C2")
+    tr = H.FusedTrainer(net, lr=0.0)
+    B = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand(B, 4, device="cuda", generator=g) * 2 - 1
+    y = torch.rand(B, 3, device="cuda", generator=g) * 2 - 1
+    loss = tr.train_step(x, y).clone()
+    gw = tr.flat_g[:-1].clone()
+    l0 = tr.train_step(x[: B // 2], y[: B // 2], global_batch=B).clone()
+    g0 = tr.flat_g[:-1].clone()
+    l1 = tr.train_step(x[B // 2:], y[B // 2:], global_batch=B).clone()
+    g1 = tr.flat_g[:-1].clone()
+    assert abs((l0 + l1).item() - loss.item()) <= 1e-5 * loss.item()
+    assert rel_err(g0 + g1, gw) <= 1e-4          # fp32 atomics: summation order differs
+
+
+def test_optimizer_kernels_match_torch():
+    torch.manual_seed(0)
+    w0 = torch.randn(1000)
+    grads = [torch.randn(1000) * (torch.rand(1000) > 0.3) for _ in range(4)]
+    for name in ("adam", "sparse_lion"):
+        pr = torch.nn.Parameter(w0.clone())
+        pc = torch.nn.Parameter(w0.clone().cuda())
+        o_ref = torch.optim.Adam([pr], lr=1e-2) if name == "adam" else O.SparseLion([pr], lr=1e-2)
+        o_gpu = H.Adam([pc], lr=1e-2) if name == "adam" else H.SparseLion([pc], lr=1e-2)
+        for g in grads:
+            pr.grad = g.clone()
+            pc.grad = g.clone().cuda()
+            o_ref.step()
+            o_gpu.step()
+        assert (pc.detach().cpu() - pr.detach()).abs().max().item() <= 1e-5, name
+
+
+def test_net_drop_in_and_checkpoint(tmp_path):
+    cfg = H.images_config(mlp=dict(layer_type="continuous", n=3, n_in=None, n_out=None,
+                                   input=dict(segments=100, width=4), output=dict(segments=2, width=3),
+                                   hidden=dict(segments=2, layers=1, width=40)),
+                          optimizer=dict(name="adam", lr=1e-3, scheduler="plateau", patience=10, factor=0.1))
+    net = H.Net(cfg).cuda()
+    assert list(net.state_dict().keys()) == ["model.model.0.w", "model.model.2.w", "model.model.4.w"]
+    assert sum(p.numel() for p in net.parameters()) == 40760
+    (opt,), (sched,) = net.configure_optimizers()
+    x, y = batch("C2", 256)
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        loss = net.training_step((x.cuda(), y.cuda()), 0)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    assert "train_loss" in net.logged and sched["monitor"] == "train_loss"
+    path = str(tmp_path / "epoch=0-step=5.ckpt")
+    net.save_checkpoint(path)
+    ckpt = torch.load(path, weights_only=False)
+    assert set(ckpt) >= {"state_dict", "hyper_parameters", "epoch", "global_step"}
+    net2 = H.Net.load_from_checkpoint(path).cuda()
+    assert torch.equal(net2(x.cuda()), net(x.cuda()))
+    with pytest.raises(ValueError, match="not recognized"):
+        H.Net(H.images_config(mlp=cfg.mlp, optimizer=dict(name="sgd", lr=1.0))).configure_optimizers()
+
+
+def test_ffma_peak_microbenchmark_runs():
+    import ctypes as C
+    ms, fl = C.c_float(), C.c_double()
+    for form in (0, 1):
+        H._lib.check(H._lib.lib().hoir_ffma_peak(2000, form, C.byref(ms), C.byref(fl), None))
+        tflops = fl.value / (ms.value * 1e-3) / 1e12
+        assert 5.0 < tflops < 120.0

@@ -1,0 +1,137 @@
+"""GPU parity of the single-layer kernels (through the C ABI) against the CPU oracle on the same
+seeded inputs and copied weights.  Bars (BASELINE.json): segment indices / node windows
+bit-exact; outputs and gradients <= 1e-5 relative (max|delta| / max|ref|); Fourier <= 1e-4."""
+import pytest
+import torch
+
+import hoir_b200 as H
+from oracle import hol_oracle as O
+from helpers import adversarial_inputs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"continuous": 1e-5, "discontinuous": 1e-5, "polynomial": 1e-5, "fourier": 1e-4}
+
+LAYER_CASES = [
+    # kind, n, in, out, segments
+    ("continuous", 3, 4, 40, 100), ("continuous", 3, 40, 40, 2), ("continuous", 3, 40, 3, 2),
+    ("continuous", 2, 216, 50, 50), ("continuous", 2, 50, 27, 2), ("continuous", 5, 7, 9, 13),
+    ("discontinuous", 3, 4, 40, 100), ("discontinuous", 3, 40, 40, 2), ("discontinuous", 2, 2, 10, 100),
+    ("discontinuous", 1, 3, 5, 8),
+    ("polynomial", 3, 4, 10, 1), ("polynomial", 6, 10, 10, 1), ("polynomial", 2, 384, 16, 1),
+    ("fourier", 31, 4, 40, 1), ("fourier", 31, 40, 40, 1), ("fourier", 3, 40, 3, 1), ("fourier", 1, 2, 2, 1),
+]
+
+
+def make_layers(kind, n, in_f, out_f, seg, **kw):
+    torch.manual_seed(1234)
+    ref = O.high_order_fc_layers(kind, n=n, in_features=in_f, out_features=out_f, segments=seg, **kw)
+    with torch.no_grad():
+        ref.w.normal_(0, 0.5)
+    lay = H.high_order_fc_layers(kind, n=n, in_features=in_f, out_features=out_f, segments=seg, **kw)
+    lay.load_state_dict(ref.state_dict())
+    return ref, lay.cuda()
+
+
+@pytest.mark.parametrize("kind,n,in_f,out_f,seg", LAYER_CASES)
+@pytest.mark.parametrize("B", [1, 257])
+def test_layer_forward_backward_parity(kind, n, in_f, out_f, seg, B):
+    ref, lay = make_layers(kind, n, in_f, out_f, seg)
+    g = torch.Generator().manual_seed(B)
+    x = (torch.rand(B, in_f, generator=g) * 2.4 - 1.2)
+    gy = torch.randn(B, out_f, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy)
+    xc = x.cuda().requires_grad_(True)
+    yc = lay(xc)
+    yc.backward(gy.cuda())
+    tol = TOL[kind]
+    assert yc.shape == yr.shape
+    assert rel_err(yc, yr) <= tol
+    assert rel_err(xc.grad, xr.grad) <= tol
+    assert rel_err(lay.w.grad, ref.w.grad) <= tol
+
+
+@pytest.mark.parametrize("kind", ["continuous", "discontinuous"])
+@pytest.mark.parametrize("n,seg", [(3, 100), (3, 2), (2, 50), (4, 7), (3, 64)])
+def test_segment_index_bit_exact(kind, n, seg):
+    ref, lay = make_layers(kind, n, 1, 3, seg)
+    g = torch.Generator().manual_seed(7)
+    x = torch.cat([adversarial_inputs(seg), torch.rand(20000, generator=g) * 2.6 - 1.3]).view(-1, 1)
+    id_ref = ref.segment_index(x)
+    wid_ref = id_ref * ref._stride
+    xl_ref = ref.local_coordinate(x, id_ref)
+    idm, wid, xl = H.segment_index(lay, x.cuda())
+    assert torch.equal(idm.cpu().long(), id_ref)
+    assert torch.equal(wid.cpu().long(), wid_ref)
+    assert torch.equal(xl.cpu(), xl_ref)            # same roundings -> bit-identical local coordinate
+
+
+@pytest.mark.parametrize("kind,n,seg", [("continuous", 3, 100), ("discontinuous", 3, 100), ("continuous", 2, 50)])
+def test_layer_adversarial_inputs(kind, n, seg):
+    ref, lay = make_layers(kind, n, 2, 5, seg)
+    a = adversarial_inputs(seg)
+    x = torch.stack([a, a.flip(0)], dim=1)
+    y_ref = ref(x)
+    y = lay(x.cuda())
+    # extrapolation outside [-1, 1] grows the values; compare relative to the reference scale
+    assert rel_err(y, y_ref) <= 1e-5
+
+
+def test_layer_options_rescale_periodicity_scale():
+    for kw in (dict(rescale_output=True), dict(periodicity=2.0), dict(scale=4.0)):
+        for kind in ("continuous", "fourier", "polynomial"):
+            ref, lay = make_layers(kind, 3, 5, 6, 4, **kw)
+            x = torch.rand(300, 5, generator=torch.Generator().manual_seed(3)) * 6 - 3
+            xr = x.clone().requires_grad_(True)
+            yr = ref(xr)
+            yr.sum().backward()
+            xc = x.cuda().requires_grad_(True)
+            yc = lay(xc)
+            yc.sum().backward()
+            tol = 1e-4 if kind == "fourier" else 2e-5
+            assert rel_err(yc, yr) <= tol, (kw, kind)
+            assert rel_err(lay.w.grad, ref.w.grad) <= tol, (kw, kind)
+            assert rel_err(xc.grad, xr.grad) <= tol, (kw, kind)
+
+
+def test_empty_batch():
+    _, lay = make_layers("continuous", 3, 4, 40, 100)
+    y = lay(torch.empty(0, 4, device="cuda"))
+    assert y.shape == (0, 40)
+    norm = H.MaxAbsNormalization()
+    assert norm(torch.empty(0, 40, device="cuda")).shape == (0, 40)
+
+
+@pytest.mark.parametrize("B,width", [(1, 40), (1000, 40), (33, 10), (64, 50), (5, 3)])
+def test_maxabs_parity(B, width):
+    g = torch.Generator().manual_seed(B + width)
+    x = torch.randn(B, width, generator=g)
+    x[0, :] = 0.0                                        # all-zero row: y = 0 / eps-denominator
+    if B > 2:
+        x[1, 1] = x[1, 0] = 3.0                          # tie: gradient goes to the first index
+        x[2, 2] = -5.0
+    gy = torch.randn(B, width, generator=g)
+    ref, mod = O.MaxAbsNormalization(), H.MaxAbsNormalization()
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy)
+    xc = x.cuda().requires_grad_(True)
+    yc = mod(xc)
+    yc.backward(gy.cuda())
+    assert torch.equal(yc.cpu(), yr.detach())            # a division: bit-exact
+    assert rel_err(xc.grad, xr.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("rows,cols,rot", [(4, 3, 2), (64, 48, 1), (37, 91, 2), (16, 16, 4)])
+def test_positions_from_mesh_bit_exact(rows, cols, rot):
+    for normalize in (True, False):
+        ref = O.positions_from_mesh(rows, cols, rotations=rot, normalize=normalize)
+        got = H.positions_from_mesh(rows, cols, device="cuda", rotations=rot, normalize=normalize)
+        host = H.positions_from_mesh(rows, cols, rotations=rot, normalize=normalize)
+        assert len(got) == len(ref) == 2 * rot
+        for a, b, c in zip(got, ref, host):
+            assert a.shape == (rows, cols)
+            assert torch.equal(a.cpu(), b.to(torch.float32))
+            assert torch.equal(c, b)
