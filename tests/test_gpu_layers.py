@@ -49,7 +49,9 @@ def test_layer_forward_backward_parity(kind, n, in_f, out_f, seg, B):
     tol = TOL[kind]
     assert yc.shape == yr.shape
     assert rel_err(yc, yr) <= tol
-    assert rel_err(xc.grad, xr.grad) <= tol
+    # n == 1: the basis is constant, the oracle's autograd leaves x.grad unset -> zero gradient
+    gx_ref = xr.grad if xr.grad is not None else torch.zeros_like(x)
+    assert rel_err(xc.grad, gx_ref) <= tol
     assert rel_err(lay.w.grad, ref.w.grad) <= tol
 
 
