@@ -201,7 +201,7 @@ def main():
         torch.cuda.synchronize()
 
     def step(s):
-        block = (s * world + rank) % n_blocks
+        block = H.parallel.training_block(s, rank, world, n_blocks)
         return trainer.train_step_mesh(img, ROTATIONS, block * BATCH, BATCH)
 
     for s in range(args.warmup):

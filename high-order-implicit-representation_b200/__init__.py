@@ -1,7 +1,7 @@
 """hoir_b200 -- B200-native (sm_100a) drop-in for the high-order layer path of
 jloveric/high-order-implicit-representation.  Importable as ``hoir_b200`` (see the shim
 ``hoir_b200.py`` at the repository root; the directory name carries hyphens)."""
-from . import _lib, config, spec  # noqa: F401
+from . import _lib, config, parallel, spec  # noqa: F401
 from ._lib import HoirUnsupported, build  # noqa: F401
 from .config import Config, apply_overrides, images_config, to_cfg  # noqa: F401
 from .engine import FusedTrainer, HostBatchStepper  # noqa: F401

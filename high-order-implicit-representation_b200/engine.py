@@ -15,10 +15,9 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.distributed as dist
 from torch import Tensor
 
-from . import _lib
+from . import _lib, parallel
 from .networks import HighOrderMLP
 
 
@@ -46,7 +45,7 @@ class FusedTrainer:
         self.weight_decay = float(weight_decay)
         self.step_count = 0
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank, self.world = parallel.world_info(process_group)
         self.out_features = self.layers[-1].out_features
         self.in_features = self.layers[0].in_features
         sizes = [l.w.numel() for l in self.layers]
@@ -92,12 +91,10 @@ class FusedTrainer:
         self.kernel_events.append((e0, e1))
 
     def _loss_scale(self, B: int, global_batch: Optional[int]) -> float:
-        gb = global_batch if global_batch is not None else B * self.world
-        return 1.0 / (gb * self.out_features) if gb > 0 else 0.0
+        return parallel.global_loss_scale(B, self.world, self.out_features, global_batch)
 
     def _finish(self) -> Tensor:
-        if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        parallel.allreduce_sum_(self.flat_g, self.group)
         self.step_count += 1
         st = _lib.stream_ptr(self.device)
         if self.optimizer == "adam":

@@ -1,0 +1,100 @@
+"""world_size-2 gloo test (CPU) of the multi-rank host logic: disjoint pixel blocks, the global
+loss scale and the single all-reduce of the flat [gradient | loss] vector reproduce the
+single-process gradient and loss (the model on each rank is the CPU oracle -- the CUDA kernels
+are covered by the -m gpu tests; here only the sharding arithmetic and the collective run)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import hoir_b200  # noqa: F401  (registers the package)
+from hoir_b200 import parallel
+from oracle import hol_oracle as O
+
+KW = dict(layer_type="continuous", n=3, in_width=2, out_width=3, hidden_layers=2, hidden_width=10,
+          in_segments=100, out_segments=2, hidden_segments=2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _build():
+    torch.manual_seed(0)
+    net = O.HighOrderMLP(normalization=O.MaxAbsNormalization, **KW)
+    O.initialize_network_polynomial_layers(net, 1.0, 0.0)
+    g = torch.Generator().manual_seed(1)
+    img = torch.randint(0, 256, (16, 32, 3), generator=g, dtype=torch.uint8)
+    y, x, _ = O.image_to_dataset(img, rotations=1)
+    return net, x, y
+
+
+def _flat_grad_and_loss(net, x, y, scale):
+    net.zero_grad()
+    out = net(x)
+    sse = ((out - y) ** 2).sum() * scale
+    sse.backward()
+    return torch.cat([p.grad.flatten() for p in net.parameters()] + [sse.detach().view(1)])
+
+
+def _worker(rank, world, port, block, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    net, x, y = _build()
+    n_blocks = x.shape[0] // block
+    r, w = parallel.world_info()
+    assert (r, w) == (rank, world)
+    b = parallel.training_block(3, rank, world, n_blocks)
+    sl = slice(b * block, (b + 1) * block)
+    scale = parallel.global_loss_scale(block, world, 3)
+    flat = _flat_grad_and_loss(net, x[sl], y[sl], scale)
+    parallel.allreduce_sum_(flat)
+    first, count = parallel.render_shard(x.shape[0], rank, world, align=64)
+    q.put((rank, b, flat, first, count))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_step_equals_single_process():
+    world, block = 2, 128
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, block, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    blocks = [r[1] for r in res]
+    assert len(set(blocks)) == world                       # disjoint blocks within a step
+    assert torch.equal(res[0][2], res[1][2])               # identical after the all-reduce
+    net, x, y = _build()
+    idx = torch.cat([torch.arange(b * block, (b + 1) * block) for b in blocks])
+    want = _flat_grad_and_loss(net, x[idx], y[idx], 1.0 / (idx.numel() * 3))
+    assert torch.allclose(res[0][2], want, rtol=1e-4, atol=1e-7)
+    mse = torch.nn.functional.mse_loss(net(x[idx]).flatten(), y[idx].flatten())
+    assert abs(res[0][2][-1].item() - mse.item()) <= 1e-5 * mse.item()
+    # render shards: disjoint, aligned, covering
+    shards = [(r[3], r[4]) for r in res]
+    assert shards[0][0] == 0 and shards[0][0] + shards[0][1] == shards[1][0]
+    assert shards[1][0] % 64 == 0 and shards[1][0] + shards[1][1] == x.shape[0]
+
+
+@pytest.mark.parametrize("n,world", [(67108864, 8), (1000, 3), (5, 8), (0, 2)])
+def test_render_shard_partition(n, world):
+    cover = 0
+    for r in range(world):
+        first, count = parallel.render_shard(n, r, world)
+        assert first == cover or count == 0
+        assert first % 256 == 0 or count == 0
+        cover += count
+    assert cover == n
