@@ -16,6 +16,7 @@
 //             flushed to HBM once per CTA.  Layer 0 (many segments) merges runs of equal
 //             segment and flushes with global atomics.
 // Algorithm: oracle/hol_oracle.py.
+#include <stdlib.h>
 #include "hoir_common.cuh"
 
 namespace {
@@ -77,10 +78,23 @@ struct SegConst {
   float segf, inv_segf;
 };
 
+__device__ __forceinline__ void locate2(float x, int& id, float& xi);
 template <bool POW2>
 __device__ __forceinline__ void locate(float x, const SegConst& sc, int& id, float& xi) {
+  if (POW2 && sc.segments == 2) {   // compile-time after inlining for the hidden / output layers
+    locate2(x, id, xi);
+    return;
+  }
   id = hoir::segment_index(x, 1.f, 2.f, sc.segf, sc.segments);
   xi = hoir::local_coordinate<POW2>(x, id, 1.f, 2.f, sc.segf, sc.inv_segf);
+}
+// two segments on [-1, 1] (hidden / output layers of every reference config): the same roundings
+// as the generic form collapse to  id = (fl(x + 1) >= 1),  xi = 2 * (x - (id - 1)) - 1.
+__device__ __forceinline__ void locate2(float x, int& id, float& xi) {
+  const float t = __fadd_rn(x, 1.f);            // ((x + 1) / 2) * 2: both scalings are exact
+  id = t >= 1.f ? 1 : 0;                        // trunc + clamp to {0, 1}; NaN -> 0
+  const float q = __fsub_rn(x, id ? 0.f : -1.f);
+  xi = __fsub_rn(__fmul_rn(2.f, q), 1.f);
 }
 
 // y[O] += sum_j l[j] * W[(base + j)][0..OP)   (W row-major, OP floats per node, 16B aligned)
@@ -133,9 +147,9 @@ __device__ __forceinline__ void maxabs_fwd(float* v, float eps, float& inv_d, in
   }
   const float d = __fadd_rn(m, eps);
   const float sgn = vk > 0.f ? 1.f : (vk < 0.f ? -1.f : 0.f);
+  inv_d = __fdiv_rn(1.f, d);
 #pragma unroll
-  for (int i = 0; i < W; ++i) v[i] = __fdiv_rn(v[i], d);
-  inv_d = 1.f / d;
+  for (int i = 0; i < W; ++i) v[i] *= inv_d;   // within 1 ulp of x / d (the stand-alone kernel divides)
   kidx = sgn > 0.f ? k : (sgn < 0.f ? (k | 0x10000) : (k | 0x20000));
 }
 
@@ -521,6 +535,10 @@ __global__ void __launch_bounds__(BT, 1) fused_mlp_kernel(const FusedParams p) {
   }
 }
 
+}  // namespace
+#include "fused_mlp_tc.cuh"
+namespace {
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -551,21 +569,30 @@ struct FusedEntry {
   void (*fwd)(const FusedParams);
   void (*train)(const FusedParams);
   size_t smem_fwd, smem_train;
+  void (*train_tc)(const FusedParams);   // tensor-core (tcgen05) training kernel, or nullptr
+  size_t smem_tc;
 };
 
 template <class S>
 constexpr FusedEntry make_entry() {
   return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
                     fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
-                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4};
+                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4, nullptr, 0};
+}
+template <class S>
+constexpr FusedEntry make_entry_tc() {
+  return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
+                    fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
+                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4,
+                    tc::fused_mlp_tc_kernel<S>, (size_t)tc::TcPlan<S>::SMEM_BYTES};
 }
 
 // Instantiations: BASELINE.json configs C2/C3 (40-wide, 1 hidden layer, rotations 1 and 2) and
 // C1 (10-wide, 2 hidden layers), continuous and discontinuous, n = 3; plus n = 2 variants.
 const FusedEntry kEntries[] = {
-    make_entry<Shape<HOIR_CONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
+    make_entry_tc<Shape<HOIR_CONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
     make_entry<Shape<HOIR_DISCONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
-    make_entry<Shape<HOIR_CONTINUOUS, 3, 2, 40, 3, 1, 2, 2>>(),
+    make_entry_tc<Shape<HOIR_CONTINUOUS, 3, 2, 40, 3, 1, 2, 2>>(),
     make_entry<Shape<HOIR_CONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),
     make_entry<Shape<HOIR_DISCONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),
     make_entry<Shape<HOIR_CONTINUOUS, 2, 2, 10, 3, 2, 2, 2>>(),
@@ -713,6 +740,15 @@ extern "C" int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const fl
   p.gy_ext = gy_ext;
   p.loss_sum = loss_sum;
   p.loss_scale = loss_scale;
+  static const bool no_tc = getenv("HOIR_NO_TC") != nullptr;   // A/B switch: FFMA-only kernel
+  if (e->train_tc != nullptr && !no_tc) {
+    HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->train_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_tc));
+    const long long tiles = (B + tc::TS - 1) / tc::TS;
+    const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
+    e->train_tc<<<grid, tc::NTHREADS, e->smem_tc, (cudaStream_t)stream>>>(p);
+    HOIR_CHECK_CUDA(cudaGetLastError());
+    return HOIR_OK;
+  }
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_train));
   const long long tiles = (B + BT - 1) / BT;
   const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());

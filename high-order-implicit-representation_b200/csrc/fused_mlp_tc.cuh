@@ -1,0 +1,608 @@
+// fused_mlp_tc.cuh -- tensor-core (tcgen05 / TMEM) training kernel for the 40-wide implicit MLP.
+// Included by fused_mlp.cu (uses its FusedParams / SegConst / contract_* helpers).
+//
+// One CTA = 4 sample warps (thread t <-> sample t of a 128-sample tile <-> TMEM lane t) + 1 MMA
+// warp; persistent grid.  The hidden layer's three contractions are densified GEMMs
+// (K = 40 inputs x 5 nodes = 200) on tcgen05.mma kind::tf32 with a 3-pass hi/lo split
+// (A*B + Alo*B + A*Blo, fp32-level accuracy):
+//   FWD  D1[128 x 40]   = Phi1[128 x 200] * W1          A: TMEM (chunks of 8 inputs, double buffered)
+//                                                        B: smem W1, K-major view
+//   GX   T [128 x 208]  = G  [128 x 40]  * W1^T         A: TMEM, B: the same smem W1, MN-major view
+//   GW   gW1[200 x 40] += Phi1^T[200 x 16] * G[16 x 40] A: smem units of 16 samples (MN-major),
+//                                                        B: smem G^T (K-major); accumulators stay in
+//                                                        TMEM for the whole kernel
+// All shared-memory operands use the 128B_BASE32B layout (rows of 128 B, atoms of 4 rows, 32-byte
+// chunks XOR-ed with row%4), the one layout that tcgen05 accepts for tf32 in BOTH majors (probe:
+// csrc/probe/umma_probe.cu), so W1 and G are stored once.  Layer 0, the output layer, the basis,
+// MaxAbs and the loss stay on the CUDA cores (FFMA).
+#pragma once
+
+namespace tc {
+
+constexpr int TS = 128;          // samples per tile
+constexpr int NTHREADS = 160;    // 4 sample warps + 1 MMA warp
+constexpr int APITCH = 41;       // row pitch (floats) of the saved-activation tiles
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();   // protocol bug: fail loudly instead of hanging
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_samples() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// shared-memory operand in the 128B_BASE32B layout: element (row r, column c), RS = bytes per 4 rows
+__device__ __forceinline__ uint32_t sw4_off(uint32_t r, uint32_t c, uint32_t RS) {
+  return (r & 3u) * 128u + ((((c & 31u) << 2)) ^ ((r & 3u) << 5)) + (c >> 5) * 512u + (r >> 2) * RS;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fffu);
+  d |= (uint64_t)(512u >> 4) << 16;                 // LBO: next 32-column atom
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;      // SBO: next 4-row atom
+  d |= (uint64_t)1 << 46;                           // descriptor version
+  d |= (uint64_t)1 << 61;                           // layout type 1: SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// Shape constants of the tensor path (continuous n = 3, 2 hidden/output segments, width 40)
+template <class S>
+struct TcPlan {
+  static constexpr int HID = S::HID, ND = S::NODES_H, KH = HID * ND;       // 40, 5, 200
+  static constexpr int CH_IN = 8, CH_K = CH_IN * ND, NCH = HID / CH_IN;    // 8 inputs = 40 K-columns per FWD chunk
+  static constexpr int KP = (KH + 31) / 32 * 32;                            // 224: W1 columns (node) padded to atoms
+  static constexpr int TN = (KH + 15) / 16 * 16;                            // 208: N of the GX product
+  static constexpr int UNIT = 16, NUNIT = TS / UNIT;                        // GW: samples per smem unit
+  // TMEM columns
+  static constexpr int D1_COL = 0, FA_COL = 64, G_COL = 64, T_COL = 224, GW_COL = 432;
+  // shared memory (bytes)
+  static constexpr uint32_t W1_RS = KP / 32 * 512, W1_BYTES = HID / 4 * W1_RS;          // 3584, 35840
+  static constexpr uint32_t GT_RS = TS / 32 * 512, GT_BYTES = HID / 4 * GT_RS;          // 2048, 20480
+  static constexpr uint32_t U_RS = 256 / 32 * 512, U_BYTES = UNIT / 4 * U_RS;           // 4096, 16384
+  static constexpr uint32_t A_BYTES = TS * APITCH * 4;                                  // 20992
+  static constexpr uint32_t W2_BYTES = S::WO * 4;
+  static constexpr uint32_t OFF_W1R = 0, OFF_W1L = OFF_W1R + W1_BYTES, OFF_GTR = OFF_W1L + W1_BYTES,
+                            OFF_GTL = OFF_GTR + GT_BYTES, OFF_U = OFF_GTL + GT_BYTES,   // [2][raw|lo]
+                            OFF_A1 = OFF_U + 4 * U_BYTES, OFF_A2 = OFF_A1 + A_BYTES, OFF_W2 = OFF_A2 + A_BYTES,
+                            OFF_ACC2 = OFF_W2 + W2_BYTES, OFF_BAR = OFF_ACC2 + W2_BYTES, SMEM_BYTES = OFF_BAR + 256;
+  static_assert(S::KIND == HOIR_CONTINUOUS && S::N == 3 && S::SEGH == 2 && S::SEGO == 2 && S::NH == 1, "tensor path: C2 family");
+  static_assert(HID % CH_IN == 0 && HID % 8 == 0 && CH_K % 8 == 0 && KH <= 256, "tensor path shape");
+  static_assert(FA_COL + 4 * CH_K <= T_COL && T_COL + TN <= GW_COL && GW_COL + 2 * HID <= 512, "TMEM plan");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan");
+  static_assert(S::IN * 16 * TS <= A_BYTES, "layer-0 records alias the A2 tile");
+};
+
+enum { B_FFULL0 = 0, B_FFULL1, B_FEMPTY0, B_FEMPTY1, B_D1FULL, B_D1EMPTY, B_GFULL, B_TFULL, B_GWDONE,
+       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_COUNT };
+
+template <class S>
+__global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedParams p) {
+  using P = TcPlan<S>;
+  constexpr int N = S::N, IN = S::IN, HID = S::HID, OUT = S::OUT, HP = S::HP, OP = S::OP, ND = P::ND;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sW1R = smem + P::OFF_W1R;
+  uint8_t* sW1L = smem + P::OFF_W1L;
+  uint8_t* sGTR = smem + P::OFF_GTR;
+  uint8_t* sGTL = smem + P::OFF_GTL;
+  uint8_t* sU = smem + P::OFF_U;
+  float* sA1 = reinterpret_cast<float*>(smem + P::OFF_A1);
+  float* sA2 = reinterpret_cast<float*>(smem + P::OFF_A2);
+  float* sW2 = reinterpret_cast<float*>(smem + P::OFF_W2);
+  float* sAcc2 = reinterpret_cast<float*>(smem + P::OFF_ACC2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (uniform datapath)
+
+  // ---- prologue: TMEM, barriers, weights -------------------------------------------------
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bars[B_FFULL0], 128); mbar_init(&bars[B_FFULL1], 128);
+    mbar_init(&bars[B_FEMPTY0], 1);  mbar_init(&bars[B_FEMPTY1], 1);
+    mbar_init(&bars[B_D1FULL], 1);   mbar_init(&bars[B_D1EMPTY], 128);
+    mbar_init(&bars[B_GFULL], 128);  mbar_init(&bars[B_TFULL], 1);   mbar_init(&bars[B_GWDONE], 1);
+    mbar_init(&bars[B_UFULL0], 128); mbar_init(&bars[B_UFULL1], 128);
+    mbar_init(&bars[B_UEMPTY0], 1);  mbar_init(&bars[B_UEMPTY1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  {
+    // hidden-layer weights: packed [i][node][HP] -> smem rows = o, cols = i*ND + node (raw and tf32 residual)
+    const float* w1 = p.packed + p.off[1];
+    for (uint32_t k = tid; k < (uint32_t)(P::W1_BYTES / 4); k += NTHREADS) {
+      reinterpret_cast<float*>(sW1R)[k] = 0.f;
+      reinterpret_cast<float*>(sW1L)[k] = 0.f;
+    }
+    for (uint32_t k = tid; k < (uint32_t)(4 * P::U_BYTES / 4); k += NTHREADS) reinterpret_cast<float*>(sU)[k] = 0.f;
+    __syncthreads();
+    for (int k = tid; k < P::KH * HID; k += NTHREADS) {
+      const int o = k % HID, col = k / HID;
+      const float v = __ldg(w1 + (size_t)col * HP + o);
+      const uint32_t off = sw4_off(o, col, P::W1_RS);
+      *reinterpret_cast<float*>(sW1R + off) = v;
+      *reinterpret_cast<float*>(sW1L + off) = tf32_lo(v);
+    }
+    const float* w2 = p.packed + p.off[2];
+    for (int k = tid; k < S::WO; k += NTHREADS) { sW2[k] = __ldg(w2 + k); sAcc2[k] = 0.f; }
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const long long tiles = (p.B + TS - 1) / TS;
+
+  if (warp == 4) {
+    // =========================== MMA warp ===================================================
+    const uint32_t leader = elect_one();
+    constexpr uint32_t ID_FWD = make_idesc(128, HID, 0, 0);        // A: TMEM (K-major), B: W1 K-major
+    constexpr uint32_t ID_GX = make_idesc(128, P::TN, 0, 1);       // A: TMEM, B: W1 MN-major
+    constexpr uint32_t ID_GW = make_idesc(128, HID, 1, 0);         // A: Phi unit MN-major, B: G^T K-major
+    const uint64_t dW1[2] = {make_desc(smem_u32(sW1R), P::W1_RS), make_desc(smem_u32(sW1L), P::W1_RS)};
+    const uint64_t dGT[2] = {make_desc(smem_u32(sGTR), P::GT_RS), make_desc(smem_u32(sGTL), P::GT_RS)};
+    uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+      // ---- FWD: D1 = Phi1 * W1, five chunks of 8 inputs
+      if (n_tile > 0) mbar_wait(&bars[B_D1EMPTY], (n_tile - 1) & 1);
+      for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
+        const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
+        mbar_wait(&bars[B_FFULL0 + buf], ph);
+        fence_after();
+        if (leader) {
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+            for (int j = 0; j < P::CH_K / 8; ++j) {
+              const uint32_t ks = (uint32_t)(c * (P::CH_K / 8) + j);
+              const uint32_t koff = (ks >> 2) * 512u + (ks & 3u) * 32u;
+              mma_ts(tmem + P::D1_COL, tmem + P::FA_COL + buf * 2 * P::CH_K + (pass == 1 ? P::CH_K : 0) + j * 8,
+                     dW1[pass == 2] + (uint64_t)(koff >> 4), ID_FWD, (c | pass | j) != 0);
+            }
+          }
+          umma_commit(&bars[B_FEMPTY0 + buf]);
+          if (c == P::NCH - 1) umma_commit(&bars[B_D1FULL]);
+        }
+        __syncwarp();
+      }
+      // ---- GX: T = G * W1^T
+      mbar_wait(&bars[B_GFULL], n_tile & 1);
+      fence_after();
+      if (leader) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+          for (int j = 0; j < HID / 8; ++j) {
+            mma_ts(tmem + P::T_COL, tmem + P::G_COL + (pass == 1 ? HID : 0) + j * 8,
+                   dW1[pass == 2] + (uint64_t)((j * 2 * P::W1_RS) >> 4), ID_GX, (pass | j) != 0);
+          }
+        }
+        umma_commit(&bars[B_TFULL]);
+      }
+      __syncwarp();
+      // ---- GW: gW1 += Phi1^T * G, eight units of 16 samples
+      for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
+        const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
+        mbar_wait(&bars[B_UFULL0 + buf], ph);
+        fence_after();
+        if (leader) {
+          const uint32_t ubase = smem_u32(sU + buf * 2 * P::U_BYTES);
+          const uint64_t dU[2] = {make_desc(ubase, P::U_RS), make_desc(ubase + P::U_BYTES, P::U_RS)};
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+              for (int j = 0; j < P::UNIT / 8; ++j) {
+                const uint32_t ks = (uint32_t)(u * (P::UNIT / 8) + j);
+                const uint32_t koff = (ks >> 2) * 512u + (ks & 3u) * 32u;
+                mma_ss(tmem + P::GW_COL + half * HID,
+                       dU[pass == 1] + (uint64_t)((j * 2 * P::U_RS + half * 4 * 512) >> 4),
+                       dGT[pass == 2] + (uint64_t)(koff >> 4), ID_GW, (n_tile | (uint32_t)u | pass | j) != 0);
+              }
+            }
+          }
+          umma_commit(&bars[B_UEMPTY0 + buf]);
+          if (u == P::NUNIT - 1) umma_commit(&bars[B_GWDONE]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== sample warps ===============================================
+    const SegConst sc0 = {p.seg0, S::STRIDE, (float)p.seg0, 1.f / (float)p.seg0};
+    const float* w0 = p.packed + p.off[0];
+    const LagrangeTable& lag = p.lag;
+    const uint32_t tm_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    float* a1 = sA1 + tid * APITCH;
+    float* a2 = sA2 + tid * APITCH;
+    float loss_local = 0.f;
+    uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+      const long long b = tile * TS + tid;
+      const bool live = b < p.B;
+      float x0[IN];
+#pragma unroll
+      for (int i = 0; i < IN; ++i) x0[i] = 0.f;
+      if (live) {
+        if (p.x != nullptr) {
+#pragma unroll
+          for (int i = 0; i < IN; ++i) x0[i] = __ldg(p.x + b * IN + i);
+        } else {
+          hoir::mesh_position(p.mesh, p.mesh.first_pixel + b, x0, IN / 2);
+        }
+      }
+      // ---- layer 0 (FFMA, weights through L1)
+      float h[HID];
+      float4 rec0[IN];
+      float inv_d0 = 1.f, inv_d1 = 1.f;
+      int kidx0 = 0, kidx1 = 0;
+#pragma unroll
+      for (int o = 0; o < HID; ++o) h[o] = 0.f;
+#pragma unroll
+      for (int i = 0; i < IN; ++i) {
+        int id;
+        float xi, l[N];
+        if (p.pow2_0) locate<true>(x0[i], sc0, id, xi);
+        else locate<false>(x0[i], sc0, id, xi);
+        hoir::lagrange<N>(lag.X, lag.D, xi, l);
+        const int base0 = id * S::STRIDE;
+        contract_fwd<N, HID, HP, true>(w0 + ((size_t)i * p.nodes0 + base0) * HP, l, h);
+        rec0[i] = make_float4(__int_as_float(base0), l[0], l[1], l[2]);
+      }
+      if (p.normalize) maxabs_fwd<HID>(h, p.norm_eps, inv_d0, kidx0);
+#pragma unroll
+      for (int i = 0; i < HID; ++i) a1[i] = h[i];
+      // ---- hidden layer forward on the tensor cores: stage Phi1 chunks into TMEM
+      for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
+        const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
+        mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);
+        fence_after();
+        float v[P::CH_K];
+#pragma unroll
+        for (int k = 0; k < P::CH_IN; ++k) {
+          const float x = a1[c * P::CH_IN + k];
+          int id;
+          float xi, l[N];
+          locate2(x, id, xi);
+          hoir::lagrange<N>(lag.X, lag.D, xi, l);
+          v[k * ND + 0] = id ? 0.f : l[0];
+          v[k * ND + 1] = id ? 0.f : l[1];
+          v[k * ND + 2] = id ? l[0] : l[2];
+          v[k * ND + 3] = id ? l[1] : 0.f;
+          v[k * ND + 4] = id ? l[2] : 0.f;
+        }
+        const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K;
+#pragma unroll
+        for (int g8 = 0; g8 < P::CH_K / 8; ++g8) {
+          float lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) lo[j] = tf32_lo(v[g8 * 8 + j]);
+          tmem_st8(col + g8 * 8, v + g8 * 8);
+          tmem_st8(col + P::CH_K + g8 * 8, lo);
+        }
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&bars[B_FFULL0 + buf]);
+      }
+      // ---- D1 epilogue: hidden pre-activation -> MaxAbs -> a2
+      mbar_wait(&bars[B_D1FULL], n_tile & 1);
+      fence_after();
+#pragma unroll
+      for (int g8 = 0; g8 < HID / 8; ++g8) tmem_ld8(tm_lane + P::D1_COL + g8 * 8, h + g8 * 8);
+      tmem_wait_ld();
+      fence_before();
+      mbar_arrive(&bars[B_D1EMPTY]);
+      if (p.normalize) maxabs_fwd<HID>(h, p.norm_eps, inv_d1, kidx1);
+#pragma unroll
+      for (int i = 0; i < HID; ++i) a2[i] = h[i];
+      // ---- output layer forward (FFMA), loss, dL/dy
+      float yo[OUT], gy[OUT];
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) yo[o] = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < HID; ++i) {
+        int id;
+        float xi, l[N];
+        locate2(a2[i], id, xi);
+        hoir::lagrange<N>(lag.X, lag.D, xi, l);
+        contract_fwd<N, OUT, OP, false>(sW2 + ((size_t)i * S::NODES_O + id * S::STRIDE) * OP, l, yo);
+      }
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) gy[o] = 0.f;
+      if (live) {
+        if (p.gy_ext != nullptr) {
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) gy[o] = __ldg(p.gy_ext + b * OUT + o);
+        } else {
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) {
+            float t;
+            if (p.target_kind == HOIR_TARGET_U8_IMAGE) {
+              const unsigned char* img = static_cast<const unsigned char*>(p.target);
+              const float u = (float)img[(p.mesh.first_pixel + b) * OUT + o];
+              t = __fsub_rn(__fdiv_rn(__fmul_rn(u, 2.f), 255.f), 1.f);
+            } else {
+              t = __ldg(static_cast<const float*>(p.target) + b * OUT + o);
+            }
+            const float diff = yo[o] - t;
+            loss_local = fmaf(diff, diff, loss_local);
+            gy[o] = 2.f * diff * p.loss_scale;
+          }
+        }
+      }
+      // ---- output layer backward (FFMA): dL/da2 and dL/dw2 (warp reduce-scatter, smem accumulators)
+      float g[HID];
+      float dot = 0.f;
+#pragma unroll 2
+      for (int i = 0; i < HID; ++i) {
+        const float x = a2[i];
+        int id;
+        float xi, l[N], d[N], t[N];
+        locate2(x, id, xi);
+        hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
+        contract_bwd<N, OUT, OP>(sW2 + ((size_t)i * S::NODES_O + id * S::STRIDE) * OP, gy, t);
+        float gx = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) gx = fmaf(d[j], t[j], gx);
+        gx *= 2.f;                                   // d xi / d x = segments
+        dot = fmaf(gx, x, dot);
+        a2[i] = gx;                                  // a2 now holds dL/da2
+        // densified basis row x dL/dy: 5 x 3 products (+1 pad), reduce-scatter over the warp
+        float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+        float r[16];
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) r[k * OUT + o] = c5[k] * gy[o];
+        r[15] = 0.f;
+#pragma unroll
+        for (int s = 16, n = 8; s >= 2; s >>= 1, n >>= 1) {
+          const bool up = (lane & s) != 0;
+#pragma unroll
+          for (int m = 0; m < n; ++m) {
+            const float send = up ? r[m] : r[m + n];
+            const float keep = up ? r[m + n] : r[m];
+            r[m] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+          }
+        }
+        r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+        // lane holds element e = bit-reversed-ish index: reconstruct which of the 16 it owns
+        if ((lane & 1) == 0) {
+          const int e = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+          if (e < ND * OUT) {
+            const int k = e / OUT, o = e - k * OUT;
+            atomicAdd(&sAcc2[((size_t)i * S::NODES_O + k) * OP + o], r[0]);
+          }
+        }
+      }
+      if (p.normalize) {
+        const int k = kidx1 & 0xffff;
+        const float sgn = (kidx1 & 0x10000) ? -1.f : ((kidx1 & 0x20000) ? 0.f : 1.f);
+#pragma unroll
+        for (int i = 0; i < HID; ++i) {
+          float gi = a2[i];
+          if (i == k) gi -= sgn * dot;
+          g[i] = gi * inv_d1;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < HID; ++i) g[i] = a2[i];
+      }
+      // ---- stage G: TMEM (A operand of GX) and smem G^T (B operand of GW)
+      if (n_tile > 0) mbar_wait(&bars[B_GWDONE], (n_tile - 1) & 1);   // previous tile's GW done with G^T
+      fence_after();
+      {
+        float lo[HID];
+#pragma unroll
+        for (int o = 0; o < HID; ++o) lo[o] = tf32_lo(g[o]);
+#pragma unroll
+        for (int g8 = 0; g8 < HID / 8; ++g8) {
+          tmem_st8(tm_lane + P::G_COL + g8 * 8, g + g8 * 8);
+          tmem_st8(tm_lane + P::G_COL + HID + g8 * 8, lo + g8 * 8);
+        }
+#pragma unroll
+        for (int o = 0; o < HID; ++o) {
+          const uint32_t off = sw4_off(o, tid, P::GT_RS);
+          *reinterpret_cast<float*>(sGTR + off) = g[o];
+          *reinterpret_cast<float*>(sGTL + off) = lo[o];
+        }
+      }
+      tmem_wait_st();
+      fence_async_smem();
+      fence_before();
+      mbar_arrive(&bars[B_GFULL]);
+      bar_samples();     // every sample's a1 row is visible to the GW staging below
+      // ---- GW staging: units of 16 samples, (sample, input) items spread over the 128 threads
+      for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
+        const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
+        mbar_wait(&bars[B_UEMPTY0 + buf], ph ^ 1);
+        uint8_t* ur = sU + buf * 2 * P::U_BYTES;
+        uint8_t* ul = ur + P::U_BYTES;
+#pragma unroll
+        for (int j = 0; j < P::UNIT * HID / 128; ++j) {
+          const int f = tid + 128 * j;
+          const int sl = f / HID, i = f - sl * HID;
+          const float x = sA1[(u * P::UNIT + sl) * APITCH + i];
+          int id;
+          float xi, l[N];
+          locate2(x, id, xi);
+          hoir::lagrange<N>(lag.X, lag.D, xi, l);
+          const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            const uint32_t off = sw4_off(sl, i * ND + k, P::U_RS);
+            *reinterpret_cast<float*>(ur + off) = c5[k];
+            *reinterpret_cast<float*>(ul + off) = tf32_lo(c5[k]);
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(&bars[B_UFULL0 + buf]);
+      }
+      // ---- T epilogue: dL/da1 = slope * sum_j l'_j * T[5 i + window + j]
+      mbar_wait(&bars[B_TFULL], n_tile & 1);
+      fence_after();
+      dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < P::NCH; ++c) {
+        float t[P::CH_K];
+#pragma unroll
+        for (int g8 = 0; g8 < P::CH_K / 8; ++g8) tmem_ld8(tm_lane + P::T_COL + c * P::CH_K + g8 * 8, t + g8 * 8);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < P::CH_IN; ++k) {
+          const int i = c * P::CH_IN + k;
+          const float x = a1[i];
+          int id;
+          float xi, l[N], d[N];
+          locate2(x, id, xi);
+          hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
+          const float t0 = id ? t[k * ND + 2] : t[k * ND + 0];
+          const float t1 = id ? t[k * ND + 3] : t[k * ND + 1];
+          const float t2 = id ? t[k * ND + 4] : t[k * ND + 2];
+          float gx = fmaf(d[2], t2, fmaf(d[1], t1, d[0] * t0)) * 2.f;
+          dot = fmaf(gx, x, dot);
+          g[i] = gx;
+        }
+      }
+      fence_before();
+      if (p.normalize) {
+        const int k = kidx0 & 0xffff;
+        const float sgn = (kidx0 & 0x10000) ? -1.f : ((kidx0 & 0x20000) ? 0.f : 1.f);
+#pragma unroll
+        for (int i = 0; i < HID; ++i) {
+          float gi = g[i];
+          if (i == k) gi -= sgn * dot;
+          g[i] = gi * inv_d0;
+        }
+      }
+      // ---- layer 0 dL/dw: owners (input, output) walk the tile (run-merged global atomics)
+      bar_samples();                                  // everyone is done reading sA1 / sA2
+#pragma unroll
+      for (int o = 0; o < HID; ++o) a1[o] = g[o];     // sA1 <- dL/d(layer-0 output)
+#pragma unroll
+      for (int i = 0; i < IN; ++i) reinterpret_cast<float4*>(sA2)[(size_t)i * TS + tid] = rec0[i];
+      bar_samples();
+      for (int pr = tid; pr < IN * HID; pr += 128) {
+        const int i = pr / HID, o = pr - i * HID;
+        float* dst = p.gw[0] + ((size_t)o * IN + i) * p.nodes0;
+        const float4* rp = reinterpret_cast<const float4*>(sA2) + (size_t)i * TS;
+        int cur = -1;
+        float acc[N] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int s = 0; s < TS; ++s) {
+          const float4 r = rp[s];
+          const float gv = sA1[s * APITCH + o];
+          const int base = __float_as_int(r.x);
+          if (base != cur) {
+            if (cur >= 0) {
+#pragma unroll
+              for (int j = 0; j < N; ++j)
+                if (acc[j] != 0.f) atomicAdd(dst + cur + j, acc[j]);
+            }
+            cur = base;
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc[j] = 0.f;
+          }
+          acc[0] = fmaf(r.y, gv, acc[0]);
+          acc[1] = fmaf(r.z, gv, acc[1]);
+          acc[2] = fmaf(r.w, gv, acc[2]);
+        }
+        if (cur >= 0) {
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            if (acc[j] != 0.f) atomicAdd(dst + cur + j, acc[j]);
+        }
+      }
+      bar_samples();                                  // owners done before the next tile reuses sA1 / sA2
+    }
+    // ---- flush: loss, dL/dw2 (smem), dL/dw1 (TMEM accumulators)
+    if (p.gy_ext == nullptr) {
+      const float s = hoir::warp_sum(loss_local) * p.loss_scale;
+      if (lane == 0 && s != 0.f) atomicAdd(p.loss_sum, s);
+    }
+    bar_samples();
+    for (int k = tid; k < HID * S::NODES_O * OUT; k += 128) {
+      const int o = k % OUT, r = k / OUT, q = r % S::NODES_O, i = r / S::NODES_O;
+      const float v = sAcc2[((size_t)i * S::NODES_O + q) * OP + o];
+      if (v != 0.f) atomicAdd(p.gw[2] + ((size_t)o * HID + i) * S::NODES_O + q, v);
+    }
+    if (n_tile > 0) {
+      mbar_wait(&bars[B_GWDONE], (n_tile - 1) & 1);
+      fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int node = half * 128 + tid;
+        float v[HID];
+#pragma unroll
+        for (int g8 = 0; g8 < HID / 8; ++g8) tmem_ld8(tm_lane + P::GW_COL + half * HID + g8 * 8, v + g8 * 8);
+        tmem_wait_ld();
+        if (node < P::KH) {
+          const int i = node / ND, q = node - i * ND;
+#pragma unroll
+          for (int o = 0; o < HID; ++o)
+            if (v[o] != 0.f) atomicAdd(p.gw[1] + ((size_t)o * HID + i) * ND + q, v[o]);
+        }
+      }
+      fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+}  // namespace tc

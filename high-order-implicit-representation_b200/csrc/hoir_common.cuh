@@ -37,9 +37,12 @@ __host__ __device__ inline int piecewise_stride(int kind, int n) {
 }
 
 // id_min = clamp(trunc(((x + half) / length) * segments), 0, segments-1)   (A.3)
+// length == 2 (every layer built through Net): the division is an exact multiplication by 0.5,
+// bit-identical to the IEEE division and ~10x cheaper.
 __device__ __forceinline__ int segment_index(float x, float half, float length, float segf,
                                              int segments) {
-  float t = __fmul_rn(__fdiv_rn(__fadd_rn(x, half), length), segf);
+  const float s = __fadd_rn(x, half);
+  float t = __fmul_rn(length == 2.f ? __fmul_rn(s, 0.5f) : __fdiv_rn(s, length), segf);
   int id = __float2int_rz(t);  // trunc toward zero, saturating; NaN -> 0
   id = min(id, segments - 1);
   id = max(id, 0);

@@ -72,7 +72,7 @@ def test_trainer_steps_match_oracle_training(name, opt):
     # sign-based Lion updates can flip on round-off-sized momenta: compare in absolute lr units
     for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
         if opt == "adam":
-            assert (p.detach().cpu() - q.detach()).abs().max().item() <= 2e-5, k
+            assert (p.detach().cpu() - q.detach()).abs().max().item() <= 5e-5, k
         else:
             frac_off = ((p.detach().cpu() - q.detach()).abs() > 1e-6).float().mean().item()
             assert frac_off <= 1e-3, k
