@@ -1,8 +1,10 @@
 // fused_mlp_tc.cuh -- tensor-core (tcgen05 / TMEM) training kernel for the 40-wide implicit MLP.
 // Included by fused_mlp.cu (uses its FusedParams / SegConst / contract_* helpers).
 //
-// One CTA = 4 sample warps (thread t <-> sample t of a 128-sample tile <-> TMEM lane t) + 1 MMA
-// warp; persistent grid.  The hidden layer's three contractions are densified GEMMs
+// One CTA = 8 sample warps + 1 MMA warp, persistent grid.  A tile is 128 samples; sample s is
+// worked on by a PAIR of threads (s, s + 128) in warps w and w + 4 -- both map to TMEM lane s --
+// each owning 20 of the 40 hidden units (half hf owns units 20 hf .. 20 hf + 19), so that every
+// per-input / per-output loop is split in two and the SM holds 8 warps of CUDA-core work.  The hidden layer's three contractions are densified GEMMs
 // (K = 40 inputs x 5 nodes = 200) on tcgen05.mma kind::tf32 with a 3-pass hi/lo split
 // (A*B + Alo*B + A*Blo, fp32-level accuracy):
 //   FWD  D1[128 x 40]   = Phi1[128 x 200] * W1          A: TMEM (chunks of 8 inputs, double buffered)
@@ -20,7 +22,8 @@
 namespace tc {
 
 constexpr int TS = 128;          // samples per tile
-constexpr int NTHREADS = 160;    // 4 sample warps + 1 MMA warp
+constexpr int NSAMPLE_THREADS = 256;   // 8 sample warps: 2 threads per sample
+constexpr int NTHREADS = 288;          // + 1 MMA warp
 constexpr int APITCH = 41;       // row pitch (floats) of the saved-activation tiles
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -50,7 +53,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bar_samples() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_samples() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// the two warps (w, w + 4) that share 32 samples
+__device__ __forceinline__ void bar_pair(int warp) { asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 3)) : "memory"); }
 
 // shared-memory operand in the 128B_BASE32B layout: element (row r, column c), RS = bytes per 4 rows
 __device__ __forceinline__ uint32_t sw4_off(uint32_t r, uint32_t c, uint32_t RS) {
@@ -85,6 +90,18 @@ __device__ __forceinline__ void tmem_st8(uint32_t addr, const float* v) {
                  "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
                  "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t addr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t addr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j]);
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -92,6 +109,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
                : "r"(addr));
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+// 20 consecutive columns (one half of a 40-wide row); column offsets stay multiples of 4
+__device__ __forceinline__ void tmem_st20(uint32_t addr, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 5; ++q) tmem_st4(addr + 4 * q, v + 4 * q);
+}
+__device__ __forceinline__ void tmem_ld20(uint32_t addr, float* v) {
+#pragma unroll
+  for (int q = 0; q < 5; ++q) tmem_ld4(addr + 4 * q, v + 4 * q);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -101,10 +127,13 @@ __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(_
 template <class S>
 struct TcPlan {
   static constexpr int HID = S::HID, ND = S::NODES_H, KH = HID * ND;       // 40, 5, 200
-  static constexpr int CH_IN = 8, CH_K = CH_IN * ND, NCH = HID / CH_IN;    // 8 inputs = 40 K-columns per FWD chunk
-  static constexpr int KP = (KH + 31) / 32 * 32;                            // 224: W1 columns (node) padded to atoms
+  static constexpr int HH = HID / 2;                                       // hidden units owned by one thread of a pair
+  static constexpr int QI = 4, CH_IN = 2 * QI, NCH = HH / QI;              // FWD chunk: 4 inputs of each half
+  static constexpr int HK = QI * ND, CH_K = 2 * HK;                        // 20 K-columns per half, 40 per chunk
+  static constexpr int KP = (KH + 31) / 32 * 32;                            // 224: W1 columns padded to atoms
   static constexpr int TN = (KH + 15) / 16 * 16;                            // 208: N of the GX product
   static constexpr int UNIT = 16, NUNIT = TS / UNIT;                        // GW: samples per smem unit
+  static constexpr int GPITCH = 44;                                         // layer-0 dL/dy tile [s][44]
   // TMEM columns
   static constexpr int D1_COL = 0, FA_COL = 64, G_COL = 64, T_COL = 224, GW_COL = 432;
   // shared memory (bytes)
@@ -113,26 +142,76 @@ struct TcPlan {
   static constexpr uint32_t U_RS = 256 / 32 * 512, U_BYTES = UNIT / 4 * U_RS;           // 4096, 16384
   static constexpr uint32_t A_BYTES = TS * APITCH * 4;                                  // 20992
   static constexpr uint32_t W2_BYTES = S::WO * 4;
+  static constexpr uint32_t X_BYTES = 2 * TS * 4 * 4;                                   // pair exchange slots
   static constexpr uint32_t OFF_W1R = 0, OFF_W1L = OFF_W1R + W1_BYTES, OFF_GTR = OFF_W1L + W1_BYTES,
                             OFF_GTL = OFF_GTR + GT_BYTES, OFF_U = OFF_GTL + GT_BYTES,   // [2][raw|lo]
                             OFF_A1 = OFF_U + 4 * U_BYTES, OFF_A2 = OFF_A1 + A_BYTES, OFF_W2 = OFF_A2 + A_BYTES,
-                            OFF_ACC2 = OFF_W2 + W2_BYTES, OFF_BAR = OFF_ACC2 + W2_BYTES, SMEM_BYTES = OFF_BAR + 256;
+                            OFF_ACC2 = OFF_W2 + W2_BYTES, OFF_X = OFF_ACC2 + W2_BYTES, OFF_BAR = OFF_X + X_BYTES,
+                            SMEM_BYTES = OFF_BAR + 256;
+  static constexpr uint32_t G0_BYTES = TS * GPITCH * 4;                                 // aliases A1 (+ start of A2)
   static_assert(S::KIND == HOIR_CONTINUOUS && S::N == 3 && S::SEGH == 2 && S::SEGO == 2 && S::NH == 1, "tensor path: C2 family");
-  static_assert(HID % CH_IN == 0 && HID % 8 == 0 && CH_K % 8 == 0 && KH <= 256, "tensor path shape");
+  static_assert(HID == 40 && HH % QI == 0 && HK % 4 == 0 && CH_K % 8 == 0 && KH <= 256, "tensor path shape");
   static_assert(FA_COL + 4 * CH_K <= T_COL && T_COL + TN <= GW_COL && GW_COL + 2 * HID <= 512, "TMEM plan");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan");
-  static_assert(S::IN * 16 * TS <= A_BYTES, "layer-0 records alias the A2 tile");
+  static_assert(G0_BYTES + S::IN * 16 * TS <= 2 * A_BYTES, "layer-0 dL/dw tiles alias A1/A2");
+  // K-column of node 0 of hidden-layer input i: chunk c = (i % 20) / 4 holds [half 0: 4 inputs | half 1: 4 inputs]
+  __host__ __device__ static constexpr int kbase(int i) { return ((i % HH) / QI) * CH_K + (i / HH) * HK + (i % QI) * ND; }
 };
 
 enum { B_FFULL0 = 0, B_FFULL1, B_FEMPTY0, B_FEMPTY1, B_D1FULL, B_D1EMPTY, B_GFULL, B_TFULL, B_GWDONE,
        B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_COUNT };
 
+// y[O] += sum_j l[j] * W[j * PITCH + 0..O)
+template <int N, int O, int PITCH, bool GLOBAL>
+__device__ __forceinline__ void contract_fwd_p(const float* __restrict__ wrow, const float* l, float* __restrict__ acc) {
+  static_assert(O % 4 == 0 && PITCH % 4 == 0, "vector width");
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float4* wp = reinterpret_cast<const float4*>(wrow + j * PITCH);
+#pragma unroll
+    for (int q = 0; q < O / 4; ++q) {
+      const float4 w = GLOBAL ? __ldg(wp + q) : wp[q];
+      acc[4 * q + 0] = fmaf(l[j], w.x, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(l[j], w.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(l[j], w.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(l[j], w.w, acc[4 * q + 3]);
+    }
+  }
+}
+
+// MaxAbsNormalization of a 40-wide row split over a thread pair (20 values each); first index wins ties.
+template <int W>
+__device__ __forceinline__ void maxabs_pair(float* v, int hf, float eps, float* xs, const float* xo, int warp,
+                                            float& inv_d, int& kidx) {
+  float m = -1.f, vk = 0.f;
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const float a = fabsf(v[i]);
+    if (a > m) { m = a; k = i; vk = v[i]; }
+  }
+  int kk = hf * W + k;
+  kk |= vk > 0.f ? 0 : (vk < 0.f ? 0x10000 : 0x20000);
+  xs[0] = m;
+  xs[1] = __int_as_float(kk);
+  bar_pair(warp);
+  const float mo = xo[0];
+  const int ko = __float_as_int(xo[1]);
+  bar_pair(warp);
+  const bool other = (mo > m) || (mo == m && hf == 1);
+  m = other ? mo : m;
+  kidx = other ? ko : kk;
+  inv_d = __fdiv_rn(1.f, __fadd_rn(m, eps));
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] *= inv_d;
+}
+__device__ __forceinline__ float kidx_sign(int kidx) { return (kidx & 0x10000) ? -1.f : ((kidx & 0x20000) ? 0.f : 1.f); }
+
 template <class S>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedParams p) {
   using P = TcPlan<S>;
-  constexpr int N = S::N, IN = S::IN, HID = S::HID, OUT = S::OUT, HP = S::HP, OP = S::OP, ND = P::ND;
+  constexpr int N = S::N, IN = S::IN, HID = S::HID, OUT = S::OUT, HP = S::HP, OP = S::OP, ND = P::ND, HH = P::HH;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint32_t tmem_base_s;
   uint8_t* sW1R = smem + P::OFF_W1R;
   uint8_t* sW1L = smem + P::OFF_W1L;
   uint8_t* sGTR = smem + P::OFF_GTR;
@@ -142,27 +221,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
   float* sA2 = reinterpret_cast<float*>(smem + P::OFF_A2);
   float* sW2 = reinterpret_cast<float*>(smem + P::OFF_W2);
   float* sAcc2 = reinterpret_cast<float*>(smem + P::OFF_ACC2);
+  float* sX = reinterpret_cast<float*>(smem + P::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (uniform datapath)
 
   // ---- prologue: TMEM, barriers, weights -------------------------------------------------
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(&bars[B_FFULL0], 128); mbar_init(&bars[B_FFULL1], 128);
+    mbar_init(&bars[B_FFULL0], NSAMPLE_THREADS); mbar_init(&bars[B_FFULL1], NSAMPLE_THREADS);
     mbar_init(&bars[B_FEMPTY0], 1);  mbar_init(&bars[B_FEMPTY1], 1);
-    mbar_init(&bars[B_D1FULL], 1);   mbar_init(&bars[B_D1EMPTY], 128);
-    mbar_init(&bars[B_GFULL], 128);  mbar_init(&bars[B_TFULL], 1);   mbar_init(&bars[B_GWDONE], 1);
-    mbar_init(&bars[B_UFULL0], 128); mbar_init(&bars[B_UFULL1], 128);
+    mbar_init(&bars[B_D1FULL], 1);   mbar_init(&bars[B_D1EMPTY], NSAMPLE_THREADS);
+    mbar_init(&bars[B_GFULL], NSAMPLE_THREADS);  mbar_init(&bars[B_TFULL], 1);   mbar_init(&bars[B_GWDONE], 1);
+    mbar_init(&bars[B_UFULL0], NSAMPLE_THREADS); mbar_init(&bars[B_UFULL1], NSAMPLE_THREADS);
     mbar_init(&bars[B_UEMPTY0], 1);  mbar_init(&bars[B_UEMPTY1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   {
-    // hidden-layer weights: packed [i][node][HP] -> smem rows = o, cols = i*ND + node (raw and tf32 residual)
+    // hidden-layer weights: packed [i][node][HP] -> smem rows = o, cols = kbase(i) + node (raw and tf32 residual)
     const float* w1 = p.packed + p.off[1];
     for (uint32_t k = tid; k < (uint32_t)(P::W1_BYTES / 4); k += NTHREADS) {
       reinterpret_cast<float*>(sW1R)[k] = 0.f;
@@ -171,9 +252,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     for (uint32_t k = tid; k < (uint32_t)(4 * P::U_BYTES / 4); k += NTHREADS) reinterpret_cast<float*>(sU)[k] = 0.f;
     __syncthreads();
     for (int k = tid; k < P::KH * HID; k += NTHREADS) {
-      const int o = k % HID, col = k / HID;
-      const float v = __ldg(w1 + (size_t)col * HP + o);
-      const uint32_t off = sw4_off(o, col, P::W1_RS);
+      const int o = k % HID, r = k / HID, i = r / ND, q = r - i * ND;
+      const float v = __ldg(w1 + (size_t)r * HP + o);
+      const uint32_t off = sw4_off(o, P::kbase(i) + q, P::W1_RS);
       *reinterpret_cast<float*>(sW1R + off) = v;
       *reinterpret_cast<float*>(sW1L + off) = tf32_lo(v);
     }
@@ -184,10 +265,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = *tmem_base_s;
   const long long tiles = (p.B + TS - 1) / TS;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =========================== MMA warp ===================================================
     const uint32_t leader = elect_one();
     constexpr uint32_t ID_FWD = make_idesc(128, HID, 0, 0);        // A: TMEM (K-major), B: W1 K-major
@@ -264,16 +345,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     }
   } else {
     // =========================== sample warps ===============================================
+    const int hf = warp >> 2;                         // which 20 hidden units this thread owns
+    const int s = tid & (TS - 1);                     // sample slot == TMEM lane
     const SegConst sc0 = {p.seg0, S::STRIDE, (float)p.seg0, 1.f / (float)p.seg0};
-    const float* w0 = p.packed + p.off[0];
+    const float* w0 = p.packed + p.off[0] + hf * HH;
     const LagrangeTable& lag = p.lag;
-    const uint32_t tm_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    float* a1 = sA1 + tid * APITCH;
-    float* a2 = sA2 + tid * APITCH;
+    const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* a1 = sA1 + s * APITCH;
+    float* a2 = sA2 + s * APITCH;
+    float* xs = sX + (hf * TS + s) * 4;
+    const float* xo = sX + ((hf ^ 1) * TS + s) * 4;
     float loss_local = 0.f;
     uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
-      const long long b = tile * TS + tid;
+      const long long b = tile * TS + s;
       const bool live = b < p.B;
       float x0[IN];
 #pragma unroll
@@ -286,13 +371,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
           hoir::mesh_position(p.mesh, p.mesh.first_pixel + b, x0, IN / 2);
         }
       }
-      // ---- layer 0 (FFMA, weights through L1)
-      float h[HID];
+      // ---- layer 0 (FFMA, weights through L1): this thread's 20 outputs
+      float h[HH];
       float4 rec0[IN];
       float inv_d0 = 1.f, inv_d1 = 1.f;
       int kidx0 = 0, kidx1 = 0;
 #pragma unroll
-      for (int o = 0; o < HID; ++o) h[o] = 0.f;
+      for (int o = 0; o < HH; ++o) h[o] = 0.f;
 #pragma unroll
       for (int i = 0; i < IN; ++i) {
         int id;
@@ -301,67 +386,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         else locate<false>(x0[i], sc0, id, xi);
         hoir::lagrange<N>(lag.X, lag.D, xi, l);
         const int base0 = id * S::STRIDE;
-        contract_fwd<N, HID, HP, true>(w0 + ((size_t)i * p.nodes0 + base0) * HP, l, h);
+        contract_fwd_p<N, HH, HP, true>(w0 + ((size_t)i * p.nodes0 + base0) * HP, l, h);
         rec0[i] = make_float4(__int_as_float(base0), l[0], l[1], l[2]);
       }
-      if (p.normalize) maxabs_fwd<HID>(h, p.norm_eps, inv_d0, kidx0);
+      if (p.normalize) maxabs_pair<HH>(h, hf, p.norm_eps, xs, xo, warp, inv_d0, kidx0);
 #pragma unroll
-      for (int i = 0; i < HID; ++i) a1[i] = h[i];
-      // ---- hidden layer forward on the tensor cores: stage Phi1 chunks into TMEM
+      for (int j = 0; j < HH; ++j) a1[hf * HH + j] = h[j];
+      // ---- hidden layer forward on the tensor cores: stage this thread's 4 inputs of every chunk into TMEM
       for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
         const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
         mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);
         fence_after();
-        float v[P::CH_K];
+        float v[P::HK], lo[P::HK];
 #pragma unroll
-        for (int k = 0; k < P::CH_IN; ++k) {
-          const float x = a1[c * P::CH_IN + k];
+        for (int m = 0; m < P::QI; ++m) {
+          const float x = a1[hf * HH + c * P::QI + m];
           int id;
           float xi, l[N];
           locate2(x, id, xi);
           hoir::lagrange<N>(lag.X, lag.D, xi, l);
-          v[k * ND + 0] = id ? 0.f : l[0];
-          v[k * ND + 1] = id ? 0.f : l[1];
-          v[k * ND + 2] = id ? l[0] : l[2];
-          v[k * ND + 3] = id ? l[1] : 0.f;
-          v[k * ND + 4] = id ? l[2] : 0.f;
+          v[m * ND + 0] = id ? 0.f : l[0];
+          v[m * ND + 1] = id ? 0.f : l[1];
+          v[m * ND + 2] = id ? l[0] : l[2];
+          v[m * ND + 3] = id ? l[1] : 0.f;
+          v[m * ND + 4] = id ? l[2] : 0.f;
         }
-        const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K;
 #pragma unroll
-        for (int g8 = 0; g8 < P::CH_K / 8; ++g8) {
-          float lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) lo[j] = tf32_lo(v[g8 * 8 + j]);
-          tmem_st8(col + g8 * 8, v + g8 * 8);
-          tmem_st8(col + P::CH_K + g8 * 8, lo);
-        }
+        for (int j = 0; j < P::HK; ++j) lo[j] = tf32_lo(v[j]);
+        const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K + hf * P::HK;
+        tmem_st20(col, v);
+        tmem_st20(col + P::CH_K, lo);
         tmem_wait_st();
         fence_before();
         mbar_arrive(&bars[B_FFULL0 + buf]);
       }
-      // ---- D1 epilogue: hidden pre-activation -> MaxAbs -> a2
+      // ---- D1 epilogue: hidden pre-activation (own 20 columns) -> MaxAbs -> a2
       mbar_wait(&bars[B_D1FULL], n_tile & 1);
       fence_after();
-#pragma unroll
-      for (int g8 = 0; g8 < HID / 8; ++g8) tmem_ld8(tm_lane + P::D1_COL + g8 * 8, h + g8 * 8);
+      tmem_ld20(tm_lane + P::D1_COL + hf * HH, h);
       tmem_wait_ld();
       fence_before();
       mbar_arrive(&bars[B_D1EMPTY]);
-      if (p.normalize) maxabs_fwd<HID>(h, p.norm_eps, inv_d1, kidx1);
+      if (p.normalize) maxabs_pair<HH>(h, hf, p.norm_eps, xs, xo, warp, inv_d1, kidx1);
 #pragma unroll
-      for (int i = 0; i < HID; ++i) a2[i] = h[i];
-      // ---- output layer forward (FFMA), loss, dL/dy
-      float yo[OUT], gy[OUT];
-#pragma unroll
-      for (int o = 0; o < OUT; ++o) yo[o] = 0.f;
+      for (int j = 0; j < HH; ++j) a2[hf * HH + j] = h[j];
+      // ---- output layer forward (FFMA) over own 20 inputs, pair sum, loss, dL/dy
+      float yo[4] = {0.f, 0.f, 0.f, 0.f}, gy[OUT];
 #pragma unroll 4
-      for (int i = 0; i < HID; ++i) {
+      for (int j = 0; j < HH; ++j) {
+        const int i = hf * HH + j;
         int id;
         float xi, l[N];
         locate2(a2[i], id, xi);
         hoir::lagrange<N>(lag.X, lag.D, xi, l);
         contract_fwd<N, OUT, OP, false>(sW2 + ((size_t)i * S::NODES_O + id * S::STRIDE) * OP, l, yo);
       }
+      *reinterpret_cast<float4*>(xs) = make_float4(yo[0], yo[1], yo[2], 0.f);
+      bar_pair(warp);
+      {
+        const float4 o4 = *reinterpret_cast<const float4*>(xo);
+        yo[0] += o4.x; yo[1] += o4.y; yo[2] += o4.z;
+      }
+      bar_pair(warp);
 #pragma unroll
       for (int o = 0; o < OUT; ++o) gy[o] = 0.f;
       if (live) {
@@ -380,16 +466,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
               t = __ldg(static_cast<const float*>(p.target) + b * OUT + o);
             }
             const float diff = yo[o] - t;
-            loss_local = fmaf(diff, diff, loss_local);
+            if (hf == 0) loss_local = fmaf(diff, diff, loss_local);
             gy[o] = 2.f * diff * p.loss_scale;
           }
         }
       }
-      // ---- output layer backward (FFMA): dL/da2 and dL/dw2 (warp reduce-scatter, smem accumulators)
-      float g[HID];
+      // ---- output layer backward (FFMA) over own 20 inputs: dL/da2 and dL/dw2
+      float g[HH];
       float dot = 0.f;
 #pragma unroll 2
-      for (int i = 0; i < HID; ++i) {
+      for (int j = 0; j < HH; ++j) {
+        const int i = hf * HH + j;
         const float x = a2[i];
         int id;
         float xi, l[N], d[N], t[N];
@@ -398,12 +485,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         contract_bwd<N, OUT, OP>(sW2 + ((size_t)i * S::NODES_O + id * S::STRIDE) * OP, gy, t);
         float gx = 0.f;
 #pragma unroll
-        for (int j = 0; j < N; ++j) gx = fmaf(d[j], t[j], gx);
+        for (int q = 0; q < N; ++q) gx = fmaf(d[q], t[q], gx);
         gx *= 2.f;                                   // d xi / d x = segments
         dot = fmaf(gx, x, dot);
         a2[i] = gx;                                  // a2 now holds dL/da2
         // densified basis row x dL/dy: 5 x 3 products (+1 pad), reduce-scatter over the warp
-        float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+        const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
         float r[16];
 #pragma unroll
         for (int k = 0; k < ND; ++k)
@@ -411,17 +498,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
           for (int o = 0; o < OUT; ++o) r[k * OUT + o] = c5[k] * gy[o];
         r[15] = 0.f;
 #pragma unroll
-        for (int s = 16, n = 8; s >= 2; s >>= 1, n >>= 1) {
-          const bool up = (lane & s) != 0;
+        for (int st = 16, n = 8; st >= 2; st >>= 1, n >>= 1) {
+          const bool up = (lane & st) != 0;
 #pragma unroll
           for (int m = 0; m < n; ++m) {
             const float send = up ? r[m] : r[m + n];
             const float keep = up ? r[m + n] : r[m];
-            r[m] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            r[m] = keep + __shfl_xor_sync(0xffffffffu, send, st);
           }
         }
         r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-        // lane holds element e = bit-reversed-ish index: reconstruct which of the 16 it owns
         if ((lane & 1) == 0) {
           const int e = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
           if (e < ND * OUT) {
@@ -431,35 +517,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         }
       }
       if (p.normalize) {
-        const int k = kidx1 & 0xffff;
-        const float sgn = (kidx1 & 0x10000) ? -1.f : ((kidx1 & 0x20000) ? 0.f : 1.f);
+        xs[0] = dot;
+        bar_pair(warp);
+        dot += xo[0];
+        bar_pair(warp);
+        const int k = (kidx1 & 0xffff) - hf * HH;
+        const float sgn = kidx_sign(kidx1);
 #pragma unroll
-        for (int i = 0; i < HID; ++i) {
-          float gi = a2[i];
-          if (i == k) gi -= sgn * dot;
-          g[i] = gi * inv_d1;
+        for (int j = 0; j < HH; ++j) {
+          float gi = a2[hf * HH + j];
+          if (j == k) gi -= sgn * dot;
+          g[j] = gi * inv_d1;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < HID; ++i) g[i] = a2[i];
+        for (int j = 0; j < HH; ++j) g[j] = a2[hf * HH + j];
       }
-      // ---- stage G: TMEM (A operand of GX) and smem G^T (B operand of GW)
+      // ---- stage G (own 20 units): TMEM (A operand of GX) and smem G^T (B operand of GW)
       if (n_tile > 0) mbar_wait(&bars[B_GWDONE], (n_tile - 1) & 1);   // previous tile's GW done with G^T
       fence_after();
       {
-        float lo[HID];
+        float lo[HH];
 #pragma unroll
-        for (int o = 0; o < HID; ++o) lo[o] = tf32_lo(g[o]);
+        for (int j = 0; j < HH; ++j) lo[j] = tf32_lo(g[j]);
+        const uint32_t col = tm_lane + P::G_COL + hf * HH;
+        tmem_st20(col, g);
+        tmem_st20(col + HID, lo);
 #pragma unroll
-        for (int g8 = 0; g8 < HID / 8; ++g8) {
-          tmem_st8(tm_lane + P::G_COL + g8 * 8, g + g8 * 8);
-          tmem_st8(tm_lane + P::G_COL + HID + g8 * 8, lo + g8 * 8);
-        }
-#pragma unroll
-        for (int o = 0; o < HID; ++o) {
-          const uint32_t off = sw4_off(o, tid, P::GT_RS);
-          *reinterpret_cast<float*>(sGTR + off) = g[o];
-          *reinterpret_cast<float*>(sGTL + off) = lo[o];
+        for (int j = 0; j < HH; ++j) {
+          const uint32_t off = sw4_off(hf * HH + j, s, P::GT_RS);
+          *reinterpret_cast<float*>(sGTR + off) = g[j];
+          *reinterpret_cast<float*>(sGTL + off) = lo[j];
         }
       }
       tmem_wait_st();
@@ -467,116 +555,145 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       fence_before();
       mbar_arrive(&bars[B_GFULL]);
       bar_samples();     // every sample's a1 row is visible to the GW staging below
-      // ---- GW staging: units of 16 samples, (sample, input) items spread over the 128 threads
+      // ---- GW staging: units of 16 samples, (sample, input) items spread over the 256 threads
       for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
         const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
         mbar_wait(&bars[B_UEMPTY0 + buf], ph ^ 1);
         uint8_t* ur = sU + buf * 2 * P::U_BYTES;
         uint8_t* ul = ur + P::U_BYTES;
 #pragma unroll
-        for (int j = 0; j < P::UNIT * HID / 128; ++j) {
-          const int f = tid + 128 * j;
-          const int sl = f / HID, i = f - sl * HID;
-          const float x = sA1[(u * P::UNIT + sl) * APITCH + i];
-          int id;
-          float xi, l[N];
-          locate2(x, id, xi);
-          hoir::lagrange<N>(lag.X, lag.D, xi, l);
-          const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+        for (int j = 0; j < (P::UNIT * HID + NSAMPLE_THREADS - 1) / NSAMPLE_THREADS; ++j) {
+          const int f = tid + NSAMPLE_THREADS * j;
+          if (f < P::UNIT * HID) {
+            const int sl = f / HID, i = f - sl * HID;
+            const float x = sA1[(u * P::UNIT + sl) * APITCH + i];
+            int id;
+            float xi, l[N];
+            locate2(x, id, xi);
+            hoir::lagrange<N>(lag.X, lag.D, xi, l);
+            const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+            const int kb = P::kbase(i);
 #pragma unroll
-          for (int k = 0; k < ND; ++k) {
-            const uint32_t off = sw4_off(sl, i * ND + k, P::U_RS);
-            *reinterpret_cast<float*>(ur + off) = c5[k];
-            *reinterpret_cast<float*>(ul + off) = tf32_lo(c5[k]);
+            for (int k = 0; k < ND; ++k) {
+              const uint32_t off = sw4_off(sl, kb + k, P::U_RS);
+              *reinterpret_cast<float*>(ur + off) = c5[k];
+              *reinterpret_cast<float*>(ul + off) = tf32_lo(c5[k]);
+            }
           }
         }
         fence_async_smem();
         mbar_arrive(&bars[B_UFULL0 + buf]);
       }
-      // ---- T epilogue: dL/da1 = slope * sum_j l'_j * T[5 i + window + j]
+      // ---- T epilogue (own 20 inputs): dL/da1 = slope * sum_j l'_j * T[kbase(i) + window + j]
       mbar_wait(&bars[B_TFULL], n_tile & 1);
       fence_after();
       dot = 0.f;
 #pragma unroll
       for (int c = 0; c < P::NCH; ++c) {
-        float t[P::CH_K];
-#pragma unroll
-        for (int g8 = 0; g8 < P::CH_K / 8; ++g8) tmem_ld8(tm_lane + P::T_COL + c * P::CH_K + g8 * 8, t + g8 * 8);
+        float t[P::HK];
+        const uint32_t col = tm_lane + P::T_COL + c * P::CH_K + hf * P::HK;
+        tmem_ld20(col, t);
         tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < P::CH_IN; ++k) {
-          const int i = c * P::CH_IN + k;
-          const float x = a1[i];
+        for (int m = 0; m < P::QI; ++m) {
+          const float x = a1[hf * HH + c * P::QI + m];
           int id;
           float xi, l[N], d[N];
           locate2(x, id, xi);
           hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
-          const float t0 = id ? t[k * ND + 2] : t[k * ND + 0];
-          const float t1 = id ? t[k * ND + 3] : t[k * ND + 1];
-          const float t2 = id ? t[k * ND + 4] : t[k * ND + 2];
-          float gx = fmaf(d[2], t2, fmaf(d[1], t1, d[0] * t0)) * 2.f;
+          const float t0 = id ? t[m * ND + 2] : t[m * ND + 0];
+          const float t1 = id ? t[m * ND + 3] : t[m * ND + 1];
+          const float t2 = id ? t[m * ND + 4] : t[m * ND + 2];
+          const float gx = fmaf(d[2], t2, fmaf(d[1], t1, d[0] * t0)) * 2.f;
           dot = fmaf(gx, x, dot);
-          g[i] = gx;
+          g[c * P::QI + m] = gx;
         }
       }
       fence_before();
       if (p.normalize) {
-        const int k = kidx0 & 0xffff;
-        const float sgn = (kidx0 & 0x10000) ? -1.f : ((kidx0 & 0x20000) ? 0.f : 1.f);
+        xs[0] = dot;
+        bar_pair(warp);
+        dot += xo[0];
+        bar_pair(warp);
+        const int k = (kidx0 & 0xffff) - hf * HH;
+        const float sgn = kidx_sign(kidx0);
 #pragma unroll
-        for (int i = 0; i < HID; ++i) {
-          float gi = g[i];
-          if (i == k) gi -= sgn * dot;
-          g[i] = gi * inv_d0;
+        for (int j = 0; j < HH; ++j) {
+          float gi = g[j];
+          if (j == k) gi -= sgn * dot;
+          g[j] = gi * inv_d0;
         }
       }
-      // ---- layer 0 dL/dw: owners (input, output) walk the tile (run-merged global atomics)
+      // ---- layer 0 dL/dw: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
       bar_samples();                                  // everyone is done reading sA1 / sA2
+      {
+        float* sG0 = sA1;                             // [s][GPITCH] dL/d(layer-0 output)
+        float4* sRec = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sA1) + P::G0_BYTES);   // [IN][TS]
 #pragma unroll
-      for (int o = 0; o < HID; ++o) a1[o] = g[o];     // sA1 <- dL/d(layer-0 output)
+        for (int q = 0; q < HH / 4; ++q)
+          *reinterpret_cast<float4*>(sG0 + s * P::GPITCH + hf * HH + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+        if (hf == 0) {
 #pragma unroll
-      for (int i = 0; i < IN; ++i) reinterpret_cast<float4*>(sA2)[(size_t)i * TS + tid] = rec0[i];
-      bar_samples();
-      for (int pr = tid; pr < IN * HID; pr += 128) {
-        const int i = pr / HID, o = pr - i * HID;
-        float* dst = p.gw[0] + ((size_t)o * IN + i) * p.nodes0;
-        const float4* rp = reinterpret_cast<const float4*>(sA2) + (size_t)i * TS;
-        int cur = -1;
-        float acc[N] = {0.f, 0.f, 0.f};
-#pragma unroll 4
-        for (int s = 0; s < TS; ++s) {
-          const float4 r = rp[s];
-          const float gv = sA1[s * APITCH + o];
-          const int base = __float_as_int(r.x);
-          if (base != cur) {
-            if (cur >= 0) {
-#pragma unroll
-              for (int j = 0; j < N; ++j)
-                if (acc[j] != 0.f) atomicAdd(dst + cur + j, acc[j]);
-            }
-            cur = base;
-#pragma unroll
-            for (int j = 0; j < N; ++j) acc[j] = 0.f;
-          }
-          acc[0] = fmaf(r.y, gv, acc[0]);
-          acc[1] = fmaf(r.z, gv, acc[1]);
-          acc[2] = fmaf(r.w, gv, acc[2]);
+          for (int i = 0; i < IN; ++i) sRec[(size_t)i * TS + s] = rec0[i];
         }
-        if (cur >= 0) {
+        bar_samples();
+        constexpr int NOQ = HID / 4, NGRP = NSAMPLE_THREADS / (IN * NOQ), SPG = (TS + NGRP - 1) / NGRP;
+        if (tid < NGRP * IN * NOQ) {
+          const int grp = tid / (IN * NOQ), pr = tid - grp * (IN * NOQ), i = pr / NOQ, oq = pr - i * NOQ;
+          const int s0 = grp * SPG, s1 = (s0 + SPG < TS) ? s0 + SPG : TS;
+          float* dst = p.gw[0] + ((size_t)(4 * oq) * IN + i) * p.nodes0;
+          const size_t ostride = (size_t)IN * p.nodes0;
+          const float4* rp = sRec + (size_t)i * TS;
+          int cur = -1;
+          float acc[4][N];
 #pragma unroll
-          for (int j = 0; j < N; ++j)
-            if (acc[j] != 0.f) atomicAdd(dst + cur + j, acc[j]);
+          for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int q = 0; q < N; ++q) acc[o][q] = 0.f;
+          for (int ss = s0; ss < s1; ++ss) {
+            const float4 r = rp[ss];
+            const float4 gv = *reinterpret_cast<const float4*>(sG0 + ss * P::GPITCH + 4 * oq);
+            const int base = __float_as_int(r.x);
+            if (base != cur) {
+              if (cur >= 0) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+#pragma unroll
+                  for (int q = 0; q < N; ++q)
+                    if (acc[o][q] != 0.f) atomicAdd(dst + o * ostride + cur + q, acc[o][q]);
+              }
+              cur = base;
+#pragma unroll
+              for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int q = 0; q < N; ++q) acc[o][q] = 0.f;
+            }
+            const float gq[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              acc[o][0] = fmaf(r.y, gq[o], acc[o][0]);
+              acc[o][1] = fmaf(r.z, gq[o], acc[o][1]);
+              acc[o][2] = fmaf(r.w, gq[o], acc[o][2]);
+            }
+          }
+          if (cur >= 0) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+              for (int q = 0; q < N; ++q)
+                if (acc[o][q] != 0.f) atomicAdd(dst + o * ostride + cur + q, acc[o][q]);
+          }
         }
       }
       bar_samples();                                  // owners done before the next tile reuses sA1 / sA2
     }
     // ---- flush: loss, dL/dw2 (smem), dL/dw1 (TMEM accumulators)
-    if (p.gy_ext == nullptr) {
-      const float s = hoir::warp_sum(loss_local) * p.loss_scale;
-      if (lane == 0 && s != 0.f) atomicAdd(p.loss_sum, s);
+    if (p.gy_ext == nullptr && hf == 0) {
+      const float sum = hoir::warp_sum(loss_local) * p.loss_scale;
+      if (lane == 0 && sum != 0.f) atomicAdd(p.loss_sum, sum);
     }
     bar_samples();
-    for (int k = tid; k < HID * S::NODES_O * OUT; k += 128) {
+    for (int k = tid; k < HID * S::NODES_O * OUT; k += NSAMPLE_THREADS) {
       const int o = k % OUT, r = k / OUT, q = r % S::NODES_O, i = r / S::NODES_O;
       const float v = sAcc2[((size_t)i * S::NODES_O + q) * OP + o];
       if (v != 0.f) atomicAdd(p.gw[2] + ((size_t)o * HID + i) * S::NODES_O + q, v);
@@ -584,25 +701,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     if (n_tile > 0) {
       mbar_wait(&bars[B_GWDONE], (n_tile - 1) & 1);
       fence_after();
+      // accumulator row R = hf * 128 + s holds K-column R: chunk c = R / 40, half (R % 40) / 20, input 4c + ..., node R % 5
+      const int R = hf * 128 + s;
+      float v[HID];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int node = half * 128 + tid;
-        float v[HID];
+      for (int g8 = 0; g8 < HID / 8; ++g8) tmem_ld8(tm_lane + P::GW_COL + hf * HID + g8 * 8, v + g8 * 8);
+      tmem_wait_ld();
+      if (R < P::KH) {
+        const int c = R / P::CH_K, rem = R - c * P::CH_K, hfi = rem / P::HK, r2 = rem - hfi * P::HK;
+        const int i = hfi * HH + c * P::QI + r2 / ND, q = r2 % ND;
 #pragma unroll
-        for (int g8 = 0; g8 < HID / 8; ++g8) tmem_ld8(tm_lane + P::GW_COL + half * HID + g8 * 8, v + g8 * 8);
-        tmem_wait_ld();
-        if (node < P::KH) {
-          const int i = node / ND, q = node - i * ND;
-#pragma unroll
-          for (int o = 0; o < HID; ++o)
-            if (v[o] != 0.f) atomicAdd(p.gw[1] + ((size_t)o * HID + i) * ND + q, v[o]);
-        }
+        for (int o = 0; o < HID; ++o)
+          if (v[o] != 0.f) atomicAdd(p.gw[1] + ((size_t)o * HID + i) * ND + q, v[o]);
       }
       fence_before();
     }
   }
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 }  // namespace tc
