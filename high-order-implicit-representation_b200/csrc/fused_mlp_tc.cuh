@@ -357,27 +357,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     const float* xo = sX + ((hf ^ 1) * TS + s) * 4;
     float loss_local = 0.f;
     uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
-      const long long b = tile * TS + s;
-      const bool live = b < p.B;
+    // layer 0 (FFMA, weights through L1) of one tile: this thread's 20 outputs, MaxAbs over the pair
+    auto layer0 = [&](long long tile_, float* h_, float4* rec_, float& inv_d_, int& kidx_) {
+      const long long b_ = tile_ * TS + s;
       float x0[IN];
 #pragma unroll
       for (int i = 0; i < IN; ++i) x0[i] = 0.f;
-      if (live) {
+      if (b_ < p.B) {
         if (p.x != nullptr) {
 #pragma unroll
-          for (int i = 0; i < IN; ++i) x0[i] = __ldg(p.x + b * IN + i);
+          for (int i = 0; i < IN; ++i) x0[i] = __ldg(p.x + b_ * IN + i);
         } else {
-          hoir::mesh_position(p.mesh, p.mesh.first_pixel + b, x0, IN / 2);
+          hoir::mesh_position(p.mesh, p.mesh.first_pixel + b_, x0, IN / 2);
         }
       }
-      // ---- layer 0 (FFMA, weights through L1): this thread's 20 outputs
-      float h[HH];
-      float4 rec0[IN];
-      float inv_d0 = 1.f, inv_d1 = 1.f;
-      int kidx0 = 0, kidx1 = 0;
 #pragma unroll
-      for (int o = 0; o < HH; ++o) h[o] = 0.f;
+      for (int o = 0; o < HH; ++o) h_[o] = 0.f;
 #pragma unroll
       for (int i = 0; i < IN; ++i) {
         int id;
@@ -386,12 +381,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         else locate<false>(x0[i], sc0, id, xi);
         hoir::lagrange<N>(lag.X, lag.D, xi, l);
         const int base0 = id * S::STRIDE;
-        contract_fwd_p<N, HH, HP, true>(w0 + ((size_t)i * p.nodes0 + base0) * HP, l, h);
-        rec0[i] = make_float4(__int_as_float(base0), l[0], l[1], l[2]);
+        contract_fwd_p<N, HH, HP, true>(w0 + ((size_t)i * p.nodes0 + base0) * HP, l, h_);
+        rec_[i] = make_float4(__int_as_float(base0), l[0], l[1], l[2]);
       }
-      if (p.normalize) maxabs_pair<HH>(h, hf, p.norm_eps, xs, xo, warp, inv_d0, kidx0);
+      inv_d_ = 1.f;
+      kidx_ = 0;
+      if (p.normalize) maxabs_pair<HH>(h_, hf, p.norm_eps, xs, xo, warp, inv_d_, kidx_);
+    };
+    float hN[HH];
+    float4 recN[IN];
+    float invN = 1.f;
+    int kidxN = 0;
+    float acc2[HH];                                   // dL/dw2 partial sums owned by this lane (see below)
 #pragma unroll
-      for (int j = 0; j < HH; ++j) a1[hf * HH + j] = h[j];
+    for (int j = 0; j < HH; ++j) acc2[j] = 0.f;
+    if ((long long)blockIdx.x < tiles) layer0(blockIdx.x, hN, recN, invN, kidxN);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+      const long long b = tile * TS + s;
+      const bool live = b < p.B;
+      float h[HH];
+      float4 rec0[IN];
+      float inv_d1 = 1.f;
+      int kidx1 = 0;
+      const float inv_d0 = invN;
+      const int kidx0 = kidxN;
+#pragma unroll
+      for (int i = 0; i < IN; ++i) rec0[i] = recN[i];
+#pragma unroll
+      for (int j = 0; j < HH; ++j) a1[hf * HH + j] = hN[j];
       // ---- hidden layer forward on the tensor cores: stage this thread's 4 inputs of every chunk into TMEM
       for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
         const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
@@ -420,6 +437,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         fence_before();
         mbar_arrive(&bars[B_FFULL0 + buf]);
       }
+      // ---- while the tensor pipe finishes D1: layer 0 of the NEXT tile (kept in registers)
+      if (tile + gridDim.x < tiles) layer0(tile + gridDim.x, hN, recN, invN, kidxN);
       // ---- D1 epilogue: hidden pre-activation (own 20 columns) -> MaxAbs -> a2
       mbar_wait(&bars[B_D1FULL], n_tile & 1);
       fence_after();
@@ -474,7 +493,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       // ---- output layer backward (FFMA) over own 20 inputs: dL/da2 and dL/dw2
       float g[HH];
       float dot = 0.f;
-#pragma unroll 2
+#pragma unroll
       for (int j = 0; j < HH; ++j) {
         const int i = hf * HH + j;
         const float x = a2[i];
@@ -508,13 +527,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
           }
         }
         r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-        if ((lane & 1) == 0) {
-          const int e = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-          if (e < ND * OUT) {
-            const int k = e / OUT, o = e - k * OUT;
-            atomicAdd(&sAcc2[((size_t)i * S::NODES_O + k) * OP + o], r[0]);
-          }
-        }
+        acc2[j] += r[0];   // this lane's element e(lane) of input i, summed over the warp's 32 samples
       }
       if (p.normalize) {
         xs[0] = dot;
@@ -556,7 +569,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       mbar_arrive(&bars[B_GFULL]);
       bar_samples();     // every sample's a1 row is visible to the GW staging below
       // ---- GW staging: units of 16 samples, (sample, input) items spread over the 256 threads
+      dot = 0.f;
+#pragma unroll
       for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
+        // T epilogue chunk c = u - 2 (own 4 inputs): dL/da1 = slope * sum_j l'_j * T[kbase(i) + window + j];
+        // interleaved with the staging so that the waits on the tensor pipe are filled with work
+        if (u >= 2 && u - 2 < P::NCH) {
+          const int c = u - 2;
+          if (c == 0) {
+            mbar_wait(&bars[B_TFULL], n_tile & 1);
+            fence_after();
+          }
+          float t[P::HK];
+          tmem_ld20(tm_lane + P::T_COL + c * P::CH_K + hf * P::HK, t);
+          tmem_wait_ld();
+#pragma unroll
+          for (int m = 0; m < P::QI; ++m) {
+            const float x = a1[hf * HH + c * P::QI + m];
+            int id;
+            float xi, l[N], d[N];
+            locate2(x, id, xi);
+            hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
+            const float t0 = id ? t[m * ND + 2] : t[m * ND + 0];
+            const float t1 = id ? t[m * ND + 3] : t[m * ND + 1];
+            const float t2 = id ? t[m * ND + 4] : t[m * ND + 2];
+            const float gx = fmaf(d[2], t2, fmaf(d[1], t1, d[0] * t0)) * 2.f;
+            dot = fmaf(gx, x, dot);
+            g[c * P::QI + m] = gx;
+          }
+        }
         const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
         mbar_wait(&bars[B_UEMPTY0 + buf], ph ^ 1);
         uint8_t* ur = sU + buf * 2 * P::U_BYTES;
@@ -583,31 +624,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         }
         fence_async_smem();
         mbar_arrive(&bars[B_UFULL0 + buf]);
-      }
-      // ---- T epilogue (own 20 inputs): dL/da1 = slope * sum_j l'_j * T[kbase(i) + window + j]
-      mbar_wait(&bars[B_TFULL], n_tile & 1);
-      fence_after();
-      dot = 0.f;
-#pragma unroll
-      for (int c = 0; c < P::NCH; ++c) {
-        float t[P::HK];
-        const uint32_t col = tm_lane + P::T_COL + c * P::CH_K + hf * P::HK;
-        tmem_ld20(col, t);
-        tmem_wait_ld();
-#pragma unroll
-        for (int m = 0; m < P::QI; ++m) {
-          const float x = a1[hf * HH + c * P::QI + m];
-          int id;
-          float xi, l[N], d[N];
-          locate2(x, id, xi);
-          hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
-          const float t0 = id ? t[m * ND + 2] : t[m * ND + 0];
-          const float t1 = id ? t[m * ND + 3] : t[m * ND + 1];
-          const float t2 = id ? t[m * ND + 4] : t[m * ND + 2];
-          const float gx = fmaf(d[2], t2, fmaf(d[1], t1, d[0] * t0)) * 2.f;
-          dot = fmaf(gx, x, dot);
-          g[c * P::QI + m] = gx;
-        }
       }
       fence_before();
       if (p.normalize) {
@@ -692,11 +708,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       const float sum = hoir::warp_sum(loss_local) * p.loss_scale;
       if (lane == 0 && sum != 0.f) atomicAdd(p.loss_sum, sum);
     }
-    bar_samples();
-    for (int k = tid; k < HID * S::NODES_O * OUT; k += NSAMPLE_THREADS) {
-      const int o = k % OUT, r = k / OUT, q = r % S::NODES_O, i = r / S::NODES_O;
-      const float v = sAcc2[((size_t)i * S::NODES_O + q) * OP + o];
-      if (v != 0.f) atomicAdd(p.gw[2] + ((size_t)o * HID + i) * S::NODES_O + q, v);
+    {
+      // after the reduce-scatter lane L holds element e(L) = (node k, output o) of every input it walked
+      const int e = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+      if ((lane & 1) == 0 && e < ND * OUT) {
+        const int k = e / OUT, o = e - k * OUT;
+#pragma unroll
+        for (int j = 0; j < HH; ++j)
+          if (acc2[j] != 0.f) atomicAdd(p.gw[2] + ((size_t)o * HID + hf * HH + j) * S::NODES_O + k, acc2[j]);
+      }
     }
     if (n_tile > 0) {
       mbar_wait(&bars[B_GWDONE], (n_tile - 1) & 1);
