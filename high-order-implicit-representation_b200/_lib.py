@@ -52,6 +52,7 @@ class HoirUnsupported(RuntimeError):
 _EXPORTS = {
     "hoir_last_error": (C.c_char_p, []),
     "hoir_version": (C.c_int, []),
+    "hoir_shutdown": (C.c_int, []),
     "hoir_layer_nodes": (C.c_int, [C.POINTER(LayerDesc)]),
     "hoir_layer_forward": (C.c_int, [C.POINTER(LayerDesc), C.c_longlong, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),

@@ -70,6 +70,12 @@ struct FusedParams {
   int seg0, nodes0, pow2_0;
   int normalize;
   float norm_eps;
+  // two-pass layer-0 dL/dw for incoherent batches (generic x, large B): the main kernel streams
+  // dL/d(layer-0 output) rows, (window, basis) records and segment ids to this workspace and a
+  // segment-owner kernel accumulates them without atomics on the hot addresses.  NULL: in-kernel.
+  float* ws_g0;              // [B][hid]
+  float4* ws_rec;            // [IN][B]
+  unsigned short* ws_seg;    // [IN][B]
   LagrangeTable lag;
 };
 
@@ -564,6 +570,126 @@ bool mlp_desc_ok(const hoir_mlp_desc* m) {
   return true;
 }
 
+// Second pass of the layer-0 dL/dw for incoherent batches.  CTA (chunk of 4096 samples, input i): counting
+// sort of the chunk's samples by segment in shared memory, then every warp reduces whole segments
+// (lane <-> outputs o and o + 32, basis record broadcast, dL/dy row coalesced) in registers and issues ONE
+// atomicAdd per owned weight and segment present in the chunk: ~12 atomics per sample instead of 480,
+// balanced for any distribution of the inputs.
+constexpr int GW0_CHUNK = 4096, GW0_MAXSEG = 1024, GW0_BLOCK = 64;
+template <int N>
+__global__ void __launch_bounds__(256) gw0_chunk_kernel(long long B, int IN, int hid, int seg0, int stride, int nodes0,
+                                                        const unsigned short* __restrict__ ws_seg,
+                                                        const float4* __restrict__ ws_rec, const float* __restrict__ ws_g0,
+                                                        float* __restrict__ gw0) {
+  __shared__ unsigned int s_ent[GW0_CHUNK];          // sorted by segment: (segment << 16) | sample offset
+  __shared__ int s_cnt[GW0_MAXSEG], s_pos[GW0_MAXSEG];
+  const int i = blockIdx.y;
+  const long long b0 = (long long)blockIdx.x * GW0_CHUNK;
+  const int n = (int)((B - b0) < GW0_CHUNK ? (B - b0) : GW0_CHUNK);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned short* seg = ws_seg + (size_t)i * B + b0;
+  const float4* rec = ws_rec + (size_t)i * B + b0;
+  for (int k = threadIdx.x; k < seg0; k += 256) s_cnt[k] = 0;
+  __syncthreads();
+  // histogram with warp-aggregated shared atomics (coherent batches put a whole warp into one bin)
+  for (int t0 = warp * 32; t0 < n; t0 += 256) {
+    const int t = t0 + lane;
+    const int key = t < n ? (int)seg[t] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[key], __popc(peers));
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int running = 0;
+    for (int base = 0; base < seg0; base += 32) {
+      const int v = base + lane < seg0 ? s_cnt[base + lane] : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (base + lane < seg0) s_pos[base + lane] = running + incl - v;
+      running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  __syncthreads();
+  for (int t0 = warp * 32; t0 < n; t0 += 256) {
+    const int t = t0 + lane;
+    const int key = t < n ? (int)seg[t] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (key >= 0 && lane == leader) base = atomicAdd(&s_pos[key], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (key >= 0) s_ent[base + __popc(peers & ((1u << lane) - 1u))] = ((unsigned)key << 16) | (unsigned)t;
+  }
+  __syncthreads();
+  // every warp reduces blocks of 64 consecutive sorted entries; a segment change inside a block flushes
+  for (int k0 = warp * GW0_BLOCK; k0 < n; k0 += 8 * GW0_BLOCK) {
+    const int k1 = k0 + GW0_BLOCK < n ? k0 + GW0_BLOCK : n;
+    int cur = (int)(s_ent[k0] >> 16);
+    float acc[N][2];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[j][0] = acc[j][1] = 0.f;
+    auto flush = [&](int sg) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        if (lane < hid && acc[j][0] != 0.f) atomicAdd(gw0 + ((size_t)lane * IN + i) * nodes0 + sg * stride + j, acc[j][0]);
+        if (lane + 32 < hid && acc[j][1] != 0.f)
+          atomicAdd(gw0 + ((size_t)(lane + 32) * IN + i) * nodes0 + sg * stride + j, acc[j][1]);
+        acc[j][0] = acc[j][1] = 0.f;
+      }
+    };
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+      const unsigned e = s_ent[k];
+      const int t = (int)(e & 0xffffu), sg = (int)(e >> 16);
+      const float4 rc = __ldg(rec + t);
+      const float* grow = ws_g0 + (size_t)(b0 + t) * hid;
+      const float g0 = __ldg(grow + lane);
+      const float g1 = lane + 32 < hid ? __ldg(grow + 32 + lane) : 0.f;
+      if (sg != cur) {
+        flush(cur);
+        cur = sg;
+      }
+      const float l[3] = {rc.y, rc.z, rc.w};
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        acc[j][0] = fmaf(l[j], g0, acc[j][0]);
+        acc[j][1] = fmaf(l[j], g1, acc[j][1]);
+      }
+    }
+    flush(cur);
+  }
+}
+
+// library-owned workspace of the two-pass path, one per device, grown on demand
+struct Workspace {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+Workspace g_ws[16];
+
+int get_workspace(size_t bytes, void** out) {
+  int dev = 0;
+  HOIR_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return hoir_set_error(HOIR_EUNSUPPORTED, "device index >= 16", "get_workspace");
+  Workspace& w = g_ws[dev];
+  if (w.bytes < bytes) {
+    if (w.ptr) {
+      HOIR_CHECK_CUDA(cudaDeviceSynchronize());
+      HOIR_CHECK_CUDA(cudaFree(w.ptr));
+      w.ptr = nullptr;
+      w.bytes = 0;
+    }
+    HOIR_CHECK_CUDA(cudaMalloc(&w.ptr, bytes));
+    w.bytes = bytes;
+  }
+  *out = w.ptr;
+  return HOIR_OK;
+}
+
 struct FusedEntry {
   int kind, n, in, hid, out, nh, segh, sego;
   void (*fwd)(const FusedParams);
@@ -741,12 +867,31 @@ extern "C" int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const fl
   p.loss_sum = loss_sum;
   p.loss_scale = loss_scale;
   static const bool no_tc = getenv("HOIR_NO_TC") != nullptr;   // A/B switch: FFMA-only kernel
+  static const bool no_2p = getenv("HOIR_NO_TWOPASS") != nullptr;
   if (e->train_tc != nullptr && !no_tc) {
+    const int in_f = m->layers[0].in_features, hid = m->layers[0].out_features;
+    const bool two_pass = x != nullptr && B >= 32768 && !no_2p && p.seg0 <= GW0_MAXSEG && hid <= 64 && m->layers[0].n == 3;
+    if (two_pass) {
+      const size_t b_al = ((size_t)B + 63) & ~(size_t)63;
+      const size_t n_g0 = b_al * hid * sizeof(float), n_rec = b_al * in_f * sizeof(float4), n_seg = b_al * in_f * sizeof(unsigned short);
+      void* ws = nullptr;
+      if (int err = get_workspace(n_g0 + n_rec + n_seg, &ws)) return err;
+      p.ws_g0 = static_cast<float*>(ws);
+      p.ws_rec = reinterpret_cast<float4*>(static_cast<char*>(ws) + n_g0);
+      p.ws_seg = reinterpret_cast<unsigned short*>(static_cast<char*>(ws) + n_g0 + n_rec);
+    }
     HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->train_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_tc));
     const long long tiles = (B + tc::TS - 1) / tc::TS;
     const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
     e->train_tc<<<grid, tc::NTHREADS, e->smem_tc, (cudaStream_t)stream>>>(p);
     HOIR_CHECK_CUDA(cudaGetLastError());
+    if (two_pass) {
+      const int stride = hoir::piecewise_stride(m->layers[0].kind, m->layers[0].n);
+      const dim3 grid2((unsigned)((B + GW0_CHUNK - 1) / GW0_CHUNK), (unsigned)in_f);
+      gw0_chunk_kernel<3><<<grid2, 256, 0, (cudaStream_t)stream>>>(B, in_f, hid, p.seg0, stride, p.nodes0, p.ws_seg,
+                                                                   p.ws_rec, p.ws_g0, p.gw[0]);
+      HOIR_CHECK_CUDA(cudaGetLastError());
+    }
     return HOIR_OK;
   }
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_train));
@@ -754,5 +899,20 @@ extern "C" int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const fl
   const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
   e->train<<<grid, BT, e->smem_train, (cudaStream_t)stream>>>(p);
   HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+extern "C" int hoir_shutdown(void) {
+  for (int d = 0; d < 16; ++d) {
+    if (g_ws[d].ptr) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(d);
+      cudaFree(g_ws[d].ptr);
+      cudaSetDevice(cur);
+      g_ws[d].ptr = nullptr;
+      g_ws[d].bytes = 0;
+    }
+  }
   return HOIR_OK;
 }

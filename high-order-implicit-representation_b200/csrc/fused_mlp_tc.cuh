@@ -640,7 +640,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
           g[j] = gi * inv_d0;
         }
       }
-      // ---- layer 0 dL/dw: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
+      // ---- layer 0 dL/dw.  Incoherent batches (two-pass mode): stream dL/dy rows, basis records and segment
+      //      ids to the workspace; gw0_owner_kernel finishes the job.
+      if (p.ws_g0 != nullptr) {
+        if (live) {
+          float4* dstg = reinterpret_cast<float4*>(p.ws_g0 + b * HID + hf * HH);
+#pragma unroll
+          for (int q = 0; q < HH / 4; ++q) dstg[q] = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+          if (hf == 0) {
+#pragma unroll
+            for (int i = 0; i < IN; ++i) {
+              p.ws_rec[(size_t)i * p.B + b] = rec0[i];
+              p.ws_seg[(size_t)i * p.B + b] = (unsigned short)(__float_as_int(rec0[i].x) / S::STRIDE);
+            }
+          }
+        }
+        bar_samples();   // all GW staging reads of sA1 are done before the next tile overwrites it
+        continue;
+      }
+      // ---- otherwise: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
       bar_samples();                                  // everyone is done reading sA1 / sA2
       {
         float* sG0 = sA1;                             // [s][GPITCH] dL/d(layer-0 output)

@@ -177,23 +177,58 @@ class FusedTrainer:
 
 
 class HostBatchStepper:
-    """End-to-end step through host memory: pinned host (x, y) -> H2D -> fused step -> loss D2H.
+    """End-to-end training through host memory: pinned host (x, y) -> H2D -> fused step -> loss D2H.
     This is the reference-facing shape of a training step (a DataLoader batch arriving from host
-    memory, /root/reference/high_order_implicit_representation/single_image_dataset.py:312-320)."""
+    memory, /root/reference/high_order_implicit_representation/single_image_dataset.py:312-320).
+
+    Two-deep pipeline: ``step(x, y)`` enqueues the H2D copy of this batch on a copy stream and its
+    training step on the compute stream, and returns the loss of the PREVIOUS step (None for the
+    first call); ``flush()`` returns the last one.  The copy of batch k+1 overlaps the compute of
+    batch k, like the reference's pinned, non-blocking DataLoader feed."""
 
     def __init__(self, trainer: FusedTrainer, batch: int):
         self.trainer = trainer
         dev = trainer.device
-        self.x_dev = torch.empty((batch, trainer.in_features), device=dev, dtype=torch.float32)
-        self.y_dev = torch.empty((batch, trainer.out_features), device=dev, dtype=torch.float32)
-        self.loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
-        self.h2d_bytes = self.x_dev.numel() * 4 + self.y_dev.numel() * 4
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.bufs = [(torch.empty((batch, trainer.in_features), device=dev, dtype=torch.float32),
+                      torch.empty((batch, trainer.out_features), device=dev, dtype=torch.float32))
+                     for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.loss_ready = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+        self.pending = None
+        self.h2d_bytes = sum(t.numel() * 4 for t in self.bufs[0])
         self.d2h_bytes = 4
 
-    def step(self, x_host: Tensor, y_host: Tensor) -> float:
-        self.x_dev.copy_(x_host, non_blocking=True)
-        self.y_dev.copy_(y_host, non_blocking=True)
-        loss = self.trainer.train_step(self.x_dev, self.y_dev)
-        self.loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream(self.trainer.device).synchronize()
-        return float(self.loss_host[0])
+    def step(self, x_host: Tensor, y_host: Tensor) -> Optional[float]:
+        slot = self.k & 1
+        xd, yd = self.bufs[slot]
+        compute = torch.cuda.current_stream(self.trainer.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.k >= 2:
+                self.copy_stream.wait_event(self.consumed[slot])   # the step that last read this slot is done
+            xd.copy_(x_host, non_blocking=True)
+            yd.copy_(y_host, non_blocking=True)
+            self.copied[slot].record(self.copy_stream)
+        compute.wait_event(self.copied[slot])
+        loss = self.trainer.train_step(xd, yd)
+        self.consumed[slot].record(compute)
+        self.loss_host[slot].copy_(loss, non_blocking=True)
+        self.loss_ready[slot].record(compute)
+        prev = self._collect()
+        self.pending = slot
+        self.k += 1
+        return prev
+
+    def _collect(self) -> Optional[float]:
+        if self.pending is None:
+            return None
+        self.loss_ready[self.pending].synchronize()
+        return float(self.loss_host[self.pending][0])
+
+    def flush(self) -> Optional[float]:
+        out = self._collect()
+        self.pending = None
+        return out

@@ -91,6 +91,9 @@ enum hoir_target_kind {
 
 const char* hoir_last_error(void);
 int hoir_version(void);
+/* frees the library-owned per-device workspace (two-pass layer-0 gradient of large generic batches);
+ * one training step may be in flight per device at a time because of that workspace */
+int hoir_shutdown(void);
 /* number of weight nodes per (out, in) link for a layer descriptor, or -1 */
 int hoir_layer_nodes(const hoir_layer_desc* d);
 
