@@ -4,7 +4,9 @@ jloveric/high-order-implicit-representation.  Importable as ``hoir_b200`` (see t
 from . import _lib, config, parallel, spec  # noqa: F401
 from ._lib import HoirUnsupported, build  # noqa: F401
 from .config import Config, apply_overrides, images_config, to_cfg  # noqa: F401
+from .datasets import image_neighborhood_dataset, image_to_dataset, neighborhood_gather  # noqa: F401
 from .engine import FusedTrainer, HostBatchStepper  # noqa: F401
+from .rendering import generate_sequence, neighborhood_sample_generator, render_image  # noqa: F401
 from .layers import (FourierSeries, HighOrderLayer, MaxAbsNormalization,  # noqa: F401
                      PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial,
                      high_order_fc_layers, segment_index)

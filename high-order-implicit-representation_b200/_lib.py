@@ -65,6 +65,13 @@ _EXPORTS = {
     "hoir_maxabs_backward": (C.c_int, [C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "hoir_mesh_positions": (C.c_int, [C.POINTER(MeshDesc), C.c_longlong, C.c_void_p, C.c_void_p]),
+    "hoir_neighborhood_patches": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hoir_neighborhood_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
+    "hoir_neighborhood_fold": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "hoir_mlp_fused_supported": (C.c_int, [C.POINTER(MlpDesc)]),
     "hoir_mlp_packed_size": (C.c_longlong, [C.POINTER(MlpDesc)]),
     "hoir_mlp_packed_offset": (C.c_longlong, [C.POINTER(MlpDesc), C.c_int]),

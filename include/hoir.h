@@ -117,6 +117,25 @@ int hoir_maxabs_backward(long long B, int width, float eps, const float* x, cons
 /* x[B][2*rotations] for pixels first_pixel .. first_pixel+B-1 (bit-identical to the host mesh) */
 int hoir_mesh_positions(const hoir_mesh_desc* mesh, long long B, float* x, void* stream);
 
+/* ---- neighborhood interpolator: patch gather / fold ------------------------------------------
+ * image [C][H][W] fp32 in [-1, 1].  Patches are the T x T windows (T = width + 2*outside) of the image
+ * reflection-padded by `pad`, taken every `stride` pixels in row-major order; patch p yields
+ *   features[p][c*(T*T - w*w) + e]   e = rank of the cell among the donut cells, row-major
+ *   targets [p][c*w*w + kh*w + kw]   the inner w x w block
+ * (image_neighborhood_dataset, /root/reference/high_order_implicit_representation/
+ *  single_image_dataset.py:83-141).  features / targets may be NULL. */
+long long hoir_neighborhood_patches(int H, int W, int width, int outside, int stride, int pad,
+                                    int* n_rows, int* n_cols);
+int hoir_neighborhood_gather(const float* image, int C, int H, int W, int width, int outside, int stride,
+                             int pad, long long first_patch, long long count, float* features,
+                             float* targets, void* stream);
+/* predictions[p][C*w*w] of the stride-w patches of the image padded by 2*outside + width ->
+ * out = alpha*prev + (1-alpha)*fold(predictions) cropped to [C][H][W]  (prev NULL: out = fold);
+ * neighborhood_sample_generator / generate_sequence,
+ * /root/reference/high_order_implicit_representation/rendering.py:76-95,119 */
+int hoir_neighborhood_fold(const float* predictions, int C, int H, int W, int width, int outside,
+                           float alpha, const float* prev_image, float* out_image, void* stream);
+
 /* ---- fused whole-network path ---------------------------------------------------------------
  * Packed weights: one flat fp32 buffer, layer l at float offset hoir_mlp_packed_offset(l) with
  * layout [in][node][out_padded] (out_padded = out rounded up to 4).  hoir_mlp_pack fills it from
