@@ -664,32 +664,6 @@ __global__ void __launch_bounds__(256) gw0_chunk_kernel(long long B, int IN, int
   }
 }
 
-// library-owned workspace of the two-pass path, one per device, grown on demand
-struct Workspace {
-  void* ptr = nullptr;
-  size_t bytes = 0;
-};
-Workspace g_ws[16];
-
-int get_workspace(size_t bytes, void** out) {
-  int dev = 0;
-  HOIR_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16) return hoir_set_error(HOIR_EUNSUPPORTED, "device index >= 16", "get_workspace");
-  Workspace& w = g_ws[dev];
-  if (w.bytes < bytes) {
-    if (w.ptr) {
-      HOIR_CHECK_CUDA(cudaDeviceSynchronize());
-      HOIR_CHECK_CUDA(cudaFree(w.ptr));
-      w.ptr = nullptr;
-      w.bytes = 0;
-    }
-    HOIR_CHECK_CUDA(cudaMalloc(&w.ptr, bytes));
-    w.bytes = bytes;
-  }
-  *out = w.ptr;
-  return HOIR_OK;
-}
-
 struct FusedEntry {
   int kind, n, in, hid, out, nh, segh, sego;
   void (*fwd)(const FusedParams);
@@ -875,7 +849,7 @@ extern "C" int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const fl
       const size_t b_al = ((size_t)B + 63) & ~(size_t)63;
       const size_t n_g0 = b_al * hid * sizeof(float), n_rec = b_al * in_f * sizeof(float4), n_seg = b_al * in_f * sizeof(unsigned short);
       void* ws = nullptr;
-      if (int err = get_workspace(n_g0 + n_rec + n_seg, &ws)) return err;
+      if (int err = hoir_get_workspace(0, n_g0 + n_rec + n_seg, &ws)) return err;
       p.ws_g0 = static_cast<float*>(ws);
       p.ws_rec = reinterpret_cast<float4*>(static_cast<char*>(ws) + n_g0);
       p.ws_seg = reinterpret_cast<unsigned short*>(static_cast<char*>(ws) + n_g0 + n_rec);
@@ -902,17 +876,3 @@ extern "C" int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const fl
   return HOIR_OK;
 }
 
-extern "C" int hoir_shutdown(void) {
-  for (int d = 0; d < 16; ++d) {
-    if (g_ws[d].ptr) {
-      int cur = 0;
-      cudaGetDevice(&cur);
-      cudaSetDevice(d);
-      cudaFree(g_ws[d].ptr);
-      cudaSetDevice(cur);
-      g_ws[d].ptr = nullptr;
-      g_ws[d].bytes = 0;
-    }
-  }
-  return HOIR_OK;
-}

@@ -12,6 +12,54 @@ int hoir_set_error(int code, const char* msg, const char* where) {
 }
 
 extern "C" const char* hoir_last_error(void) { return g_err; }
+
+namespace {
+struct Workspace {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+Workspace g_ws[16][2];
+}  // namespace
+
+int hoir_get_workspace(int slot, size_t bytes, void** out) {
+  int dev = 0;
+  HOIR_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16 || slot < 0 || slot >= 2)
+    return hoir_set_error(HOIR_EUNSUPPORTED, "device index >= 16", "hoir_get_workspace");
+  Workspace& w = g_ws[dev][slot];
+  if (w.bytes < bytes) {
+    if (w.ptr) {
+      HOIR_CHECK_CUDA(cudaDeviceSynchronize());
+      HOIR_CHECK_CUDA(cudaFree(w.ptr));
+      w.ptr = nullptr;
+      w.bytes = 0;
+    }
+    const size_t grow = bytes + bytes / 4;
+    HOIR_CHECK_CUDA(cudaMalloc(&w.ptr, grow));
+    w.bytes = grow;
+  }
+  *out = w.ptr;
+  return HOIR_OK;
+}
+
+void hoir_free_workspaces() {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 16; ++d)
+    for (int s = 0; s < 2; ++s)
+      if (g_ws[d][s].ptr) {
+        cudaSetDevice(d);
+        cudaFree(g_ws[d][s].ptr);
+        g_ws[d][s].ptr = nullptr;
+        g_ws[d][s].bytes = 0;
+      }
+  cudaSetDevice(cur);
+}
+
+extern "C" int hoir_shutdown(void) {
+  hoir_free_workspaces();
+  return HOIR_OK;
+}
 extern "C" int hoir_version(void) { return HOIR_VERSION; }
 
 // Chebyshev-Lobatto nodes the way the package builds them: -cos(k*pi/(n-1))

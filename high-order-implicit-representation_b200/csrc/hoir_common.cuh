@@ -15,6 +15,9 @@
   } while (0)
 
 int hoir_set_error(int code, const char* msg, const char* where);
+// library-owned per-device scratch (slot 0: two-pass layer-0 gradient, slot 1: packed layer weights)
+int hoir_get_workspace(int slot, size_t bytes, void** out);
+void hoir_free_workspaces();
 
 // Lagrange nodes X_j (fp32, exactly the host table of the package) and
 // D_j = 1 / prod_{m != j} (X_j - X_m) (computed in double on the host).

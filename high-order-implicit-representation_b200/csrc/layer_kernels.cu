@@ -47,75 +47,197 @@ __device__ __forceinline__ void eval_record(const LayerParams& p, float x, float
   rec[1] = slope * psign;
 }
 
+// ---- weights re-laid out as [in][node][out_pad4] so that a sample's node window x all outputs is one
+//      contiguous run: lanes that walk the outputs read coalesced float4s.
+__global__ void layer_pack_kernel(const float* __restrict__ w, float* __restrict__ packed, int in_f,
+                                  int out_f, int nodes, int out_pad) {
+  const long long total = (long long)in_f * nodes * out_pad;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total;
+       k += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(k % out_pad);
+    const long long r = k / out_pad;
+    const int q = (int)(r % nodes), i = (int)(r / nodes);
+    packed[k] = o < out_f ? w[((size_t)o * in_f + i) * nodes + q] : 0.f;
+  }
+}
+
+// forward: work item = (sample, 4 outputs)
 __global__ void __launch_bounds__(256)
 layer_fwd_kernel(LayerParams p, long long B, int TB, const float* __restrict__ x,
-                 const float* __restrict__ w, float* __restrict__ y) {
+                 const float* __restrict__ wp, float* __restrict__ y) {
   extern __shared__ float smem[];
-  const int recw = p.n + 2;
+  const int recw = p.n + 2, OP = (p.out_f + 3) & ~3, OPQ = OP / 4;
   for (long long tile = blockIdx.x; tile * TB < B; tile += gridDim.x) {
     const long long b0 = tile * TB;
     const int nb = (int)min((long long)TB, B - b0);
     for (int it = threadIdx.x; it < nb * p.in_f; it += blockDim.x)
       eval_record(p, x[b0 * p.in_f + it], smem + (size_t)it * recw, false);
     __syncthreads();
-    for (int it = threadIdx.x; it < nb * p.out_f; it += blockDim.x) {
-      const int bl = it / p.out_f, o = it - bl * p.out_f;
+    for (int it = threadIdx.x; it < nb * OPQ; it += blockDim.x) {
+      const int bl = it / OPQ, oq = it - bl * OPQ;
       const float* rec = smem + (size_t)bl * p.in_f * recw;
-      const float* wo = w + (size_t)o * p.in_f * p.nodes;
-      float acc = 0.f;
-      for (int i = 0; i < p.in_f; ++i, rec += recw, wo += p.nodes) {
-        const float* wi = wo + __float_as_int(rec[0]);
-        for (int j = 0; j < p.n; ++j) acc = fmaf(rec[2 + j], __ldg(wi + j), acc);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < p.in_f; ++i, rec += recw) {
+        const float4* wr = reinterpret_cast<const float4*>(wp + ((size_t)i * p.nodes + __float_as_int(rec[0])) * OP) + oq;
+        for (int j = 0; j < p.n; ++j) {
+          const float4 w4 = __ldg(wr + (size_t)j * OPQ);
+          const float v = rec[2 + j];
+          acc.x = fmaf(v, w4.x, acc.x); acc.y = fmaf(v, w4.y, acc.y);
+          acc.z = fmaf(v, w4.z, acc.z); acc.w = fmaf(v, w4.w, acc.w);
+        }
       }
-      y[(b0 + bl) * p.out_f + o] = acc * p.rescale;
+      float* yo = y + (b0 + bl) * p.out_f + 4 * oq;
+      const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+      for (int c = 0; c < 4; ++c)
+        if (4 * oq + c < p.out_f) yo[c] = a4[c] * p.rescale;
     }
     __syncthreads();
   }
 }
 
+// backward: dL/dx per (sample, input); dL/dw by owners (input, 4 outputs) that walk the tile's samples,
+// accumulate the current node window in registers and flush (global atomics) when the window changes.
+template <int NT>
 __global__ void __launch_bounds__(256)
 layer_bwd_kernel(LayerParams p, long long B, int TB, const float* __restrict__ x,
-                 const float* __restrict__ w, const float* __restrict__ gy,
+                 const float* __restrict__ wp, const float* __restrict__ gy,
                  float* __restrict__ gx, float* __restrict__ gw) {
   extern __shared__ float smem[];
-  const int recw = 2 * p.n + 2;
+  const int recw = 2 * p.n + 2, OP = (p.out_f + 3) & ~3, OPQ = OP / 4;
   for (long long tile = blockIdx.x; tile * TB < B; tile += gridDim.x) {
     const long long b0 = tile * TB;
     const int nb = (int)min((long long)TB, B - b0);
+    float* sgy = smem + (((size_t)TB * p.in_f * recw + 3) & ~(size_t)3);   // [TB][OP], zero padded, 16 B aligned
     for (int it = threadIdx.x; it < nb * p.in_f; it += blockDim.x)
       eval_record(p, x[b0 * p.in_f + it], smem + (size_t)it * recw, true);
+    for (int it = threadIdx.x; it < nb * OP; it += blockDim.x) {
+      const int bl = it / OP, o = it - bl * OP;
+      sgy[it] = o < p.out_f ? gy[(b0 + bl) * p.out_f + o] * p.rescale : 0.f;
+    }
     __syncthreads();
     if (gx != nullptr) {
       for (int it = threadIdx.x; it < nb * p.in_f; it += blockDim.x) {
         const int bl = it / p.in_f, i = it - bl * p.in_f;
         const float* rec = smem + (size_t)it * recw;
-        const int base = __float_as_int(rec[0]);
-        const float* g = gy + (b0 + bl) * p.out_f;
+        const float4* g4 = reinterpret_cast<const float4*>(sgy + (size_t)bl * OP);
+        const float4* wr = reinterpret_cast<const float4*>(wp + ((size_t)i * p.nodes + __float_as_int(rec[0])) * OP);
         float acc = 0.f;
-        for (int o = 0; o < p.out_f; ++o) {
-          const float* wi = w + ((size_t)o * p.in_f + i) * p.nodes + base;
-          float t = 0.f;
-          for (int j = 0; j < p.n; ++j) t = fmaf(rec[2 + p.n + j], __ldg(wi + j), t);
-          acc = fmaf(__ldg(g + o), t, acc);
+        for (int j = 0; j < p.n; ++j) {
+          float t0 = 0.f, t1 = 0.f;
+          for (int q = 0; q < OPQ; ++q) {
+            const float4 w4 = __ldg(wr + (size_t)j * OPQ + q);
+            const float4 g = g4[q];
+            t0 = fmaf(g.x, w4.x, fmaf(g.z, w4.z, t0));
+            t1 = fmaf(g.y, w4.y, fmaf(g.w, w4.w, t1));
+          }
+          acc = fmaf(rec[2 + p.n + j], t0 + t1, acc);
         }
-        gx[(b0 + bl) * p.in_f + i] = acc * rec[1] * p.rescale;
+        gx[(b0 + bl) * p.in_f + i] = acc * rec[1];
       }
     }
     if (gw != nullptr) {
-      const int per_b = p.in_f * p.out_f;
-      for (int it = threadIdx.x; it < nb * per_b; it += blockDim.x) {
-        const int bl = it / per_b, r = it - bl * per_b;
-        const int o = r / p.in_f, i = r - o * p.in_f;
-        const float* rec = smem + ((size_t)bl * p.in_f + i) * recw;
-        const int base = __float_as_int(rec[0]);
-        const float g = __ldg(gy + (b0 + bl) * p.out_f + o) * p.rescale;
-        if (g != 0.f) {
-          float* dst = gw + ((size_t)o * p.in_f + i) * p.nodes + base;
-          for (int j = 0; j < p.n; ++j) atomicAdd(dst + j, rec[2 + j] * g);
+      for (int it = threadIdx.x; it < p.in_f * OPQ; it += blockDim.x) {
+        const int i = it / OPQ, oq = it - i * OPQ;
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        int cur = -1;
+        auto flush = [&]() {
+          if (cur < 0) return;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            if (j < p.n) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int o = 4 * oq + c;
+                if (o < p.out_f && acc[j][c] != 0.f) atomicAdd(gw + ((size_t)o * p.in_f + i) * p.nodes + cur + j, acc[j][c]);
+                acc[j][c] = 0.f;
+              }
+            }
+          }
+        };
+        for (int bl = 0; bl < nb; ++bl) {
+          const float* rec = smem + ((size_t)bl * p.in_f + i) * recw;
+          const int base = __float_as_int(rec[0]);
+          if (base != cur) {
+            flush();
+            cur = base;
+          }
+          const float4 g = *reinterpret_cast<const float4*>(sgy + (size_t)bl * OP + 4 * oq);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            if (j < p.n) {
+              const float v = rec[2 + j];
+              acc[j][0] = fmaf(v, g.x, acc[j][0]); acc[j][1] = fmaf(v, g.y, acc[j][1]);
+              acc[j][2] = fmaf(v, g.z, acc[j][2]); acc[j][3] = fmaf(v, g.w, acc[j][3]);
+            }
+          }
         }
+        flush();
       }
     }
     __syncthreads();
+  }
+}
+
+// dL/dw of a layer with MANY node windows (piecewise layers with many segments, e.g. the 216 x 51 x 50
+// first layer of the neighborhood interpolator): CTA = (input i, slice of the batch); each warp keeps a
+// PRIVATE copy of w[:, i, :]'s gradient in shared memory (lanes <-> outputs, no conflicts, no atomics),
+// walks its samples, and the copies are summed and flushed once per CTA.
+template <int NT>
+__global__ void __launch_bounds__(256)
+layer_gw_input_owner_kernel(LayerParams p, long long B, int parts, int nwarps, const float* __restrict__ x,
+                            const float* __restrict__ gy, float* __restrict__ gw) {
+  extern __shared__ float smem[];
+  const int i = blockIdx.x / parts, part = blockIdx.x - i * parts;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slab = p.nodes * p.out_f;
+  for (int k = threadIdx.x; k < nwarps * slab; k += blockDim.x) smem[k] = 0.f;
+  __syncthreads();
+  const long long per = (B + parts - 1) / parts, b_lo = part * per, b_hi = min(B, b_lo + per);
+  float* mine = smem + (size_t)warp * slab;
+  if (warp < nwarps) {
+    for (long long b0 = b_lo + (long long)warp * 32; b0 < b_hi; b0 += (long long)nwarps * 32) {
+      // lane-parallel basis evaluation of 32 samples (independent loads), then a broadcast walk
+      float rec[2 + NT];
+      const long long bl = b0 + lane;
+      rec[0] = __int_as_float(0);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) rec[2 + j] = 0.f;
+      if (bl < b_hi) {
+        float full[2 + HOIR_MAX_N];
+        eval_record(p, __ldg(x + bl * p.in_f + i), full, false);
+        rec[0] = full[0];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          if (j < p.n) rec[2 + j] = full[2 + j];
+      }
+      const int cnt = (int)min((long long)32, b_hi - b0);
+      for (int o0 = 0; o0 < p.out_f; o0 += 32) {        // warp-uniform trip count: the shuffles need every lane
+        const int o = o0 + lane;
+        const bool act = o < p.out_f;
+#pragma unroll 4
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+          const float gv = act ? __ldg(gy + (b0 + sidx) * p.out_f + o) * p.rescale : 0.f;
+          const int base = __shfl_sync(0xffffffffu, __float_as_int(rec[0]), sidx);
+          float* dst = mine + base * p.out_f + (act ? o : 0);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            const float v = __shfl_sync(0xffffffffu, rec[2 + j], sidx);
+            if (act && j < p.n) dst[j * p.out_f] = fmaf(v, gv, dst[j * p.out_f]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < slab; k += blockDim.x) {
+    float v = 0.f;
+    for (int w = 0; w < nwarps; ++w) v += smem[(size_t)w * slab + k];
+    if (v != 0.f) {
+      const int q = k / p.out_f, o = k - q * p.out_f;
+      atomicAdd(gw + ((size_t)o * p.in_f + i) * p.nodes + q, v);
+    }
   }
 }
 
@@ -246,6 +368,19 @@ extern "C" int hoir_layer_nodes(const hoir_layer_desc* d) {
   }
 }
 
+// packed copy of w in the library-owned workspace (slot 1), refreshed per call (w is small)
+static int pack_weights(const LayerParams& p, const float* w, float** packed, cudaStream_t stream) {
+  const int OP = (p.out_f + 3) & ~3;
+  const size_t n = (size_t)p.in_f * p.nodes * OP;
+  void* ws = nullptr;
+  if (int e = hoir_get_workspace(1, n * sizeof(float), &ws)) return e;
+  int grid = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
+  layer_pack_kernel<<<grid, 256, 0, stream>>>(w, static_cast<float*>(ws), p.in_f, p.out_f, p.nodes, OP);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  *packed = static_cast<float*>(ws);
+  return HOIR_OK;
+}
+
 extern "C" int hoir_layer_forward(const hoir_layer_desc* d, long long B, const float* x,
                                   const float* w, float* y, void* stream) {
   LayerParams p;
@@ -256,13 +391,15 @@ extern "C" int hoir_layer_forward(const hoir_layer_desc* d, long long B, const f
   const size_t per_sample = (size_t)p.in_f * (p.n + 2) * sizeof(float);
   if (per_sample > (size_t)kSmemBudget)
     return hoir_set_error(HOIR_EUNSUPPORTED, "in_features*(n+2) exceeds the shared-memory tile", "hoir_layer_forward");
+  float* wp = nullptr;
+  if (int e = pack_weights(p, w, &wp, (cudaStream_t)stream)) return e;
   int TB = (int)min((size_t)64, (size_t)kSmemBudget / per_sample);
   if ((long long)TB > B) TB = (int)B;
   const size_t smem = per_sample * TB;
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
   long long tiles = (B + TB - 1) / TB;
   int grid = (int)min(tiles, (long long)num_sms() * 4);
-  layer_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, B, TB, x, w, y);
+  layer_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, B, TB, x, wp, y);
   HOIR_CHECK_CUDA(cudaGetLastError());
   return HOIR_OK;
 }
@@ -275,16 +412,35 @@ extern "C" int hoir_layer_backward(const hoir_layer_desc* d, long long B, const 
   if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_layer_backward");
   if (B == 0 || (gx == nullptr && gw == nullptr)) return HOIR_OK;
   if (!x || !w || !gy) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_layer_backward");
-  const size_t per_sample = (size_t)p.in_f * (2 * p.n + 2) * sizeof(float);
-  if (per_sample > (size_t)kSmemBudget)
+  const int OP = (p.out_f + 3) & ~3;
+  const size_t per_sample = ((size_t)p.in_f * (2 * p.n + 2) + OP) * sizeof(float);
+  if (per_sample + 16 > (size_t)kSmemBudget)
     return hoir_set_error(HOIR_EUNSUPPORTED, "in_features*(2n+2) exceeds the shared-memory tile", "hoir_layer_backward");
-  int TB = (int)min((size_t)64, (size_t)kSmemBudget / per_sample);
+  float* wp = nullptr;
+  if (gx != nullptr)
+    if (int e = pack_weights(p, w, &wp, (cudaStream_t)stream)) return e;
+  // many node windows and a big batch: dL/dw through the input-owner kernel (no per-sample atomics)
+  const size_t slab = (size_t)p.nodes * p.out_f * sizeof(float);
+  const bool piecewise = p.kind == HOIR_CONTINUOUS || p.kind == HOIR_DISCONTINUOUS;
+  float* gw_tile = gw;
+  if (gw != nullptr && piecewise && p.segments > 8 && B >= 4096 && slab <= 200 * 1024 / 2) {
+    int nwarps = (int)min((size_t)8, (size_t)(200 * 1024) / slab);
+    int parts = max(1, min(64, (num_sms() * 2 + p.in_f - 1) / p.in_f));
+    auto okern = p.n <= 4 ? layer_gw_input_owner_kernel<4> : (p.n <= 8 ? layer_gw_input_owner_kernel<8> : layer_gw_input_owner_kernel<HOIR_MAX_N>);
+    HOIR_CHECK_CUDA(cudaFuncSetAttribute(okern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    okern<<<p.in_f * parts, 256, nwarps * slab, (cudaStream_t)stream>>>(p, B, parts, nwarps, x, gy, gw);
+    HOIR_CHECK_CUDA(cudaGetLastError());
+    gw_tile = nullptr;
+    if (gx == nullptr) return HOIR_OK;
+  }
+  int TB = (int)min((size_t)64, ((size_t)kSmemBudget - 16) / per_sample);
   if ((long long)TB > B) TB = (int)B;
-  const size_t smem = per_sample * TB;
-  HOIR_CHECK_CUDA(cudaFuncSetAttribute(layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  const size_t smem = per_sample * TB + 16;
   long long tiles = (B + TB - 1) / TB;
   int grid = (int)min(tiles, (long long)num_sms() * 4);
-  layer_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, B, TB, x, w, gy, gx, gw);
+  auto kern = p.n <= 4 ? layer_bwd_kernel<4> : (p.n <= 8 ? layer_bwd_kernel<8> : layer_bwd_kernel<HOIR_MAX_N>);
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  kern<<<grid, 256, smem, (cudaStream_t)stream>>>(p, B, TB, x, wp, gy, gx, gw_tile);
   HOIR_CHECK_CUDA(cudaGetLastError());
   return HOIR_OK;
 }

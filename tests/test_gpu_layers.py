@@ -137,3 +137,20 @@ def test_positions_from_mesh_bit_exact(rows, cols, rot):
             assert a.shape == (rows, cols)
             assert torch.equal(a.cpu(), b.to(torch.float32))
             assert torch.equal(c, b)
+
+
+@pytest.mark.parametrize("kind,n,in_f,out_f,seg", [("continuous", 2, 24, 50, 50), ("continuous", 3, 4, 40, 100),
+                                                   ("discontinuous", 3, 5, 33, 17)])
+def test_large_batch_many_segments_gradient(kind, n, in_f, out_f, seg):
+    """B >= 4096 with many segments routes dL/dw through the input-owner kernel (per-warp private accumulators)."""
+    ref, lay = make_layers(kind, n, in_f, out_f, seg)
+    B = 5000
+    g = torch.Generator().manual_seed(B)
+    x = torch.rand(B, in_f, generator=g) * 2.2 - 1.1
+    gy = torch.randn(B, out_f, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref(xr).backward(gy)
+    xc = x.cuda().requires_grad_(True)
+    lay(xc).backward(gy.cuda())
+    assert rel_err(xc.grad, xr.grad) <= 1e-5
+    assert rel_err(lay.w.grad, ref.w.grad) <= 1e-5
