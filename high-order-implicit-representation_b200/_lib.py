@@ -45,6 +45,17 @@ class MeshDesc(C.Structure):
                 ("rot_sum", C.c_float * HOIR_MAX_ROTATIONS)]
 
 
+OPT_KIND = {"adam": 1, "sparse_lion": 2}
+
+
+class OptDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("weight_decay", C.c_float), ("step", C.c_longlong),
+                ("flat_w", C.c_void_p), ("flat_g", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("packed", C.c_void_p), ("loss_out", C.c_void_p),
+                ("keep_grad", C.c_int)]
+
+
 class HoirUnsupported(RuntimeError):
     """The fused whole-network kernel has no instantiation for this network."""
 
@@ -83,6 +94,10 @@ _EXPORTS = {
                                       C.POINTER(MeshDesc), C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_float,
                                       C.c_void_p]),
+    "hoir_mlp_optimizer_tail": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(OptDesc), C.c_void_p]),
+    "hoir_mlp_train_step_fused": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p,
+                                            C.POINTER(MeshDesc), C.c_int, C.c_void_p, C.c_float,
+                                            C.POINTER(OptDesc), C.c_void_p]),
     "hoir_adam_step": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_longlong, C.c_void_p]),

@@ -16,8 +16,11 @@
 //             flushed to HBM once per CTA.  Layer 0 (many segments) merges runs of equal
 //             segment and flushes with global atomics.
 // Algorithm: oracle/hol_oracle.py.
+#include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "hoir_common.cuh"
+#include "opt_tail.cuh"
 
 namespace {
 
@@ -77,6 +80,7 @@ struct FusedParams {
   float4* ws_rec;            // [IN][B]
   unsigned short* ws_seg;    // [IN][B]
   LagrangeTable lag;
+  OptTail tail;              // kind != 0: optimizer tail inside the kernel (behind a grid barrier)
 };
 
 struct SegConst {
@@ -288,7 +292,7 @@ __device__ __forceinline__ void layer_bwd_w(const float* __restrict__ a, const f
             const int o = og + OGRP * m;
             if (o < O) {
               if (ACC_SMEM) gws[((size_t)i * NODES + q) * OPAD + o] += acc[q][m];
-              else if (acc[q][m] != 0.f) atomicAdd(gwg + ((size_t)o * I + i) * NODES + q, acc[q][m]);
+              else if (acc[q][m] != 0.f) hoir::red_add(gwg + ((size_t)o * I + i) * NODES + q, acc[q][m]);
             }
           }
       }
@@ -326,7 +330,7 @@ __device__ __forceinline__ void layer0_bwd_w(const float* __restrict__ rec0,
       if (cur >= 0) {
 #pragma unroll
         for (int j = 0; j < N; ++j)
-          if (a[j] != 0.f) atomicAdd(dst + cur + j, a[j]);
+          if (a[j] != 0.f) hoir::red_add(dst + cur + j, a[j]);
       }
       cur = base;
 #pragma unroll
@@ -339,7 +343,7 @@ __device__ __forceinline__ void layer0_bwd_w(const float* __restrict__ rec0,
   if (cur >= 0) {
 #pragma unroll
     for (int j = 0; j < N; ++j)
-      if (a[j] != 0.f) atomicAdd(dst + cur + j, a[j]);
+      if (a[j] != 0.f) hoir::red_add(dst + cur + j, a[j]);
   }
 }
 
@@ -520,7 +524,7 @@ __global__ void __launch_bounds__(BT, 1) fused_mlp_kernel(const FusedParams p) {
   // ---- flush: loss and the shared-memory dL/dw accumulators (boundary layout [out][in][nodes])
   if (p.gy_ext == nullptr) {
     float s = hoir::warp_sum(loss_local) * p.loss_scale;
-    if ((tid & 31) == 0 && s != 0.f) atomicAdd(p.loss_sum, s);
+    if ((tid & 31) == 0 && s != 0.f) hoir::red_add(p.loss_sum, s);
   }
   if (S::ACC_SMEM) {
     __syncthreads();
@@ -529,16 +533,17 @@ __global__ void __launch_bounds__(BT, 1) fused_mlp_kernel(const FusedParams p) {
       for (int k = tid; k < HID * S::NODES_H * HID; k += BT) {
         const int o = k % HID, r = k / HID, q = r % S::NODES_H, i = r / S::NODES_H;
         const float v = acc[((size_t)i * S::NODES_H + q) * HP + o];
-        if (v != 0.f) atomicAdd(p.gw[l + 1] + ((size_t)o * HID + i) * S::NODES_H + q, v);
+        if (v != 0.f) hoir::red_add(p.gw[l + 1] + ((size_t)o * HID + i) * S::NODES_H + q, v);
       }
     }
     const float* acc = sAcc + (size_t)NH * S::WH;
     for (int k = tid; k < HID * S::NODES_O * OUT; k += BT) {
       const int o = k % OUT, r = k / OUT, q = r % S::NODES_O, i = r / S::NODES_O;
       const float v = acc[((size_t)i * S::NODES_O + q) * OP + o];
-      if (v != 0.f) atomicAdd(p.gw[NH + 1] + ((size_t)o * HID + i) * S::NODES_O + q, v);
+      if (v != 0.f) hoir::red_add(p.gw[NH + 1] + ((size_t)o * HID + i) * S::NODES_O + q, v);
     }
   }
+  hoir::opt_tail_in_kernel(p.tail);
 }
 
 }  // namespace
@@ -635,9 +640,9 @@ __global__ void __launch_bounds__(256) gw0_chunk_kernel(long long B, int IN, int
     auto flush = [&](int sg) {
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        if (lane < hid && acc[j][0] != 0.f) atomicAdd(gw0 + ((size_t)lane * IN + i) * nodes0 + sg * stride + j, acc[j][0]);
+        if (lane < hid && acc[j][0] != 0.f) hoir::red_add(gw0 + ((size_t)lane * IN + i) * nodes0 + sg * stride + j, acc[j][0]);
         if (lane + 32 < hid && acc[j][1] != 0.f)
-          atomicAdd(gw0 + ((size_t)(lane + 32) * IN + i) * nodes0 + sg * stride + j, acc[j][1]);
+          hoir::red_add(gw0 + ((size_t)(lane + 32) * IN + i) * nodes0 + sg * stride + j, acc[j][1]);
         acc[j][0] = acc[j][1] = 0.f;
       }
     };
@@ -814,65 +819,164 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
   return HOIR_OK;
 }
 
-extern "C" int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const float* x,
-                                   const hoir_mesh_desc* mesh, int target_kind, const void* target,
-                                   const float* gy_ext, const float* packed, float* const* gw,
-                                   float* loss_sum, float loss_scale, void* stream) {
-  const FusedEntry* e = find_entry(m);
-  if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", "hoir_mlp_train_step");
-  FusedParams p;
-  if (int err = fill_params(m, B, x, mesh, packed, &p, "hoir_mlp_train_step")) return err;
-  if (B == 0) return HOIR_OK;
-  if (!gw) return hoir_set_error(HOIR_EINVAL, "null gradient pointer table", "hoir_mlp_train_step");
+namespace {
+
+__global__ void __launch_bounds__(256) opt_tail_kernel(const OptTail t) {
+  hoir::opt_tail_rows(t, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), (int)((gridDim.x * blockDim.x) >> 5),
+                      threadIdx.x & 31);
+}
+
+long long boundary_offset(const hoir_mlp_desc* m, int layer) {
+  long long off = 0;
+  for (int l = 0; l < layer; ++l)
+    off += (long long)m->layers[l].out_features * m->layers[l].in_features * hoir_layer_nodes(&m->layers[l]);
+  return off;
+}
+
+int fill_tail(const hoir_mlp_desc* m, const hoir_opt_desc* o, OptTail* t, const char* where) {
+  memset(t, 0, sizeof(*t));
+  if (!mlp_desc_ok(m)) return hoir_set_error(HOIR_EINVAL, "bad network descriptor", where);
+  if (!o) return hoir_set_error(HOIR_EINVAL, "null optimizer descriptor", where);
+  if (o->kind != HOIR_OPT_ADAM && o->kind != HOIR_OPT_SPARSE_LION)
+    return hoir_set_error(HOIR_EINVAL, "optimizer kind not recognized", where);
+  if (!o->flat_w || !o->flat_g || !o->exp_avg || !o->packed || (o->kind == HOIR_OPT_ADAM && !o->exp_avg_sq))
+    return hoir_set_error(HOIR_EINVAL, "null optimizer state pointer", where);
+  if (o->step < 1) return hoir_set_error(HOIR_EINVAL, "step must be >= 1", where);
+  t->kind = o->kind;
+  t->keep_grad = o->keep_grad;
+  t->num_layers = m->num_layers;
   for (int l = 0; l < m->num_layers; ++l) {
-    if (!gw[l]) return hoir_set_error(HOIR_EINVAL, "null gradient pointer", "hoir_mlp_train_step");
+    const hoir_layer_desc& d = m->layers[l];
+    t->in_f[l] = d.in_features;
+    t->nodes[l] = hoir_layer_nodes(&d);
+    t->out_pad[l] = (d.out_features + 3) & ~3;
+    t->row0[l + 1] = t->row0[l] + d.out_features * d.in_features;
+    t->woff[l + 1] = boundary_offset(m, l + 1);
+    t->poff[l] = hoir_mlp_packed_offset(m, l);
+  }
+  t->w = o->flat_w;
+  t->g = o->flat_g;
+  t->m = o->exp_avg;
+  t->v = o->exp_avg_sq;
+  t->packed = o->packed;
+  t->loss_out = o->loss_out;
+  t->lr = o->lr;
+  t->b1 = o->beta1;
+  t->b2 = o->beta2;
+  t->eps = o->eps;
+  t->wd = o->weight_decay;
+  t->bc1 = (float)(1.0 - pow((double)o->beta1, (double)o->step));
+  t->bc2_sqrt = (float)sqrt(1.0 - pow((double)o->beta2, (double)o->step));
+  return HOIR_OK;
+}
+
+int launch_tail(const OptTail& t, cudaStream_t stream) {
+  long long grid = (t.woff[t.num_layers] + 255) / 256;
+  if (grid > num_sms_fused() * 8) grid = num_sms_fused() * 8;
+  opt_tail_kernel<<<(int)grid, 256, 0, stream>>>(t);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+// shared launcher of the training kernels; tail != nullptr: optimizer tail in-kernel when the step is a
+// single launch (cooperative), as a separate launch after the second pass otherwise
+int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
+                 int target_kind, const void* target, const float* gy_ext, const float* packed,
+                 float* const* gw, float* loss_sum, float loss_scale, const OptTail* tail, void* stream,
+                 const char* where) {
+  const FusedEntry* e = find_entry(m);
+  if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", where);
+  FusedParams p;
+  if (int err = fill_params(m, B, x, mesh, packed, &p, where)) return err;
+  if (B == 0) return HOIR_OK;
+  if (!gw) return hoir_set_error(HOIR_EINVAL, "null gradient pointer table", where);
+  for (int l = 0; l < m->num_layers; ++l) {
+    if (!gw[l]) return hoir_set_error(HOIR_EINVAL, "null gradient pointer", where);
     p.gw[l] = gw[l];
   }
   if (gy_ext == nullptr) {
-    if (!target || !loss_sum) return hoir_set_error(HOIR_EINVAL, "target / loss_sum required", "hoir_mlp_train_step");
+    if (!target || !loss_sum) return hoir_set_error(HOIR_EINVAL, "target / loss_sum required", where);
     if (target_kind != HOIR_TARGET_F32 && target_kind != HOIR_TARGET_U8_IMAGE)
-      return hoir_set_error(HOIR_EINVAL, "unknown target kind", "hoir_mlp_train_step");
+      return hoir_set_error(HOIR_EINVAL, "unknown target kind", where);
     if (target_kind == HOIR_TARGET_U8_IMAGE && (mesh == nullptr || m->layers[m->num_layers - 1].out_features != 3))
-      return hoir_set_error(HOIR_EINVAL, "uint8 image targets need a mesh and 3 outputs", "hoir_mlp_train_step");
+      return hoir_set_error(HOIR_EINVAL, "uint8 image targets need a mesh and 3 outputs", where);
   }
   p.target_kind = target_kind;
   p.target = target;
   p.gy_ext = gy_ext;
   p.loss_sum = loss_sum;
   p.loss_scale = loss_scale;
+  cudaStream_t st = (cudaStream_t)stream;
   static const bool no_tc = getenv("HOIR_NO_TC") != nullptr;   // A/B switch: FFMA-only kernel
   static const bool no_2p = getenv("HOIR_NO_TWOPASS") != nullptr;
-  if (e->train_tc != nullptr && !no_tc) {
-    const int in_f = m->layers[0].in_features, hid = m->layers[0].out_features;
-    const bool two_pass = x != nullptr && B >= 32768 && !no_2p && p.seg0 <= GW0_MAXSEG && hid <= 64 && m->layers[0].n == 3;
-    if (two_pass) {
-      const size_t b_al = ((size_t)B + 63) & ~(size_t)63;
-      const size_t n_g0 = b_al * hid * sizeof(float), n_rec = b_al * in_f * sizeof(float4), n_seg = b_al * in_f * sizeof(unsigned short);
-      void* ws = nullptr;
-      if (int err = hoir_get_workspace(0, n_g0 + n_rec + n_seg, &ws)) return err;
-      p.ws_g0 = static_cast<float*>(ws);
-      p.ws_rec = reinterpret_cast<float4*>(static_cast<char*>(ws) + n_g0);
-      p.ws_seg = reinterpret_cast<unsigned short*>(static_cast<char*>(ws) + n_g0 + n_rec);
-    }
-    HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->train_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_tc));
-    const long long tiles = (B + tc::TS - 1) / tc::TS;
-    const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
-    e->train_tc<<<grid, tc::NTHREADS, e->smem_tc, (cudaStream_t)stream>>>(p);
-    HOIR_CHECK_CUDA(cudaGetLastError());
-    if (two_pass) {
-      const int stride = hoir::piecewise_stride(m->layers[0].kind, m->layers[0].n);
-      const dim3 grid2((unsigned)((B + GW0_CHUNK - 1) / GW0_CHUNK), (unsigned)in_f);
-      gw0_chunk_kernel<3><<<grid2, 256, 0, (cudaStream_t)stream>>>(B, in_f, hid, p.seg0, stride, p.nodes0, p.ws_seg,
-                                                                   p.ws_rec, p.ws_g0, p.gw[0]);
-      HOIR_CHECK_CUDA(cudaGetLastError());
-    }
-    return HOIR_OK;
+  static const bool no_fuse = getenv("HOIR_NO_FUSED_TAIL") != nullptr;   // A/B switch: tail as its own launch
+  const bool use_tc = e->train_tc != nullptr && !no_tc;
+  const int in_f = m->layers[0].in_features, hid = m->layers[0].out_features;
+  const bool two_pass = use_tc && x != nullptr && B >= 32768 && !no_2p && p.seg0 <= GW0_MAXSEG && hid <= 64 &&
+                        m->layers[0].n == 3;
+  if (two_pass) {
+    const size_t b_al = ((size_t)B + 63) & ~(size_t)63;
+    const size_t n_g0 = b_al * hid * sizeof(float), n_rec = b_al * in_f * sizeof(float4), n_seg = b_al * in_f * sizeof(unsigned short);
+    void* ws = nullptr;
+    if (int err = hoir_get_workspace(0, n_g0 + n_rec + n_seg, &ws)) return err;
+    p.ws_g0 = static_cast<float*>(ws);
+    p.ws_rec = reinterpret_cast<float4*>(static_cast<char*>(ws) + n_g0);
+    p.ws_seg = reinterpret_cast<unsigned short*>(static_cast<char*>(ws) + n_g0 + n_rec);
   }
-  HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_train));
-  const long long tiles = (B + BT - 1) / BT;
+  const bool tail_inside = tail != nullptr && !two_pass && !no_fuse;
+  if (tail_inside) {
+    p.tail = *tail;
+    void* ws = nullptr;
+    if (int err = hoir_get_workspace(2, 64, &ws)) return err;
+    p.tail.sync = static_cast<unsigned int*>(ws);
+  }
+  auto kern = use_tc ? e->train_tc : e->train;
+  const size_t smem = use_tc ? e->smem_tc : e->smem_train;
+  const int block = use_tc ? tc::NTHREADS : BT, ts = use_tc ? tc::TS : BT;
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long tiles = (B + ts - 1) / ts;
   const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
-  e->train<<<grid, BT, e->smem_train, (cudaStream_t)stream>>>(p);
+  if (tail_inside) {
+    // the grid barrier needs every CTA resident: cooperative launch (grid <= #SMs, 1 CTA per SM)
+    void* args[] = {&p};
+    HOIR_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), args, smem, st));
+  } else {
+    kern<<<grid, block, smem, st>>>(p);
+  }
   HOIR_CHECK_CUDA(cudaGetLastError());
+  if (two_pass) {
+    const int stride = hoir::piecewise_stride(m->layers[0].kind, m->layers[0].n);
+    const dim3 grid2((unsigned)((B + GW0_CHUNK - 1) / GW0_CHUNK), (unsigned)in_f);
+    gw0_chunk_kernel<3><<<grid2, 256, 0, st>>>(B, in_f, hid, p.seg0, stride, p.nodes0, p.ws_seg, p.ws_rec, p.ws_g0, p.gw[0]);
+    HOIR_CHECK_CUDA(cudaGetLastError());
+  }
+  if (tail != nullptr && !tail_inside) return launch_tail(*tail, st);
   return HOIR_OK;
 }
 
+}  // namespace
+
+extern "C" int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const float* x,
+                                   const hoir_mesh_desc* mesh, int target_kind, const void* target,
+                                   const float* gy_ext, const float* packed, float* const* gw,
+                                   float* loss_sum, float loss_scale, void* stream) {
+  return train_launch(m, B, x, mesh, target_kind, target, gy_ext, packed, gw, loss_sum, loss_scale, nullptr,
+                      stream, "hoir_mlp_train_step");
+}
+
+extern "C" int hoir_mlp_optimizer_tail(const hoir_mlp_desc* m, const hoir_opt_desc* opt, void* stream) {
+  OptTail t;
+  if (int err = fill_tail(m, opt, &t, "hoir_mlp_optimizer_tail")) return err;
+  return launch_tail(t, (cudaStream_t)stream);
+}
+
+extern "C" int hoir_mlp_train_step_fused(const hoir_mlp_desc* m, long long B, const float* x,
+                                         const hoir_mesh_desc* mesh, int target_kind, const void* target,
+                                         float loss_scale, const hoir_opt_desc* opt, void* stream) {
+  OptTail t;
+  if (int err = fill_tail(m, opt, &t, "hoir_mlp_train_step_fused")) return err;
+  float* gw[HOIR_MAX_LAYERS] = {};
+  for (int l = 0; l < m->num_layers; ++l) gw[l] = opt->flat_g + t.woff[l];
+  return train_launch(m, B, x, mesh, target_kind, target, nullptr, opt->packed, gw,
+                      opt->flat_g + t.woff[m->num_layers], loss_scale, &t, stream, "hoir_mlp_train_step_fused");
+}

@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
                 for (int o = 0; o < 4; ++o)
 #pragma unroll
                   for (int q = 0; q < N; ++q)
-                    if (acc[o][q] != 0.f) atomicAdd(dst + o * ostride + cur + q, acc[o][q]);
+                    if (acc[o][q] != 0.f) hoir::red_add(dst + o * ostride + cur + q, acc[o][q]);
               }
               cur = base;
 #pragma unroll
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
             for (int o = 0; o < 4; ++o)
 #pragma unroll
               for (int q = 0; q < N; ++q)
-                if (acc[o][q] != 0.f) atomicAdd(dst + o * ostride + cur + q, acc[o][q]);
+                if (acc[o][q] != 0.f) hoir::red_add(dst + o * ostride + cur + q, acc[o][q]);
           }
         }
       }
@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     // ---- flush: loss, dL/dw2 (smem), dL/dw1 (TMEM accumulators)
     if (p.gy_ext == nullptr && hf == 0) {
       const float sum = hoir::warp_sum(loss_local) * p.loss_scale;
-      if (lane == 0 && sum != 0.f) atomicAdd(p.loss_sum, sum);
+      if (lane == 0 && sum != 0.f) hoir::red_add(p.loss_sum, sum);
     }
     {
       // after the reduce-scatter lane L holds element e(L) = (node k, output o) of every input it walked
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         const int k = e / OUT, o = e - k * OUT;
 #pragma unroll
         for (int j = 0; j < HH; ++j)
-          if (acc2[j] != 0.f) atomicAdd(p.gw[2] + ((size_t)o * HID + hf * HH + j) * S::NODES_O + k, acc2[j]);
+          if (acc2[j] != 0.f) hoir::red_add(p.gw[2] + ((size_t)o * HID + hf * HH + j) * S::NODES_O + k, acc2[j]);
       }
     }
     if (n_tile > 0) {
@@ -750,13 +750,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         const int i = hfi * HH + c * P::QI + r2 / ND, q = r2 % ND;
 #pragma unroll
         for (int o = 0; o < HID; ++o)
-          if (v[o] != 0.f) atomicAdd(p.gw[1] + ((size_t)o * HID + i) * ND + q, v[o]);
+          if (v[o] != 0.f) hoir::red_add(p.gw[1] + ((size_t)o * HID + i) * ND + q, v[o]);
       }
       fence_before();
     }
   }
   __syncthreads();
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  hoir::opt_tail_in_kernel(p.tail);
 }
 
 }  // namespace tc

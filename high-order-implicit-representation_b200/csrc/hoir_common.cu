@@ -18,13 +18,14 @@ struct Workspace {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-Workspace g_ws[16][2];
+constexpr int kSlots = 3;
+Workspace g_ws[16][kSlots];
 }  // namespace
 
 int hoir_get_workspace(int slot, size_t bytes, void** out) {
   int dev = 0;
   HOIR_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16 || slot < 0 || slot >= 2)
+  if (dev < 0 || dev >= 16 || slot < 0 || slot >= kSlots)
     return hoir_set_error(HOIR_EUNSUPPORTED, "device index >= 16", "hoir_get_workspace");
   Workspace& w = g_ws[dev][slot];
   if (w.bytes < bytes) {
@@ -36,6 +37,7 @@ int hoir_get_workspace(int slot, size_t bytes, void** out) {
     }
     const size_t grow = bytes + bytes / 4;
     HOIR_CHECK_CUDA(cudaMalloc(&w.ptr, grow));
+    HOIR_CHECK_CUDA(cudaMemset(w.ptr, 0, grow));   // slot 2 holds the grid-barrier counters
     w.bytes = grow;
   }
   *out = w.ptr;
@@ -46,7 +48,7 @@ void hoir_free_workspaces() {
   int cur = 0;
   cudaGetDevice(&cur);
   for (int d = 0; d < 16; ++d)
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < kSlots; ++s)
       if (g_ws[d][s].ptr) {
         cudaSetDevice(d);
         cudaFree(g_ws[d][s].ptr);

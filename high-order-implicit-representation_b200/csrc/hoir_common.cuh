@@ -15,7 +15,8 @@
   } while (0)
 
 int hoir_set_error(int code, const char* msg, const char* where);
-// library-owned per-device scratch (slot 0: two-pass layer-0 gradient, slot 1: packed layer weights)
+// library-owned per-device scratch (slot 0: two-pass layer-0 gradient, slot 1: packed layer weights,
+// slot 2: grid-barrier counters of the in-kernel optimizer tail; memory is zeroed when (re)allocated)
 int hoir_get_workspace(int slot, size_t bytes, void** out);
 void hoir_free_workspaces();
 
@@ -151,6 +152,13 @@ __device__ __forceinline__ void fourier_rt(int n, const float* c, float x, float
     val[j] = is_sin ? sn : cs;
     if (der) der[j] = (is_sin ? cs : -sn) * (c[j] / length);
   }
+}
+
+// fire-and-forget fp32 add to global memory.  Explicit PTX: once a kernel also contains fences / acquire
+// loads (the in-kernel optimizer tail), nvcc turns atomicAdd with an unused result into the RETURNING form
+// (ATOMG instead of REDG), which stalls the issuing warp on the round trip (measured: +25% kernel time).
+__device__ __forceinline__ void red_add(float* addr, float v) {
+  asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1,0 +1,119 @@
+// opt_tail.cuh -- the tail of a training step, fused: optimizer update (torch.optim.Adam /
+// SparseLion semantics, /root/reference/high_order_implicit_representation/networks.py:93-102) on the
+// flat parameter vector, refresh of the kernel-side packed weights [in][node][out_pad], zeroing of the
+// flat gradient for the next step and hand-over of the loss -- one pass over the parameters.
+//
+// It runs either (a) inside the fused whole-network kernels, after a grid-wide barrier that follows
+// the gradient flush (single GPU, coherent batches: ONE launch per training step), or (b) as the
+// stand-alone opt_tail_kernel after the NCCL all-reduce / the second pass of the layer-0 gradient.
+// Flat walk over the boundary-layout parameters: coalesced reads, scattered packed writes.
+#pragma once
+#include "hoir_common.cuh"
+
+struct OptTail {
+  int kind;                               // 0: none, HOIR_OPT_ADAM, HOIR_OPT_SPARSE_LION
+  int keep_grad;                          // 1: do not zero the gradient / loss accumulator
+  int num_layers;
+  int in_f[HOIR_MAX_LAYERS], nodes[HOIR_MAX_LAYERS], out_pad[HOIR_MAX_LAYERS];
+  int row0[HOIR_MAX_LAYERS + 1];          // prefix sums of out*in links
+  long long woff[HOIR_MAX_LAYERS + 1];    // boundary-layout float offsets; woff[L] = number of parameters
+  long long poff[HOIR_MAX_LAYERS];        // packed float offsets
+  float* w;
+  float* g;                               // [n + 1]: gradients, then the loss accumulator
+  float* m;
+  float* v;
+  float* packed;
+  float* loss_out;
+  float lr, b1, b2, eps, wd, bc1, bc2_sqrt;
+  unsigned int* sync;                     // [2] arrive / depart counters of the in-kernel grid barrier
+};
+
+namespace hoir {
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid-wide barrier for a grid whose CTAs are all resident (cooperative launch).  Every thread of
+// every CTA must call it; writes (including atomics) made before it are visible to L2 reads after it.
+__device__ __forceinline__ void grid_barrier_arrive_wait(unsigned int* sync) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&sync[0], 1u);
+    unsigned int spins = 0;
+    while (ld_acquire_u32(&sync[0]) < gridDim.x) {
+      __nanosleep(64);
+      if (++spins > (1u << 26)) __trap();   // a CTA never arrived: fail loudly instead of hanging
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// the last CTA to leave re-arms the counters for the next launch
+__device__ __forceinline__ void grid_barrier_depart(unsigned int* sync) {
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&sync[1], 1u) == gridDim.x - 1) {
+      sync[0] = 0u;
+      sync[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+__device__ __forceinline__ void opt_tail_rows(const OptTail& t, int gwarp, int nwarps, int lane) {
+  const float one_m_b1 = 1.f - t.b1, one_m_b2 = 1.f - t.b2, step_size = t.lr / t.bc1;
+  const long long n = t.woff[t.num_layers];
+  const long long stride = (long long)nwarps * 32;
+  // flat walk over the boundary-layout parameters (coalesced); iterations are independent, so the
+  // unrolled loads overlap -- a small grid (batch 256: one CTA) is latency-, not bandwidth-bound here
+#pragma unroll 4
+  for (long long k = (long long)gwarp * 32 + lane; k < n; k += stride) {
+    int l = 0;
+    while (l + 1 < t.num_layers && k >= t.woff[l + 1]) ++l;
+    const int e = (int)(k - t.woff[l]);
+    const int nodes = t.nodes[l], in_f = t.in_f[l], op = t.out_pad[l];
+    const int r = e / nodes, q = e - r * nodes;
+    const int o = r / in_f, i = r - o * in_f;
+    float gk = __ldcg(t.g + k);           // written by other SMs' atomics: read at L2
+    float wk = t.w[k];
+    if (t.kind == HOIR_OPT_ADAM) {
+      if (t.wd != 0.f) gk = fmaf(t.wd, wk, gk);
+      const float m0 = t.m[k];
+      const float mk = m0 + one_m_b1 * (gk - m0);          // lerp, as torch does
+      const float vk = t.b2 * t.v[k] + one_m_b2 * gk * gk;
+      t.m[k] = mk;
+      t.v[k] = vk;
+      const float denom = sqrtf(vk) / t.bc2_sqrt + t.eps;
+      wk = wk - step_size * (mk / denom);
+      t.w[k] = wk;
+    } else if (gk != 0.f) {               // SparseLion: only entries with a non-zero gradient
+      const float ea = t.m[k];
+      const float wd = wk * (1.f - t.lr * t.wd);
+      const float u = ea * t.b1 + gk * one_m_b1;
+      const float sg = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+      wk = wd - t.lr * sg;
+      t.w[k] = wk;
+      t.m[k] = ea * t.b2 + gk * one_m_b2;
+    }
+    if (!t.keep_grad) t.g[k] = 0.f;
+    t.packed[t.poff[l] + ((long long)i * nodes + q) * op + o] = wk;
+  }
+  if (gwarp == 0 && lane == 0) {
+    if (t.loss_out != nullptr) t.loss_out[0] = __ldcg(t.g + n);
+    if (!t.keep_grad) t.g[n] = 0.f;
+  }
+}
+
+// called by every thread of a fused kernel at its very end
+__device__ __forceinline__ void opt_tail_in_kernel(const OptTail& t) {
+  if (t.kind == 0) return;
+  grid_barrier_arrive_wait(t.sync);
+  const int wpb = blockDim.x >> 5;
+  opt_tail_rows(t, blockIdx.x * wpb + (threadIdx.x >> 5), gridDim.x * wpb, threadIdx.x & 31);
+  grid_barrier_depart(t.sync);
+}
+
+}  // namespace hoir

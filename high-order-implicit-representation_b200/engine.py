@@ -7,8 +7,9 @@ zeroed with a single memset, reduced across ranks with a single NCCL all-reduce 
 over disjoint pixel tiles) and consumed by a single fused Adam / SparseLion
 launch.  One training step of ``Net.eval_step`` + ``backward`` + ``optimizer.step``
 (/root/reference/high_order_implicit_representation/networks.py:64-70, 93-102) is
-``memset, pack, hoir_mlp_train_step, [all_reduce], optimizer`` -- no PyTorch autograd, no
-per-layer tensors in HBM.
+ONE launch on a single GPU (``hoir_mlp_train_step_fused``: the optimizer update, the weight re-pack
+and the gradient zeroing run inside the whole-network kernel behind a grid barrier) and
+``kernel, all_reduce, tail`` across GPUs -- no PyTorch autograd, no per-layer tensors in HBM.
 """
 from __future__ import annotations
 
@@ -22,9 +23,12 @@ from .networks import HighOrderMLP
 
 
 class FusedTrainer:
+    """``keep_grads=True`` leaves ``flat_g`` / ``g_views`` holding the step's gradient (parity tests,
+    inspection) at the price of one extra memset per step; by default the fused tail zeroes it."""
+
     def __init__(self, mlp: HighOrderMLP, optimizer: str = "adam", lr: float = 1e-4,
                  betas: Optional[tuple] = None, eps: float = 1e-8, weight_decay: float = 0.0,
-                 process_group=None):
+                 process_group=None, keep_grads: bool = False):
         self.lib = _lib.lib()
         self.mlp = mlp
         self.layers = mlp.high_order_layers()
@@ -44,6 +48,7 @@ class FusedTrainer:
         self.eps = float(eps)
         self.weight_decay = float(weight_decay)
         self.step_count = 0
+        self.keep_grads = bool(keep_grads)
         self.group = process_group
         self.rank, self.world = parallel.world_info(process_group)
         self.out_features = self.layers[-1].out_features
@@ -51,7 +56,8 @@ class FusedTrainer:
         sizes = [l.w.numel() for l in self.layers]
         self.n_params = sum(sizes)
         self.flat_w = torch.empty(self.n_params, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(self.n_params + 1, device=dev, dtype=torch.float32)  # [-1] = loss
+        self.flat_g = torch.zeros(self.n_params + 1, device=dev, dtype=torch.float32)  # [-1] = loss accumulator
+        self.loss_out = torch.zeros(1, device=dev, dtype=torch.float32)
         self.w_views, self.g_views = [], []
         off = 0
         with torch.no_grad():
@@ -64,50 +70,77 @@ class FusedTrainer:
                 off += sz
         self.exp_avg = torch.zeros(self.n_params, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(self.n_params, device=dev, dtype=torch.float32) if optimizer == "adam" else None
-        self.packed = torch.empty(self.lib.hoir_mlp_packed_size(self.desc), device=dev, dtype=torch.float32)
+        self.packed = torch.zeros(self.lib.hoir_mlp_packed_size(self.desc), device=dev, dtype=torch.float32)
         self._w_table = _lib.ptr_table(self.w_views)
         self._g_table = _lib.ptr_table(self.g_views)
         self._loss_ptr = _lib.C.c_void_p(self.flat_g.data_ptr() + 4 * self.n_params)
-        self._packed_fresh = False
-        #: kernels launched by the last train step (memset excluded)
-        self.launches_per_step = len(self.layers) + 2
+        self._w_version = -1
+        self._opt = _lib.OptDesc()
+        self._opt.kind = _lib.OPT_KIND[optimizer]
+        self._opt.flat_w = self.flat_w.data_ptr()
+        self._opt.flat_g = self.flat_g.data_ptr()
+        self._opt.exp_avg = self.exp_avg.data_ptr()
+        self._opt.exp_avg_sq = self.exp_avg_sq.data_ptr() if self.exp_avg_sq is not None else None
+        self._opt.packed = self.packed.data_ptr()
+        self._opt.loss_out = self.loss_out.data_ptr()
+        #: kernels launched by the last train step
+        self.launches_per_step = 1 if self.world == 1 else 2
         #: set to a list to collect (start, end) CUDA events around the fused training kernel
         self.kernel_events = None
 
     # ------------------------------------------------------------------------------------------
     def pack(self) -> None:
+        """Refresh the kernel-side packed weights from ``flat_w``.  The fused tail keeps them in sync
+        during training; this is only needed after the weights were written from outside
+        (``load_state_dict``, manual edits), which ``_ensure_packed`` detects by the version counter."""
         _lib.check(self.lib.hoir_mlp_pack(self.desc, self._w_table, _lib.dptr(self.packed),
                                           _lib.stream_ptr(self.device)))
-        self._packed_fresh = True
+        self._w_version = self.flat_w._version
 
-    def _train_kernel(self, *args) -> None:
-        if self.kernel_events is None:
-            _lib.check(self.lib.hoir_mlp_train_step(*args))
-            return
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(self.lib.hoir_mlp_train_step(*args))
-        e1.record()
-        self.kernel_events.append((e0, e1))
+    def _ensure_packed(self) -> None:
+        if self.flat_w._version != self._w_version:
+            self.pack()
 
     def _loss_scale(self, B: int, global_batch: Optional[int]) -> float:
         return parallel.global_loss_scale(B, self.world, self.out_features, global_batch)
 
-    def _finish(self) -> Tensor:
-        parallel.allreduce_sum_(self.flat_g, self.group)
+    def _opt_desc(self) -> "_lib.OptDesc":
+        o = self._opt
+        o.lr, o.beta1, o.beta2 = self.lr, self.betas[0], self.betas[1]
+        o.eps, o.weight_decay = self.eps, self.weight_decay
+        o.step = self.step_count
+        o.keep_grad = 1 if self.keep_grads else 0
+        return o
+
+    def _step(self, B: int, x_ptr, mesh, target_kind: int, target_ptr, global_batch: Optional[int]) -> Tensor:
+        """zero_grad + forward + MSE + backward + [all-reduce] + optimizer + weight re-pack.
+        Single GPU: ONE launch (the optimizer tail runs inside the whole-network kernel behind a grid
+        barrier), or kernel + second pass + tail for large incoherent batches.  Multi-GPU: kernel, one NCCL
+        all-reduce of ``flat_g``, tail."""
+        lib, st = self.lib, _lib.stream_ptr(self.device)
+        self._ensure_packed()
+        if self.keep_grads:
+            self.flat_g.zero_()
         self.step_count += 1
-        st = _lib.stream_ptr(self.device)
-        if self.optimizer == "adam":
-            _lib.check(self.lib.hoir_adam_step(
-                self.n_params, _lib.dptr(self.flat_w), _lib.dptr(self.flat_g), _lib.dptr(self.exp_avg),
-                _lib.dptr(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
-                self.weight_decay, self.step_count, st))
+        scale = self._loss_scale(B, global_batch)
+        ev = None
+        if self.kernel_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        if self.world == 1:
+            _lib.check(lib.hoir_mlp_train_step_fused(self.desc, B, x_ptr, mesh, target_kind, target_ptr,
+                                                     scale, _lib.C.byref(self._opt_desc()), st))
         else:
-            _lib.check(self.lib.hoir_sparse_lion_step(
-                self.n_params, _lib.dptr(self.flat_w), _lib.dptr(self.flat_g), _lib.dptr(self.exp_avg),
-                self.lr, self.betas[0], self.betas[1], self.weight_decay, st))
-        self._packed_fresh = False
-        return self.flat_g[self.n_params:]  # 1-element view: MSE(mean) of this step (all ranks)
+            _lib.check(lib.hoir_mlp_train_step(self.desc, B, x_ptr, mesh, target_kind, target_ptr, None,
+                                               _lib.dptr(self.packed), self._g_table, self._loss_ptr,
+                                               scale, st))
+        if ev is not None:
+            ev[1].record()
+            self.kernel_events.append(ev)
+        if self.world > 1:
+            parallel.allreduce_sum_(self.flat_g, self.group)
+            _lib.check(lib.hoir_mlp_optimizer_tail(self.desc, _lib.C.byref(self._opt_desc()), st))
+        return self.loss_out     # 1-element tensor: MSE(mean) of this step over all ranks
 
     def train_step(self, x: Tensor, y: Tensor, global_batch: Optional[int] = None) -> Tensor:
         """One optimisation step on explicit samples x[B, in], y[B, out] (the reference's batch).
@@ -117,15 +150,8 @@ class FusedTrainer:
         if x2.shape[1] != self.in_features or y2.shape[1] != self.out_features:
             raise ValueError(f"expected x[B,{self.in_features}] / y[B,{self.out_features}], got "
                              f"{tuple(x.shape)} / {tuple(y.shape)}")
-        B = x2.shape[0]
         with torch.cuda.device(self.device):
-            self.flat_g.zero_()
-            self.pack()
-            self._train_kernel(
-                self.desc, B, _lib.dptr(x2), None, _lib.TARGET_F32, _lib.dptr(y2), None,
-                _lib.dptr(self.packed), self._g_table, self._loss_ptr,
-                self._loss_scale(B, global_batch), _lib.stream_ptr(self.device))
-            return self._finish()
+            return self._step(x2.shape[0], _lib.dptr(x2), None, _lib.TARGET_F32, _lib.dptr(y2), global_batch)
 
     def train_step_mesh(self, image_u8: Tensor, rotations: int, first_pixel: int, B: int,
                         global_batch: Optional[int] = None) -> Tensor:
@@ -137,21 +163,15 @@ class FusedTrainer:
             raise ValueError("expected a uint8 image [rows, cols, 3]")
         mesh = _lib.make_mesh_desc(image_u8.shape[0], image_u8.shape[1], rotations, True, first_pixel)
         with torch.cuda.device(self.device):
-            self.flat_g.zero_()
-            self.pack()
-            self._train_kernel(
-                self.desc, B, None, mesh, _lib.TARGET_U8_IMAGE, _lib.dptr(image_u8, torch.uint8), None,
-                _lib.dptr(self.packed), self._g_table, self._loss_ptr,
-                self._loss_scale(B, global_batch), _lib.stream_ptr(self.device))
-            return self._finish()
+            return self._step(B, None, mesh, _lib.TARGET_U8_IMAGE, _lib.dptr(image_u8, torch.uint8),
+                              global_batch)
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x: Tensor) -> Tensor:
         x2 = x.reshape(x.shape[0], -1).contiguous()
         y = torch.empty((x2.shape[0], self.out_features), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
-            if not self._packed_fresh:
-                self.pack()
+            self._ensure_packed()
             _lib.check(self.lib.hoir_mlp_forward(self.desc, x2.shape[0], _lib.dptr(x2), None,
                                                  _lib.dptr(self.packed), _lib.dptr(y), 0,
                                                  _lib.stream_ptr(self.device)))
@@ -168,8 +188,7 @@ class FusedTrainer:
             out = torch.empty((count, self.out_features), device=self.device, dtype=torch.float32)
         mesh = _lib.make_mesh_desc(rows, cols, rotations, True, first_pixel)
         with torch.cuda.device(self.device):
-            if not self._packed_fresh:
-                self.pack()
+            self._ensure_packed()
             _lib.check(self.lib.hoir_mlp_forward(self.desc, count, None, mesh, _lib.dptr(self.packed),
                                                  _lib.dptr(out), 1 if post_scale else 0,
                                                  _lib.stream_ptr(self.device)))

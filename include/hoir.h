@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HOIR_VERSION 100
+#define HOIR_VERSION 101
 #define HOIR_MAX_LAYERS 8
 #define HOIR_MAX_N 32          /* max basis functions per segment / Fourier terms          */
 #define HOIR_MAX_ROTATIONS 8
@@ -161,6 +161,38 @@ int hoir_mlp_train_step(const hoir_mlp_desc* m, long long B, const float* x,
                         const hoir_mesh_desc* mesh, int target_kind, const void* target,
                         const float* gy_ext, const float* packed, float* const* gw,
                         float* loss_sum, float loss_scale, void* stream);
+
+/* ---- fused training step with the optimizer in the same launch -------------------------------
+ * State of one optimizer over the FLAT parameter vector of a network (all w tensors in boundary
+ * layout, concatenated in layer order).  Replaces optimizer.zero_grad() / loss.backward() /
+ * optimizer.step() of the reference's training loop
+ * (/root/reference/high_order_implicit_representation/networks.py:64-70, 93-102). */
+enum hoir_opt_kind { HOIR_OPT_ADAM = 1, HOIR_OPT_SPARSE_LION = 2 };
+typedef struct hoir_opt_desc {
+  int kind;                    /* enum hoir_opt_kind                                          */
+  float lr, beta1, beta2, eps, weight_decay;
+  long long step;              /* 1-based index of this update (Adam bias correction)         */
+  float* flat_w;               /* [n_params]                                                   */
+  float* flat_g;               /* [n_params + 1]: dL/dw then the loss accumulator; must be zero
+                                  on entry of a training step and is left zeroed by the tail   */
+  float* exp_avg;              /* [n_params]                                                   */
+  float* exp_avg_sq;           /* [n_params] (Adam only)                                       */
+  float* packed;               /* kernel-side weights (hoir_mlp_packed_size floats); kept in
+                                  sync with flat_w by the tail                                 */
+  float* loss_out;             /* [1] receives the loss of the step                            */
+  int keep_grad;               /* 1: leave flat_g as computed (inspection / parity tests); the
+                                  caller zeroes it before the next step                        */
+} hoir_opt_desc;
+
+/* optimizer update + packed-weight refresh + gradient zeroing + loss hand-over: ONE launch.
+ * Multi-GPU: call after the all-reduce of flat_g. */
+int hoir_mlp_optimizer_tail(const hoir_mlp_desc* m, const hoir_opt_desc* opt, void* stream);
+/* hoir_mlp_train_step with gw = views of opt->flat_g, packed = opt->packed, loss_sum =
+ * opt->flat_g + n_params, followed by the tail.  For coherent batches the tail runs INSIDE the
+ * whole-network kernel behind a grid-wide barrier: one launch per training step. */
+int hoir_mlp_train_step_fused(const hoir_mlp_desc* m, long long B, const float* x,
+                              const hoir_mesh_desc* mesh, int target_kind, const void* target,
+                              float loss_scale, const hoir_opt_desc* opt, void* stream);
 
 /* ---- optimizers on flat fp32 vectors --------------------------------------------------------
  * torch.optim.Adam (networks.py:94-97) and SparseLion (networks.py:99-102). */

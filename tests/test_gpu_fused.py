@@ -56,7 +56,7 @@ def test_fused_matches_per_layer_kernels(name):
 @pytest.mark.parametrize("opt", ["adam", "sparse_lion"])
 def test_trainer_steps_match_oracle_training(name, opt):
     ref, net = make_pair(name)
-    tr = H.FusedTrainer(net, optimizer=opt, lr=1e-3)
+    tr = H.FusedTrainer(net, optimizer=opt, lr=1e-3, keep_grads=(opt == "adam"))
     ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-3) if opt == "adam" else O.SparseLion(ref.parameters(), lr=1e-3)
     for step in range(3):
         x, y = batch(name, 600, seed=step)
@@ -66,7 +66,7 @@ def test_trainer_steps_match_oracle_training(name, opt):
         ref_opt.step()
         loss = tr.train_step(x.cuda(), y.cuda())
         assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
-        if step == 0:
+        if step == 0 and tr.keep_grads:
             for gv, q in zip(tr.g_views, ref.parameters()):
                 assert rel_err(gv, q.grad) <= 2e-5
     # sign-based Lion updates can flip on round-off-sized momenta: compare in absolute lr units
@@ -87,7 +87,7 @@ def test_mesh_mode_training_and_render(rows, cols, rot, name):
     g = torch.Generator().manual_seed(11)
     img = torch.randint(0, 256, (rows, cols, 3), generator=g, dtype=torch.uint8)
     y_flat, x_flat, _ = O.image_to_dataset(img, rotations=rot)
-    tr = H.FusedTrainer(net, optimizer="adam", lr=0.0)      # lr 0: weights stay put, grads visible
+    tr = H.FusedTrainer(net, optimizer="adam", lr=0.0, keep_grads=True)      # lr 0: weights stay put, grads visible
     first, count = 5, rows * cols - 9
     loss_ref = O.mse_training_step(ref, x_flat[first:first + count], y_flat[first:first + count])
     loss_ref.backward()
@@ -103,10 +103,44 @@ def test_mesh_mode_training_and_render(rows, cols, rot, name):
     assert rel_err(part, ref(x_flat[first:first + count])) <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_single_launch_step_equals_unfused_tail(name):
+    """The in-kernel optimizer tail (grid barrier, one launch per step; gradients zeroed by the tail) must give
+    the same weights as the inspection mode (memset + kernel + tail reading a kept gradient) -- both against
+    the oracle's Adam and against each other."""
+    ref, net_a = make_pair(name)
+    _, net_b = make_pair(name)
+    net_b.load_state_dict(net_a.state_dict())
+    tr_a = H.FusedTrainer(net_a, optimizer="adam", lr=1e-3)
+    tr_b = H.FusedTrainer(net_b, optimizer="adam", lr=1e-3, keep_grads=True)
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    for step in range(4):
+        x, y = batch(name, 3000, seed=20 + step)
+        ref_opt.zero_grad()
+        loss_ref = O.mse_training_step(ref, x, y)
+        loss_ref.backward()
+        ref_opt.step()
+        la = tr_a.train_step(x.cuda(), y.cuda()).clone()
+        lb = tr_b.train_step(x.cuda(), y.cuda()).clone()
+        assert abs(la.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+        assert abs(la.item() - lb.item()) <= 2e-6 * abs(lb.item())
+        assert float(tr_a.flat_g.abs().max()) == 0.0          # left zeroed for the next step
+    # Adam turns round-off-sized gradients (fp32 atomics: run-to-run summation order) into +-lr steps:
+    # compare the bulk of the entries, not the worst one
+    assert ((tr_a.flat_w - tr_b.flat_w).abs() > 2e-6).float().mean().item() <= 2e-3
+    for (k, p), (_, q) in zip(net_a.named_parameters(), ref.named_parameters()):
+        frac_off = ((p.detach().cpu() - q.detach()).abs() > 5e-5).float().mean().item()
+        assert frac_off <= 2e-3, (k, frac_off)
+    # weights written from outside (load_state_dict) are re-packed before the next step
+    net_a.load_state_dict(net_b.state_dict())
+    x, y = batch(name, 512, seed=99)
+    assert abs(tr_a.train_step(x.cuda(), y.cuda()).item() - tr_b.train_step(x.cuda(), y.cuda()).item()) <= 1e-5
+
+
 def test_fused_empty_and_edge_batches():
     ref, net = make_pair("C2")
     assert net(torch.empty(0, 4, device="cuda")).shape == (0, 3)
-    tr = H.FusedTrainer(net, lr=0.0)
+    tr = H.FusedTrainer(net, lr=0.0, keep_grads=True)
     assert tr.render(8, 8, 2, first_pixel=64, count=0).shape == (0, 3)
     for B in (1, 256, 257, 148 * 256 + 3):
         x, _ = batch("C2", B, seed=B)
@@ -117,7 +151,7 @@ def test_large_batch_linearity_of_gradients():
     """Full-size property check (2^20 samples, too big for the oracle): dL/dw over the batch equals
     the sum over its halves, and the loss is the mean of the halves' losses."""
     _, net = make_pair("C2")
-    tr = H.FusedTrainer(net, lr=0.0)
+    tr = H.FusedTrainer(net, lr=0.0, keep_grads=True)
     B = 1 << 20
     g = torch.Generator(device="cuda").manual_seed(3)
     x = torch.rand(B, 4, device="cuda", generator=g) * 2 - 1
@@ -192,7 +226,7 @@ def test_two_pass_layer0_gradient_matches_in_kernel_path(coherent, monkeypatch):
     """Large generic batches route the layer-0 dL/dw through the segment-owner kernel; it must agree with the
     oracle on a sub-sample and with full-batch linearity (the oracle cannot run 2^16 samples quickly)."""
     ref, net = make_pair("C2")
-    tr = H.FusedTrainer(net, lr=0.0)
+    tr = H.FusedTrainer(net, lr=0.0, keep_grads=True)
     B = 1 << 16
     g = torch.Generator().manual_seed(9)
     x = torch.rand(B, 4, generator=g) * 2.2 - 1.1
