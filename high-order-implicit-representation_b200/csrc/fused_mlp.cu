@@ -575,29 +575,38 @@ bool mlp_desc_ok(const hoir_mlp_desc* m) {
   return true;
 }
 
-// Second pass of the layer-0 dL/dw for incoherent batches.  CTA (chunk of 4096 samples, input i): counting
-// sort of the chunk's samples by segment in shared memory, then every warp reduces whole segments
-// (lane <-> outputs o and o + 32, basis record broadcast, dL/dy row coalesced) in registers and issues ONE
-// atomicAdd per owned weight and segment present in the chunk: ~12 atomics per sample instead of 480,
-// balanced for any distribution of the inputs.
-constexpr int GW0_CHUNK = 4096, GW0_MAXSEG = 1024, GW0_BLOCK = 64;
+// Second pass of the layer-0 dL/dw for incoherent batches.  CTA (chunk of 16384 samples, input i):
+//   1. counting sort of the chunk's samples by segment in shared memory;
+//   2. every warp reduces blocks of 128 consecutive sorted entries in registers (lane <-> outputs o and
+//      o + 32, basis record broadcast, dL/dy row coalesced) and adds a finished segment run into the CTA's
+//      shared-memory slab  gw0[:, i, :]  ([node][out], 32 KB for 201 x 40);
+//   3. the slab is flushed once: one fire-and-forget global add per weight and CTA, nodes fastest so that
+//      a warp's adds fall into consecutive addresses of the boundary layout [out][in][nodes].
+// ~0.25 global adds per (sample, input) instead of the 120 of a per-sample scatter, balanced for any
+// distribution of the inputs.
+constexpr int GW0_CHUNK = 16384, GW0_MAXSEG = 1024, GW0_BLOCK = 128, GW0_PITCH_PAD = 1, GW0_THREADS = 512, GW0_WARPS = GW0_THREADS / 32;
 template <int N>
-__global__ void __launch_bounds__(256) gw0_chunk_kernel(long long B, int IN, int hid, int seg0, int stride, int nodes0,
-                                                        const unsigned short* __restrict__ ws_seg,
-                                                        const float4* __restrict__ ws_rec, const float* __restrict__ ws_g0,
-                                                        float* __restrict__ gw0) {
-  __shared__ unsigned int s_ent[GW0_CHUNK];          // sorted by segment: (segment << 16) | sample offset
-  __shared__ int s_cnt[GW0_MAXSEG], s_pos[GW0_MAXSEG];
+__global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int chunk, int IN, int hid, int seg0, int stride, int nodes0,
+                                                       const unsigned short* __restrict__ ws_seg,
+                                                       const float4* __restrict__ ws_rec, const float* __restrict__ ws_g0,
+                                                       float* __restrict__ gw0) {
+  extern __shared__ __align__(16) unsigned char gw0_smem[];
+  unsigned int* s_ent = reinterpret_cast<unsigned int*>(gw0_smem);      // sorted: (segment << 14) | sample offset
+  int* s_cnt = reinterpret_cast<int*>(s_ent + GW0_CHUNK);
+  int* s_pos = s_cnt + GW0_MAXSEG;
+  float* slab = reinterpret_cast<float*>(s_pos + GW0_MAXSEG);           // [nodes0][pitch]
+  const int pitch = hid + GW0_PITCH_PAD;
   const int i = blockIdx.y;
-  const long long b0 = (long long)blockIdx.x * GW0_CHUNK;
-  const int n = (int)((B - b0) < GW0_CHUNK ? (B - b0) : GW0_CHUNK);
+  const long long b0 = (long long)blockIdx.x * chunk;
+  const int n = (int)((B - b0) < chunk ? (B - b0) : chunk);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short* seg = ws_seg + (size_t)i * B + b0;
   const float4* rec = ws_rec + (size_t)i * B + b0;
-  for (int k = threadIdx.x; k < seg0; k += 256) s_cnt[k] = 0;
+  for (int k = threadIdx.x; k < seg0; k += GW0_THREADS) s_cnt[k] = 0;
+  for (int k = threadIdx.x; k < nodes0 * pitch; k += GW0_THREADS) slab[k] = 0.f;
   __syncthreads();
   // histogram with warp-aggregated shared atomics (coherent batches put a whole warp into one bin)
-  for (int t0 = warp * 32; t0 < n; t0 += 256) {
+  for (int t0 = warp * 32; t0 < n; t0 += GW0_THREADS) {
     const int t = t0 + lane;
     const int key = t < n ? (int)seg[t] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -619,7 +628,7 @@ __global__ void __launch_bounds__(256) gw0_chunk_kernel(long long B, int IN, int
     }
   }
   __syncthreads();
-  for (int t0 = warp * 32; t0 < n; t0 += 256) {
+  for (int t0 = warp * 32; t0 < n; t0 += GW0_THREADS) {
     const int t = t0 + lane;
     const int key = t < n ? (int)seg[t] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -627,33 +636,34 @@ __global__ void __launch_bounds__(256) gw0_chunk_kernel(long long B, int IN, int
     int base = 0;
     if (key >= 0 && lane == leader) base = atomicAdd(&s_pos[key], __popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (key >= 0) s_ent[base + __popc(peers & ((1u << lane) - 1u))] = ((unsigned)key << 16) | (unsigned)t;
+    if (key >= 0) s_ent[base + __popc(peers & ((1u << lane) - 1u))] = ((unsigned)key << 14) | (unsigned)t;
   }
   __syncthreads();
-  // every warp reduces blocks of 64 consecutive sorted entries; a segment change inside a block flushes
-  for (int k0 = warp * GW0_BLOCK; k0 < n; k0 += 8 * GW0_BLOCK) {
+  // every warp reduces blocks of consecutive sorted entries; a segment change inside a block flushes to the slab
+  const bool hi = lane + 32 < hid, lo = lane < hid;
+  for (int k0 = warp * GW0_BLOCK; k0 < n; k0 += GW0_WARPS * GW0_BLOCK) {
     const int k1 = k0 + GW0_BLOCK < n ? k0 + GW0_BLOCK : n;
-    int cur = (int)(s_ent[k0] >> 16);
+    int cur = (int)(s_ent[k0] >> 14);
     float acc[N][2];
 #pragma unroll
     for (int j = 0; j < N; ++j) acc[j][0] = acc[j][1] = 0.f;
     auto flush = [&](int sg) {
+      float* dst = slab + (size_t)(sg * stride) * pitch + lane;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        if (lane < hid && acc[j][0] != 0.f) hoir::red_add(gw0 + ((size_t)lane * IN + i) * nodes0 + sg * stride + j, acc[j][0]);
-        if (lane + 32 < hid && acc[j][1] != 0.f)
-          hoir::red_add(gw0 + ((size_t)(lane + 32) * IN + i) * nodes0 + sg * stride + j, acc[j][1]);
+        if (lo && acc[j][0] != 0.f) atomicAdd(dst + j * pitch, acc[j][0]);
+        if (hi && acc[j][1] != 0.f) atomicAdd(dst + j * pitch + 32, acc[j][1]);
         acc[j][0] = acc[j][1] = 0.f;
       }
     };
-#pragma unroll 4
+#pragma unroll 8
     for (int k = k0; k < k1; ++k) {
       const unsigned e = s_ent[k];
-      const int t = (int)(e & 0xffffu), sg = (int)(e >> 16);
+      const int t = (int)(e & 0x3fffu), sg = (int)(e >> 14);
       const float4 rc = __ldg(rec + t);
       const float* grow = ws_g0 + (size_t)(b0 + t) * hid;
-      const float g0 = __ldg(grow + lane);
-      const float g1 = lane + 32 < hid ? __ldg(grow + 32 + lane) : 0.f;
+      const float g0 = lo ? __ldg(grow + lane) : 0.f;
+      const float g1 = hi ? __ldg(grow + 32 + lane) : 0.f;
       if (sg != cur) {
         flush(cur);
         cur = sg;
@@ -667,6 +677,15 @@ __global__ void __launch_bounds__(256) gw0_chunk_kernel(long long B, int IN, int
     }
     flush(cur);
   }
+  __syncthreads();
+  for (int k = threadIdx.x; k < hid * nodes0; k += GW0_THREADS) {
+    const int o = k / nodes0, q = k - o * nodes0;
+    const float v = slab[(size_t)q * pitch + o];
+    if (v != 0.f) hoir::red_add(gw0 + ((size_t)o * IN + i) * nodes0 + q, v);
+  }
+}
+inline size_t gw0_smem_bytes(int nodes0, int hid) {
+  return (size_t)GW0_CHUNK * 4 + 2 * GW0_MAXSEG * 4 + (size_t)nodes0 * (hid + GW0_PITCH_PAD) * 4;
 }
 
 struct FusedEntry {
@@ -913,7 +932,7 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
   const bool use_tc = e->train_tc != nullptr && !no_tc;
   const int in_f = m->layers[0].in_features, hid = m->layers[0].out_features;
   const bool two_pass = use_tc && x != nullptr && B >= 32768 && !no_2p && p.seg0 <= GW0_MAXSEG && hid <= 64 &&
-                        m->layers[0].n == 3;
+                        m->layers[0].n == 3 && gw0_smem_bytes(p.nodes0, hid) <= 200 * 1024;
   if (two_pass) {
     const size_t b_al = ((size_t)B + 63) & ~(size_t)63;
     const size_t n_g0 = b_al * hid * sizeof(float), n_rec = b_al * in_f * sizeof(float4), n_seg = b_al * in_f * sizeof(unsigned short);
@@ -946,8 +965,14 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
   HOIR_CHECK_CUDA(cudaGetLastError());
   if (two_pass) {
     const int stride = hoir::piecewise_stride(m->layers[0].kind, m->layers[0].n);
-    const dim3 grid2((unsigned)((B + GW0_CHUNK - 1) / GW0_CHUNK), (unsigned)in_f);
-    gw0_chunk_kernel<3><<<grid2, 256, 0, st>>>(B, in_f, hid, p.seg0, stride, p.nodes0, p.ws_seg, p.ws_rec, p.ws_g0, p.gw[0]);
+    // one wave of 2 CTAs per SM when the batch is large enough; chunks of 2048 .. 16384 samples
+    const long long want = (2LL * num_sms_fused() + in_f - 1) / in_f;
+    long long chunk = ((B + want - 1) / want + 255) & ~255LL;
+    chunk = chunk < 2048 ? 2048 : (chunk > GW0_CHUNK ? GW0_CHUNK : chunk);
+    const dim3 grid2((unsigned)((B + chunk - 1) / chunk), (unsigned)in_f);
+    const size_t smem2 = gw0_smem_bytes(p.nodes0, hid);
+    HOIR_CHECK_CUDA(cudaFuncSetAttribute(gw0_slab_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    gw0_slab_kernel<3><<<grid2, GW0_THREADS, smem2, st>>>(B, (int)chunk, in_f, hid, p.seg0, stride, p.nodes0, p.ws_seg, p.ws_rec, p.ws_g0, p.gw[0]);
     HOIR_CHECK_CUDA(cudaGetLastError());
   }
   if (tail != nullptr && !tail_inside) return launch_tail(*tail, st);
