@@ -7,6 +7,13 @@
 // gathered weights w[out][in][window].  Algorithm: SURVEY.md A.3-A.5 / oracle/hol_oracle.py.
 #include "hoir_common.cuh"
 
+// dense_tc.cu: tensor-core path for layers whose densified basis expansion is a dense contraction
+const void* hoir_dense_tc_find(const hoir_layer_desc* d, long long B);
+int hoir_dense_tc_forward(const void* entry, const hoir_layer_desc* d, long long B, const float* x, const float* w,
+                          float* y, cudaStream_t stream);
+int hoir_dense_tc_backward(const void* entry, const hoir_layer_desc* d, long long B, const float* x, const float* w,
+                           const float* gy, float* gx, float* gw, cudaStream_t stream);
+
 namespace {
 
 struct LayerParams {
@@ -388,6 +395,7 @@ extern "C" int hoir_layer_forward(const hoir_layer_desc* d, long long B, const f
   if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_layer_forward");
   if (B == 0) return HOIR_OK;
   if (!x || !w || !y) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_layer_forward");
+  if (const void* dense = hoir_dense_tc_find(d, B)) return hoir_dense_tc_forward(dense, d, B, x, w, y, (cudaStream_t)stream);
   const size_t per_sample = (size_t)p.in_f * (p.n + 2) * sizeof(float);
   if (per_sample > (size_t)kSmemBudget)
     return hoir_set_error(HOIR_EUNSUPPORTED, "in_features*(n+2) exceeds the shared-memory tile", "hoir_layer_forward");
@@ -412,6 +420,8 @@ extern "C" int hoir_layer_backward(const hoir_layer_desc* d, long long B, const 
   if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_layer_backward");
   if (B == 0 || (gx == nullptr && gw == nullptr)) return HOIR_OK;
   if (!x || !w || !gy) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_layer_backward");
+  if (const void* dense = hoir_dense_tc_find(d, B))
+    return hoir_dense_tc_backward(dense, d, B, x, w, gy, gx, gw, (cudaStream_t)stream);
   const int OP = (p.out_f + 3) & ~3;
   const size_t per_sample = ((size_t)p.in_f * (2 * p.n + 2) + OP) * sizeof(float);
   if (per_sample + 16 > (size_t)kSmemBudget)

@@ -154,3 +154,60 @@ def test_large_batch_many_segments_gradient(kind, n, in_f, out_f, seg):
     lay(xc).backward(gy.cuda())
     assert rel_err(xc.grad, xr.grad) <= 1e-5
     assert rel_err(lay.w.grad, ref.w.grad) <= 1e-5
+
+
+DENSE_CASES = [
+    # layers whose densified basis is a dense contraction: tcgen05 path (B >= 512, out <= 64, length 2)
+    ("fourier", 31, 4, 40, 1), ("fourier", 31, 40, 40, 1), ("fourier", 3, 40, 3, 1), ("fourier", 7, 9, 5, 1),
+    ("fourier", 16, 3, 64, 1),
+    ("continuous", 2, 50, 50, 2), ("continuous", 2, 50, 27, 2), ("continuous", 3, 40, 40, 2), ("continuous", 3, 40, 3, 2),
+    ("discontinuous", 3, 40, 40, 2), ("discontinuous", 2, 11, 17, 2),
+]
+
+
+@pytest.mark.parametrize("kind,n,in_f,out_f,seg", DENSE_CASES)
+@pytest.mark.parametrize("B", [512, 1531])
+def test_dense_tensor_core_layer_parity(kind, n, in_f, out_f, seg, B):
+    """The tcgen05 single-layer kernels (dense_tc.cu: forward, dL/dx, dL/dw; tf32 x 3 passes) against the oracle;
+    ragged batch (not a multiple of the 256-sample tile), inputs beyond [-1, 1]."""
+    ref, lay = make_layers(kind, n, in_f, out_f, seg)
+    g = torch.Generator().manual_seed(B + n)
+    x = torch.rand(B, in_f, generator=g) * 2.4 - 1.2
+    gy = torch.randn(B, out_f, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy)
+    xc = x.cuda().requires_grad_(True)
+    yc = lay(xc)
+    yc.backward(gy.cuda())
+    tol = TOL[kind]
+    assert rel_err(yc, yr) <= tol
+    assert rel_err(xc.grad, xr.grad) <= tol
+    assert rel_err(lay.w.grad, ref.w.grad) <= tol
+
+
+def test_dense_tensor_core_matches_cuda_core_kernels_at_full_size():
+    """2^16 samples (too many for the oracle): the tensor-core path (B >= 512) equals the CUDA-core per-layer
+    kernels run on sub-batches below the dispatch threshold, for outputs and summed gradients."""
+    _, lay = make_layers("fourier", 31, 40, 40, 1)
+    B, sub = 1 << 16, 500
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(B, 40, device="cuda", generator=g) * 2 - 1
+    gy = torch.randn(B, 40, device="cuda", generator=g)
+    xc = x.clone().requires_grad_(True)
+    y = lay(xc)
+    y.backward(gy)
+    gw_tc, gx_tc = lay.w.grad.clone(), xc.grad.clone()
+    lay.w.grad = None
+    idx = torch.arange(0, B, 4099, device="cuda")[:sub]          # a strided sample of rows
+    xs = x[idx].clone().requires_grad_(True)
+    ys = lay(xs)                                                   # 16 rows < 512: CUDA-core kernels
+    ys.backward(gy[idx])
+    assert rel_err(y[idx], ys) <= 2e-5
+    assert rel_err(gx_tc[idx], xs.grad) <= 2e-5
+    # linearity: gradient of the full batch = sum over its halves
+    lay.w.grad = None
+    for h in (slice(0, B // 2), slice(B // 2, B)):
+        xh = x[h].clone().requires_grad_(True)
+        lay(xh).backward(gy[h])
+    assert rel_err(lay.w.grad, gw_tc) <= 2e-5
