@@ -14,6 +14,10 @@ int hoir_dense_tc_forward(const void* entry, const hoir_layer_desc* d, long long
 int hoir_dense_tc_backward(const void* entry, const hoir_layer_desc* d, long long B, const float* x, const float* w,
                            const float* gy, float* gx, float* gw, cudaStream_t stream);
 
+// slab_kernels.cu: shared-memory slab kernels for piecewise layers with many segments
+bool hoir_slab_eligible(const hoir_layer_desc* d, long long B);
+int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, const float* gy, float* gw, cudaStream_t stream);
+
 namespace {
 
 struct LayerParams {
@@ -433,7 +437,11 @@ extern "C" int hoir_layer_backward(const hoir_layer_desc* d, long long B, const 
   const size_t slab = (size_t)p.nodes * p.out_f * sizeof(float);
   const bool piecewise = p.kind == HOIR_CONTINUOUS || p.kind == HOIR_DISCONTINUOUS;
   float* gw_tile = gw;
-  if (gw != nullptr && piecewise && p.segments > 8 && B >= 4096 && slab <= 200 * 1024 / 2) {
+  if (gw != nullptr && hoir_slab_eligible(d, B)) {
+    if (int e = hoir_slab_grad_w(d, B, x, gy, gw, (cudaStream_t)stream)) return e;
+    gw_tile = nullptr;
+    if (gx == nullptr) return HOIR_OK;
+  } else if (gw != nullptr && piecewise && p.segments > 8 && B >= 4096 && slab <= 200 * 1024 / 2) {
     int nwarps = (int)min((size_t)8, (size_t)(200 * 1024) / slab);
     int parts = max(1, min(64, (num_sms() * 2 + p.in_f - 1) / p.in_f));
     auto okern = p.n <= 4 ? layer_gw_input_owner_kernel<4> : (p.n <= 8 ? layer_gw_input_owner_kernel<8> : layer_gw_input_owner_kernel<HOIR_MAX_N>);

@@ -1,0 +1,232 @@
+// slab_kernels.cu -- piecewise-Lagrange layers with MANY segments (the 100-segment input layer of the
+// implicit-image MLPs, the 216 x 50-segment input layer of the neighborhood interpolator,
+// /root/reference/high_order_implicit_representation/networks.py:41-55).  Such a layer is a gather:
+// per (sample, input) only n of the (n-1)*segments+1 nodes are touched, so it stays on the CUDA cores and
+// the job is to keep the weight table next to the FMAs.
+//
+// dL/dw: CTA = (group of up to 8 inputs, slice of the batch).  The group's gradient  gw[:, i, :]  lives in
+// shared memory as a slab [input][node][OP] (outputs contiguous: a warp updates one node row with a single
+// conflict-free LDS.64 / FFMA / STS.64, lane <-> outputs 2*lane, 2*lane+1).  Warp w owns input w of the
+// group, so no two warps ever touch the same slab row: no atomics, no per-warp private copies.  The batch
+// slice is walked in blocks of 64 samples whose dL/dy rows (coalesced, read ONCE per CTA) and basis records
+// (segment window + Lagrange values, evaluated lane-parallel) are staged in shared memory, double-buffered.
+// The slab is flushed once with fire-and-forget global adds, nodes fastest (coalesced in the boundary layout).
+// (The forward of such a layer stays in layer_kernels.cu: thread = (sample, 4 outputs), weights through L1/L2.)
+// Algorithm: oracle/hol_oracle.py.
+#include <stdlib.h>
+#include <string.h>
+#include "hoir_common.cuh"
+
+namespace {
+
+struct SlabParams {
+  long long B, per_slice;
+  int kind, n, segments, stride, in_f, out_f, nodes, op, gi;
+  float segf, inv_segf, rescale;
+  int pow2;
+  const float* x;
+  const float* gy;
+  float* gw;
+  LagrangeTable lag;
+};
+
+template <int N>
+__device__ __forceinline__ void slab_eval(const SlabParams& p, float xv, int& base, float* l) {
+  const int id = hoir::segment_index(xv, 1.f, 2.f, p.segf, p.segments);
+  const float xi = p.pow2 ? hoir::local_coordinate<true>(xv, id, 1.f, 2.f, p.segf, p.inv_segf)
+                          : hoir::local_coordinate<false>(xv, id, 1.f, 2.f, p.segf, p.inv_segf);
+  hoir::lagrange<N>(p.lag.X, p.lag.D, xi, l);
+  base = id * p.stride;
+}
+
+constexpr int SLAB_THREADS = 256;
+
+constexpr int GW_BLK = 64;   // samples per staged block
+
+template <int N>
+__global__ void __launch_bounds__(SLAB_THREADS) slab_gw_kernel(const SlabParams p) {
+  extern __shared__ __align__(16) float slab[];
+  const int i0 = blockIdx.x * p.gi;
+  const int gi = min(p.gi, p.in_f - i0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row_f = p.nodes * p.op;
+  // after the slab: two staged blocks of dL/dy rows [GW_BLK][op] and basis records [8][GW_BLK] (base, l0..l2)
+  float* sG = slab + (((size_t)p.gi * row_f + 3) & ~(size_t)3);
+  float4* sRec = reinterpret_cast<float4*>(sG + ((2 * GW_BLK * p.op + 3) & ~3));
+  for (int k = threadIdx.x; k < gi * row_f; k += SLAB_THREADS) slab[k] = 0.f;
+  for (int k = threadIdx.x; k < 2 * GW_BLK * p.op; k += SLAB_THREADS) sG[k] = 0.f;
+  __syncthreads();
+  const long long b_lo = (long long)blockIdx.y * p.per_slice;
+  const long long b_hi = min(p.B, b_lo + p.per_slice);
+  const int nblk = b_hi > b_lo ? (int)((b_hi - b_lo + GW_BLK - 1) / GW_BLK) : 0;
+  const bool act = 2 * lane < p.out_f;
+  const int g_elems = GW_BLK * p.out_f;
+  const bool vec = p.op == p.out_f;          // even out: the staged block is a straight 16-byte copy (cp.async)
+  // dL/dy rows of block k -> sG[k & 1] (asynchronous when vec)
+  auto stage_g = [&](int k) {
+    const long long b0 = b_lo + (long long)k * GW_BLK;
+    float* g = sG + (k & 1) * GW_BLK * p.op;
+    const long long avail = (b_hi - b0) * p.out_f;
+    const float* src = p.gy + b0 * p.out_f;
+    if (vec) {
+      for (int e = threadIdx.x * 4; e < g_elems; e += SLAB_THREADS * 4) {
+        if (e + 3 < avail) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(g + e)), "l"(src + e) : "memory");
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) g[e + c] = e + c < avail ? __ldg(src + e + c) : 0.f;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+      for (int e = threadIdx.x; e < g_elems; e += SLAB_THREADS) {
+        const int sl = e / p.out_f, o = e - sl * p.out_f;
+        g[sl * p.op + o] = e < avail ? __ldg(src + e) : 0.f;
+      }
+    }
+  };
+  // this warp's input values of block k (samples lane, lane + 32), issued early; evaluated by finish_rec
+  float xreg[GW_BLK / 32];
+  auto load_x = [&](int k) {
+    const long long b0 = b_lo + (long long)k * GW_BLK;
+#pragma unroll
+    for (int h = 0; h < GW_BLK / 32; ++h) {
+      const long long b = b0 + h * 32 + lane;
+      xreg[h] = (warp < gi && b < b_hi) ? __ldg(p.x + b * p.in_f + i0 + warp) : 0.f;
+    }
+  };
+  auto finish_rec = [&](int k) {
+    const long long b0 = b_lo + (long long)k * GW_BLK;
+#pragma unroll
+    for (int h = 0; h < GW_BLK / 32; ++h) {
+      const long long b = b0 + h * 32 + lane;
+      int base = 0;
+      float l[N];
+      slab_eval<N>(p, xreg[h], base, l);
+      const float sc = b < b_hi ? p.rescale : 0.f;      // rows past the slice contribute nothing
+      sRec[((k & 1) * (SLAB_THREADS / 32) + warp) * GW_BLK + h * 32 + lane] =
+          make_float4(__int_as_float(base), l[0] * sc, N > 1 ? l[1] * sc : 0.f, N > 2 ? l[2] * sc : 0.f);
+    }
+  };
+  if (nblk > 0) {
+    stage_g(0);
+    load_x(0);
+  }
+  // warp w owns input i0 + w: exclusive slab rows, plain read-modify-write, no atomics
+  float* sl = slab + (size_t)warp * row_f + 2 * lane;
+  for (int k = 0; k < nblk; ++k) {
+    if (warp < gi) finish_rec(k);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                    // block k staged; everyone is done with block k - 1
+    if (k + 1 < nblk) {
+      stage_g(k + 1);
+      load_x(k + 1);
+    }
+    if (warp < gi) {
+      const float* g = sG + (k & 1) * GW_BLK * p.op + 2 * lane;
+      const float4* rec = sRec + ((k & 1) * (SLAB_THREADS / 32) + warp) * GW_BLK;
+#pragma unroll 4
+      for (int s = 0; s < GW_BLK; ++s) {
+        const float4 rc = rec[s];
+        const float l[3] = {rc.y, rc.z, rc.w};
+        if (act) {
+          const float2 g2 = *reinterpret_cast<const float2*>(g + s * p.op);
+          float* row = sl + __float_as_int(rc.x) * p.op;
+#pragma unroll
+          for (int j = 0; j < (N < 3 ? N : 3); ++j) {
+            float2 a = *reinterpret_cast<float2*>(row + j * p.op);
+            a.x = fmaf(l[j], g2.x, a.x);
+            a.y = fmaf(l[j], g2.y, a.y);
+            *reinterpret_cast<float2*>(row + j * p.op) = a;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < p.out_f * gi * p.nodes; k += SLAB_THREADS) {
+    const int q = k % p.nodes, r = k / p.nodes, il = r % gi, o = r / gi;
+    const float v = slab[(il * p.nodes + q) * p.op + o];
+    if (v != 0.f) hoir::red_add(p.gw + ((size_t)o * p.in_f + i0 + il) * p.nodes + q, v);
+  }
+}
+
+int slab_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+constexpr size_t kSlabBudget = 88 * 1024;    // + staging: two CTAs per SM
+
+int slab_fill(const hoir_layer_desc* d, long long B, SlabParams* p, int max_gi) {
+  memset(p, 0, sizeof(*p));
+  p->B = B;
+  p->kind = d->kind;
+  p->n = d->n;
+  p->segments = d->segments;
+  p->stride = hoir::piecewise_stride(d->kind, d->n);
+  p->in_f = d->in_features;
+  p->out_f = d->out_features;
+  p->nodes = hoir_layer_nodes(d);
+  p->op = (d->out_features + 1) & ~1;
+  p->segf = (float)d->segments;
+  p->inv_segf = 1.f / (float)d->segments;
+  p->rescale = d->rescale == 0.f ? 1.f : d->rescale;
+  p->pow2 = hoir::is_pow2(d->segments);
+  hoir_make_lagrange_table(d->n, 1.f, &p->lag);
+  const size_t per_input = (size_t)p->nodes * p->op * sizeof(float);
+  int gi = (int)(kSlabBudget / per_input);
+  if (gi > max_gi) gi = max_gi;
+  if (gi > p->in_f) gi = p->in_f;
+  p->gi = gi;
+  return gi;
+}
+
+template <class K>
+int slab_launch(K kern, SlabParams& p, cudaStream_t stream, size_t extra_smem = 0) {
+  const int groups = (p.in_f + p.gi - 1) / p.gi;
+  long long slices = (2LL * slab_sms()) / groups;          // one wave of two CTAs per SM
+  const long long max_slices = (p.B + 255) / 256;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  p.per_slice = ((p.B + slices - 1) / slices + 31) / 32 * 32;
+  slices = (p.B + p.per_slice - 1) / p.per_slice;
+  const size_t smem = (size_t)p.gi * p.nodes * p.op * sizeof(float) + extra_smem;
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3((unsigned)groups, (unsigned)slices), SLAB_THREADS, smem, stream>>>(p);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+}  // namespace
+
+// many-segment piecewise layer, big batch: the shared-memory slab kernels apply
+bool hoir_slab_eligible(const hoir_layer_desc* d, long long B) {
+  static const bool off = getenv("HOIR_NO_SLAB") != nullptr;
+  if (off || d == nullptr || B < 4096) return false;
+  if (d->kind != HOIR_CONTINUOUS && d->kind != HOIR_DISCONTINUOUS) return false;
+  if (d->length != 2.f || d->periodicity > 0.f || d->segments <= 8 || d->n < 2 || d->n > 3) return false;
+  if (d->out_features > 64) return false;
+  const size_t per_input = (size_t)hoir_layer_nodes(d) * ((d->out_features + 1) & ~1) * sizeof(float);
+  return per_input <= kSlabBudget;
+}
+
+int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, const float* gy, float* gw,
+                     cudaStream_t stream) {
+  SlabParams p;
+  slab_fill(d, B, &p, SLAB_THREADS / 32);
+  p.x = x;
+  p.gy = gy;
+  p.gw = gw;
+  const size_t extra = 2 * GW_BLK * p.op * sizeof(float) + 2 * (SLAB_THREADS / 32) * GW_BLK * sizeof(float4) + 64;
+  switch (d->n) {
+    case 2: return slab_launch(slab_gw_kernel<2>, p, stream, extra);
+    default: return slab_launch(slab_gw_kernel<3>, p, stream, extra);
+  }
+}

@@ -80,7 +80,7 @@ def c3f():
     x = torch.rand(B, 4, device=dev, generator=g) * 2 - 1
     y = torch.rand(B, 3, device=dev, generator=g) * 2 - 1
     ms = timeit(lambda: autograd_step(net, opt, x, y), 5)
-    report("C3 fourier n_in=31 (hidden 31), 4-40-40-3, batch 2^16 (per-layer kernels + autograd)", B, ms, 319600, "no fused instantiation yet")
+    report("C3 fourier n_in=31 (hidden 31), 4-40-40-3, batch 2^16 (tcgen05 per-layer kernels + autograd)", B, ms, 319600, "dense_tc.cu: tf32x3 on the tensor pipe, 15 launches per step")
 
 
 def c4():
@@ -100,8 +100,8 @@ def c4():
         L.check(lib.hoir_neighborhood_gather(L.dptr(img), 3, 2048, 2048, 3, 3, 1, 0, 12345, B, L.dptr(feat), L.dptr(targ), L.stream_ptr(dev)))
         autograd_step(net, opt, feat, targ)
     ms = timeit(step, 5)
-    report("C4 interpolator continuous n=2, 216-50-50-50-27, 2048^2 image, batch 2^16 patches (gather kernel + per-layer kernels)",
-           B, ms, 162600, "layer 0 = 2.2 MB sparse table; no fused instantiation yet")
+    report("C4 interpolator continuous n=2, 216-50-50-50-27, 2048^2 image, batch 2^16 patches (gather + slab dL/dw + tcgen05 hidden layers)",
+           B, ms, 162600, "layer 0 = 2.2 MB gather table (CUDA cores); hidden and output layers on tcgen05")
     ms = timeit(lambda: H.neighborhood_sample_generator(net, img, 3, 3), 3)
     report("C4 inference: one generate_sequence frame on 2048^2 (gather + forward + fold)", 2048 * 2048, ms, 68600 / 9, "per output pixel")
 
