@@ -1,0 +1,180 @@
+"""The caller of the hot path: what ``examples/implicit_images.py`` does with Lightning's ``Trainer``,
+``ImageDataModule`` and the ``ImageGenerator`` callback
+(/root/reference/examples/implicit_images.py:31-52, /root/reference/high_order_implicit_representation/
+single_image_dataset.py:286-333, rendering.py:166-222) as a plain loop over the fused engine:
+
+    epochs x (shuffled pixel batches -> one fused training step each) -> epoch ``train_loss`` ->
+    ReduceLROnPlateau / ExponentialLR on it (networks.py:104-118) -> render the image -> checkpoint
+
+Lightning, Hydra and TensorBoard are not installable here and are host-side harness; this module keeps the
+``cfg`` keys, the ``train_loss`` metric name and the Lightning checkpoint layout so runs are interchangeable.
+SURVEY.md section 8f, row 1.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from typing import Callable, List, Optional, Union
+
+import torch
+from torch import Tensor
+
+from . import _lib, parallel
+from .config import to_cfg
+from .datasets import _load_image_u8, image_to_dataset
+from .engine import FusedTrainer
+from .networks import Net
+from .rendering import render_image
+
+logger = logging.getLogger(__name__)
+
+
+class _LrSchedule:
+    """``optimizer.scheduler`` of the reference config on a bare learning rate (networks.py:104-118):
+    'plateau' = ReduceLROnPlateau(patience, factor) on the epoch train_loss, 'exponential' = ExponentialLR(gamma)."""
+
+    def __init__(self, opt_cfg, lr: float):
+        get = opt_cfg.get if hasattr(opt_cfg, "get") else (lambda k, d=None: getattr(opt_cfg, k, d))
+        self.kind = get("scheduler", None)
+        self.lr = lr
+        self.patience = int(get("patience", 10) or 10)
+        self.factor = float(get("factor", 0.1) or 0.1)
+        self.gamma = float(get("gamma", 0.99) or 0.99)
+        self.best = math.inf
+        self.bad = 0
+
+    def step(self, metric: float) -> float:
+        if self.kind == "plateau":          # torch defaults: mode='min', threshold=1e-4 'rel', cooldown=0
+            if metric < self.best * (1.0 - 1e-4):
+                self.best, self.bad = metric, 0
+            else:
+                self.bad += 1
+            if self.bad > self.patience:
+                self.lr *= self.factor
+                self.bad = 0
+        elif self.kind == "exponential":
+            self.lr *= self.gamma
+        return self.lr
+
+
+class ImageTrainer:
+    """Fit ``Net(cfg)`` to one image.  ``sampling='shuffle'`` draws the reference's shuffled pixel batches
+    (DataLoader(shuffle=True) over image_to_dataset rows) on the device; ``sampling='tiles'`` walks contiguous
+    pixel ranges in random order with coordinates and targets generated in-kernel (no dataset in HBM)."""
+
+    def __init__(self, cfg, image: Union[str, Tensor], device: str = "cuda", sampling: str = "shuffle",
+                 process_group=None, seed: int = 0):
+        if sampling not in ("shuffle", "tiles"):
+            raise ValueError(f"sampling {sampling} not recognized")
+        self.cfg = to_cfg(cfg)
+        self.device = torch.device(device)
+        self.sampling = sampling
+        self.rotations = int(self.cfg.rotations)
+        self.batch_size = int(self.cfg.batch_size)
+        self.image_u8 = _load_image_u8(image).to(self.device).contiguous()
+        self.rows, self.cols = int(self.image_u8.shape[0]), int(self.image_u8.shape[1])
+        self.net = Net(self.cfg).to(self.device)
+        self.rank, self.world = parallel.world_info(process_group)
+        self.gen = torch.Generator(device=self.device).manual_seed(seed)     # same stream on every rank
+        opt = self.cfg.optimizer
+        self.schedule = _LrSchedule(opt, float(opt.lr))
+        self.fused: Optional[FusedTrainer] = None
+        self.optimizer = None
+        if self.net.model.fused_supported():
+            self.fused = FusedTrainer(self.net.model, optimizer=opt.name, lr=float(opt.lr),
+                                      process_group=process_group)
+        else:                                   # per-layer kernels under autograd (Fourier, polynomial, ...)
+            conf = self.net.configure_optimizers()
+            self.optimizer = conf[0][0] if isinstance(conf, tuple) else conf
+        self._pos = self._targets = None
+        self.history: List[float] = []
+
+    # ------------------------------------------------------------------------------------------------
+    def _dataset(self):
+        if self._pos is None:
+            self._targets, self._pos, _ = image_to_dataset(self.image_u8, rotations=self.rotations,
+                                                           device=str(self.device))
+        return self._pos, self._targets
+
+    def _set_lr(self, lr: float) -> None:
+        if self.fused is not None:
+            self.fused.lr = lr
+        else:
+            for g in self.optimizer.param_groups:
+                g["lr"] = lr
+
+    def _step(self, x: Optional[Tensor], y: Optional[Tensor], first: int, count: int, global_batch: int) -> Tensor:
+        if self.fused is not None:
+            if x is None:
+                return self.fused.train_step_mesh(self.image_u8, self.rotations, first, count, global_batch=global_batch)
+            return self.fused.train_step(x, y, global_batch=global_batch)
+        if x is None:
+            pos, tg = self._dataset()
+            x, y = pos[first:first + count], tg[first:first + count]
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.net.training_step((x, y), 0)
+        loss.backward()
+        if self.world > 1:
+            for p in self.net.parameters():
+                parallel.allreduce_sum_(p.grad, None)
+                p.grad /= self.world
+        self.optimizer.step()
+        return loss.detach().reshape(1)
+
+    def train_epoch(self) -> float:
+        """One pass over the image; every rank takes its share of each global batch.  Returns train_loss."""
+        n = self.rows * self.cols
+        bs = self.batch_size
+        total = torch.zeros(1, device=self.device)
+        steps = 0
+        if self.sampling == "shuffle":
+            pos, tg = self._dataset()
+            perm = torch.randperm(n, device=self.device, generator=self.gen)
+            for k in range(0, n, bs * self.world):
+                idx = perm[k:k + bs * self.world]
+                mine = idx[self.rank::self.world]
+                if mine.numel() == 0:
+                    continue
+                total += self._step(pos[mine], tg[mine], 0, 0, global_batch=int(idx.numel()))
+                steps += 1
+        else:
+            n_blocks = (n + bs - 1) // bs
+            order = torch.randperm(n_blocks, device=self.device, generator=self.gen).tolist()
+            for k in range(0, n_blocks, self.world):
+                blocks = order[k:k + self.world]
+                sizes = [min(bs, n - b * bs) for b in blocks]
+                if self.rank < len(blocks):
+                    b = blocks[self.rank]
+                    total += self._step(None, None, b * bs, sizes[self.rank], global_batch=sum(sizes))
+                    steps += 1
+        self.net.global_step += steps
+        return float(total.item()) / max(steps, 1)
+
+    def fit(self, max_epochs: Optional[int] = None,
+            on_epoch_end: Optional[Callable[["ImageTrainer", int, float], None]] = None) -> List[float]:
+        epochs = int(max_epochs if max_epochs is not None else self.cfg.max_epochs)
+        for epoch in range(epochs):
+            loss = self.train_epoch()
+            self.history.append(loss)
+            self.net.current_epoch = epoch + 1
+            self.net.log("train_loss", loss)
+            self._set_lr(self.schedule.step(loss))
+            logger.info("epoch %d train_loss %.6f lr %.3g", epoch, loss, self.schedule.lr)
+            if on_epoch_end is not None:
+                on_epoch_end(self, epoch, loss)
+        return self.history
+
+    # ------------------------------------------------------------------------------------------------
+    def render(self) -> Tensor:
+        """ImageGenerator.on_train_epoch_end (rendering.py:195-213): ``[rows, cols, 3]`` in [0, 1]."""
+        if self.fused is not None:
+            return self.fused.render(self.rows, self.cols, self.rotations).reshape(self.rows, self.cols, -1)
+        return render_image(self.net, self.rows, self.cols, self.rotations, batch_size=max(self.batch_size, 1 << 16))
+
+    def psnr(self) -> float:
+        target = self.image_u8.float() / 255.0
+        mse = torch.mean((self.render().clamp(0, 1) - target) ** 2).item()
+        return 10.0 * math.log10(1.0 / max(mse, 1e-12))
+
+    def save_checkpoint(self, path: str) -> None:
+        self.net.save_checkpoint(path)

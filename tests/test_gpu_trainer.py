@@ -1,0 +1,70 @@
+"""The caller of the hot path: epoch loop, lr schedule, render, Lightning-format checkpoint."""
+import os
+
+import pytest
+import torch
+
+import hoir_b200 as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(**kw):
+    cfg = H.images_config(mlp=dict(layer_type="continuous", n=3, n_in=None, n_out=None, n_hidden=None,
+                                   periodicity=None, rescale_output=False, scale=2.0,
+                                   input=dict(segments=20, width=4), output=dict(segments=2, width=3),
+                                   hidden=dict(segments=2, layers=1, width=40)),
+                          batch_size=4096, max_epochs=6, rotations=2,
+                          optimizer=dict(name="adam", lr=3e-3, scheduler="plateau", patience=2, factor=0.5))
+    for k, v in kw.items():
+        cfg[k] = v
+    return cfg
+
+
+def _card(rows=96, cols=128):
+    u = torch.linspace(0, 1, cols).view(1, cols, 1)
+    v = torch.linspace(0, 1, rows).view(rows, 1, 1)
+    img = 0.5 + 0.5 * torch.sin(6.0 * u + 4.0 * v + torch.tensor([0.0, 2.0, 4.0]).view(1, 1, 3))
+    return (img * 255).round().to(torch.uint8)
+
+
+@pytest.mark.parametrize("sampling", ["shuffle", "tiles"])
+def test_image_trainer_fits_and_checkpoints(sampling, tmp_path):
+    torch.manual_seed(0)
+    tr = H.ImageTrainer(_cfg(), _card(), sampling=sampling)
+    assert tr.fused is not None
+    hist = tr.fit()
+    assert len(hist) == 6 and hist[-1] < 0.5 * hist[0]          # the loss goes down
+    img = tr.render()
+    assert img.shape == (96, 128, 3) and torch.isfinite(img).all()
+    path = os.path.join(tmp_path, "last.ckpt")
+    tr.save_checkpoint(path)
+    ckpt = torch.load(path, weights_only=False)
+    assert set(ckpt["state_dict"]) == {"model.model.0.w", "model.model.2.w", "model.model.4.w"}
+    assert ckpt["hyper_parameters"]["mlp"]["hidden"]["width"] == 40
+    net = H.Net.load_from_checkpoint(path, map_location="cuda")
+    again = H.render_image(net, 96, 128, 2)
+    assert torch.allclose(again, img, atol=1e-6)
+
+
+def test_image_trainer_autograd_path_for_fourier():
+    cfg = _cfg(max_epochs=2)
+    cfg.mlp.layer_type = "fourier"
+    cfg.mlp.n = 5
+    torch.manual_seed(0)
+    tr = H.ImageTrainer(cfg, _card(48, 64), sampling="shuffle")
+    assert tr.fused is None                                     # per-layer (tensor-core) kernels under autograd
+    hist = tr.fit()
+    assert len(hist) == 2 and all(h == h for h in hist) and hist[1] < hist[0]
+
+
+def test_plateau_schedule_matches_torch():
+    from hoir_b200.trainer import _LrSchedule
+    opt = dict(name="adam", lr=1e-2, scheduler="plateau", patience=2, factor=0.5)
+    p = torch.nn.Parameter(torch.zeros(1))
+    ref_opt = torch.optim.SGD([p], lr=1e-2)
+    ref = torch.optim.lr_scheduler.ReduceLROnPlateau(ref_opt, patience=2, factor=0.5)
+    mine = _LrSchedule(H.Config(opt), 1e-2)
+    for m in [1.0, 0.9, 0.95, 0.96, 0.97, 0.98, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]:
+        ref.step(m)
+        assert abs(mine.step(m) - ref_opt.param_groups[0]["lr"]) < 1e-12
