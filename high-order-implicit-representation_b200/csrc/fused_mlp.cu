@@ -695,20 +695,23 @@ struct FusedEntry {
   size_t smem_fwd, smem_train;
   void (*train_tc)(const FusedParams);   // tensor-core (tcgen05) training kernel, or nullptr
   size_t smem_tc;
+  void (*fwd_tc)(const FusedParams);     // tensor-core forward kernel (2 CTAs per SM), or nullptr
+  size_t smem_fwd_tc;
 };
 
 template <class S>
 constexpr FusedEntry make_entry() {
   return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
                     fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
-                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4, nullptr, 0};
+                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4, nullptr, 0, nullptr, 0};
 }
 template <class S>
 constexpr FusedEntry make_entry_tc() {
   return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
                     fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
                     (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4,
-                    tc::fused_mlp_tc_kernel<S>, (size_t)tc::TcPlan<S>::SMEM_BYTES};
+                    tc::fused_mlp_tc_kernel<S>, (size_t)tc::TcPlan<S>::SMEM_BYTES,
+                    tc::fused_mlp_tc_fwd_kernel<S>, (size_t)tc::TcFwdPlan<S>::SMEM_BYTES};
 }
 
 // Instantiations: BASELINE.json configs C2/C3 (40-wide, 1 hidden layer, rotations 1 and 2) and
@@ -830,6 +833,15 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
   if (!y) return hoir_set_error(HOIR_EINVAL, "null output pointer", "hoir_mlp_forward");
   p.y = y;
   p.post_scale = post_scale;
+  static const bool no_tc_fwd = getenv("HOIR_NO_TC") != nullptr || getenv("HOIR_NO_TC_FWD") != nullptr;
+  if (e->fwd_tc != nullptr && !no_tc_fwd && B >= 4 * tc::TS) {
+    HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd_tc));
+    const long long tiles_tc = (B + tc::TS - 1) / tc::TS;
+    const long long cap = 2LL * num_sms_fused();
+    e->fwd_tc<<<(int)(tiles_tc < cap ? tiles_tc : cap), tc::NTHREADS, e->smem_fwd_tc, (cudaStream_t)stream>>>(p);
+    HOIR_CHECK_CUDA(cudaGetLastError());
+    return HOIR_OK;
+  }
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
   const long long tiles = (B + BT - 1) / BT;
   const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());

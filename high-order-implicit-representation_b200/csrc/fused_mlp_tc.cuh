@@ -664,4 +664,208 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
   hoir::opt_tail_in_kernel(p.tail);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Forward-only tensor-core kernel (rendering / inference: hoir_mlp_forward): the forward half of the kernel
+// above.  Same thread-pair organisation and FWD product (Phi1 chunks in TMEM x W1 in smem, tf32 x 3 passes);
+// activations never leave registers, the only shared memory is W1 (raw + residual), W2 and the pair-exchange
+// slots (72 KB) and only 256 TMEM columns are allocated, so TWO CTAs share an SM and one CTA's basis / output
+// layer work fills the other's waits on the tensor pipe.
+template <class S>
+struct TcFwdPlan {
+  using P = TcPlan<S>;
+  static constexpr uint32_t OFF_W1R = 0, OFF_W1L = OFF_W1R + P::W1_BYTES, OFF_W2 = OFF_W1L + P::W1_BYTES,
+                            OFF_X = OFF_W2 + P::W2_BYTES, OFF_BAR = OFF_X + P::X_BYTES, SMEM_BYTES = OFF_BAR + 256;
+  static constexpr int TMEM_COLS = 256;
+  static_assert(P::FA_COL + 4 * P::CH_K <= TMEM_COLS, "TMEM plan (forward)");
+};
+
+template <class S>
+__global__ void __launch_bounds__(NTHREADS, 2) fused_mlp_tc_fwd_kernel(const FusedParams p) {
+  using P = TcPlan<S>;
+  using F = TcFwdPlan<S>;
+  constexpr int N = S::N, IN = S::IN, HID = S::HID, OUT = S::OUT, HP = S::HP, OP = S::OP, ND = P::ND, HH = P::HH;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW1R = smem + F::OFF_W1R;
+  uint8_t* sW1L = smem + F::OFF_W1L;
+  float* sW2 = reinterpret_cast<float*>(smem + F::OFF_W2);
+  float* sX = reinterpret_cast<float*>(smem + F::OFF_X);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F::OFF_BAR);
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(F::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bars[B_FFULL0], NSAMPLE_THREADS); mbar_init(&bars[B_FFULL1], NSAMPLE_THREADS);
+    mbar_init(&bars[B_FEMPTY0], 1);  mbar_init(&bars[B_FEMPTY1], 1);
+    mbar_init(&bars[B_D1FULL], 1);   mbar_init(&bars[B_D1EMPTY], NSAMPLE_THREADS);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  {
+    const float* w1 = p.packed + p.off[1];
+    for (uint32_t k = tid; k < (uint32_t)(P::W1_BYTES / 4); k += NTHREADS) {
+      reinterpret_cast<float*>(sW1R)[k] = 0.f;
+      reinterpret_cast<float*>(sW1L)[k] = 0.f;
+    }
+    __syncthreads();
+    for (int k = tid; k < P::KH * HID; k += NTHREADS) {
+      const int o = k % HID, r = k / HID, i = r / ND, q = r - i * ND;
+      const float v = __ldg(w1 + (size_t)r * HP + o);
+      const uint32_t off = sw4_off(o, P::kbase(i) + q, P::W1_RS);
+      *reinterpret_cast<float*>(sW1R + off) = v;
+      *reinterpret_cast<float*>(sW1L + off) = tf32_lo(v);
+    }
+    const float* w2 = p.packed + p.off[2];
+    for (int k = tid; k < S::WO; k += NTHREADS) sW2[k] = __ldg(w2 + k);
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_base_s;
+  const long long tiles = (p.B + TS - 1) / TS;
+
+  if (warp == 8) {
+    const uint32_t leader = elect_one();
+    constexpr uint32_t ID_FWD = make_idesc(128, HID, 0, 0);
+    const uint64_t dW1[2] = {make_desc(smem_u32(sW1R), P::W1_RS), make_desc(smem_u32(sW1L), P::W1_RS)};
+    uint32_t q_chunk = 0, n_tile = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+      if (n_tile > 0) mbar_wait(&bars[B_D1EMPTY], (n_tile - 1) & 1);
+      for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
+        const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
+        mbar_wait(&bars[B_FFULL0 + buf], ph);
+        fence_after();
+        if (leader) {
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+            for (int j = 0; j < P::CH_K / 8; ++j) {
+              const uint32_t ks = (uint32_t)(c * (P::CH_K / 8) + j);
+              const uint32_t koff = (ks >> 2) * 512u + (ks & 3u) * 32u;
+              mma_ts(tmem + P::D1_COL, tmem + P::FA_COL + buf * 2 * P::CH_K + (pass == 1 ? P::CH_K : 0) + j * 8,
+                     dW1[pass == 2] + (uint64_t)(koff >> 4), ID_FWD, (c | pass | j) != 0);
+            }
+          }
+          umma_commit(&bars[B_FEMPTY0 + buf]);
+          if (c == P::NCH - 1) umma_commit(&bars[B_D1FULL]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int hf = warp >> 2;
+    const int s = tid & (TS - 1);
+    const SegConst sc0 = {p.seg0, S::STRIDE, (float)p.seg0, 1.f / (float)p.seg0};
+    const float* w0 = p.packed + p.off[0] + hf * HH;
+    const LagrangeTable& lag = p.lag;
+    const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* xs = sX + (hf * TS + s) * 4;
+    const float* xo = sX + ((hf ^ 1) * TS + s) * 4;
+    uint32_t q_chunk = 0, n_tile = 0;
+    auto layer0 = [&](long long tile_, float* h_) {
+      const long long b_ = tile_ * TS + s;
+      float x0[IN];
+#pragma unroll
+      for (int i = 0; i < IN; ++i) x0[i] = 0.f;
+      if (b_ < p.B) {
+        if (p.x != nullptr) {
+#pragma unroll
+          for (int i = 0; i < IN; ++i) x0[i] = __ldg(p.x + b_ * IN + i);
+        } else {
+          hoir::mesh_position(p.mesh, p.mesh.first_pixel + b_, x0, IN / 2);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < HH; ++o) h_[o] = 0.f;
+#pragma unroll
+      for (int i = 0; i < IN; ++i) {
+        int id;
+        float xi, l[N];
+        if (p.pow2_0) locate<true>(x0[i], sc0, id, xi);
+        else locate<false>(x0[i], sc0, id, xi);
+        hoir::lagrange<N>(lag.X, lag.D, xi, l);
+        contract_fwd_p<N, HH, HP, true>(w0 + ((size_t)i * p.nodes0 + id * S::STRIDE) * HP, l, h_);
+      }
+      float inv_d_ = 1.f;
+      int kidx_ = 0;
+      if (p.normalize) maxabs_pair<HH>(h_, hf, p.norm_eps, xs, xo, warp, inv_d_, kidx_);
+    };
+    float hN[HH];
+    if ((long long)blockIdx.x < tiles) layer0(blockIdx.x, hN);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+      const long long b = tile * TS + s;
+      // ---- hidden layer on the tensor cores: this thread's 4 inputs of every chunk -> TMEM
+#pragma unroll
+      for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
+        const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
+        float v[P::HK], lo[P::HK];
+#pragma unroll
+        for (int m = 0; m < P::QI; ++m) {
+          int id;
+          float xi, l[N];
+          locate2(hN[c * P::QI + m], id, xi);
+          hoir::lagrange<N>(lag.X, lag.D, xi, l);
+          v[m * ND + 0] = id ? 0.f : l[0];
+          v[m * ND + 1] = id ? 0.f : l[1];
+          v[m * ND + 2] = id ? l[0] : l[2];
+          v[m * ND + 3] = id ? l[1] : 0.f;
+          v[m * ND + 4] = id ? l[2] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < P::HK; ++j) lo[j] = tf32_lo(v[j]);
+        mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);
+        fence_after();
+        const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K + hf * P::HK;
+        tmem_st20(col, v);
+        tmem_st20(col + P::CH_K, lo);
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&bars[B_FFULL0 + buf]);
+      }
+      // ---- while the tensor pipe finishes D1: layer 0 of the next tile
+      if (tile + gridDim.x < tiles) layer0(tile + gridDim.x, hN);
+      float h[HH];
+      mbar_wait(&bars[B_D1FULL], n_tile & 1);
+      fence_after();
+      tmem_ld20(tm_lane + P::D1_COL + hf * HH, h);
+      tmem_wait_ld();
+      fence_before();
+      mbar_arrive(&bars[B_D1EMPTY]);
+      float inv_d1 = 1.f;
+      int kidx1 = 0;
+      if (p.normalize) maxabs_pair<HH>(h, hf, p.norm_eps, xs, xo, warp, inv_d1, kidx1);
+      // ---- output layer (FFMA) over own 20 inputs, pair sum
+      float yo[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < HH; ++j) {
+        const int i = hf * HH + j;
+        int id;
+        float xi, l[N];
+        locate2(h[j], id, xi);
+        hoir::lagrange<N>(lag.X, lag.D, xi, l);
+        contract_fwd<N, OUT, OP, false>(sW2 + ((size_t)i * S::NODES_O + id * S::STRIDE) * OP, l, yo);
+      }
+      if (hf == 1) *reinterpret_cast<float4*>(xs) = make_float4(yo[0], yo[1], yo[2], 0.f);
+      bar_pair(warp);
+      if (hf == 0 && b < p.B) {
+        const float4 o4 = *reinterpret_cast<const float4*>(xo);
+        const float other[3] = {o4.x, o4.y, o4.z};
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+          const float yv = yo[o] + other[o];
+          p.y[b * OUT + o] = p.post_scale ? 0.5f * (yv + 1.f) : yv;
+        }
+      }
+      bar_pair(warp);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(F::TMEM_COLS));
+}
+
 }  // namespace tc

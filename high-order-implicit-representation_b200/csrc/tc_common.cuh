@@ -36,8 +36,16 @@ __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::aft
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // (fused_mlp_tc) all 256 sample threads
 __device__ __forceinline__ void bar_samples() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-// the two warps (w, w + 4) that share 32 samples
-__device__ __forceinline__ void bar_pair(int warp) { asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 3)) : "memory"); }
+// the two warps (w, w + 4) that share 32 samples; immediate barrier ids so that ptxas counts 6 named
+// barriers instead of reserving all 16 (which would cap a kernel at one CTA per SM)
+__device__ __forceinline__ void bar_pair(int warp) {
+  switch (warp & 3) {
+    case 0: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+  }
+}
 
 // shared-memory operand in the 128B_BASE32B layout: element (row r, column c), RS = bytes per 4 rows
 __device__ __forceinline__ uint32_t sw4_off(uint32_t r, uint32_t c, uint32_t RS) {

@@ -110,7 +110,7 @@ def c5(tr):
     rows = cols = 8192
     out = torch.empty((rows * cols, 3), device=dev)
     ms = timeit(lambda: tr.render(rows, cols, 2, out=out), 3)
-    report("C5 render 8192x8192, C2 model, rotations=2, one GPU (fused FFMA forward kernel)", rows * cols, ms, 11280, "12 B/pixel written")
+    report("C5 render 8192x8192, C2 model, rotations=2, one GPU (tcgen05 forward kernel, 2 CTAs per SM)", rows * cols, ms, 11280, "12 B/pixel written")
 
 
 if __name__ == "__main__":
