@@ -56,6 +56,13 @@ class OptDesc(C.Structure):
                 ("keep_grad", C.c_int)]
 
 
+HOIR_MAX_PEERS = 16
+
+
+class PeerDesc(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("block", C.c_void_p * HOIR_MAX_PEERS)]
+
+
 class HoirUnsupported(RuntimeError):
     """The fused whole-network kernel has no instantiation for this network."""
 
@@ -98,6 +105,11 @@ _EXPORTS = {
     "hoir_mlp_train_step_fused": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p,
                                             C.POINTER(MeshDesc), C.c_int, C.c_void_p, C.c_float,
                                             C.POINTER(OptDesc), C.c_void_p]),
+    "hoir_peer_stride": (C.c_longlong, [C.POINTER(MlpDesc)]),
+    "hoir_peer_block_floats": (C.c_longlong, [C.POINTER(MlpDesc)]),
+    "hoir_mlp_train_step_fused_peer": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p,
+                                                 C.POINTER(MeshDesc), C.c_int, C.c_void_p, C.c_float,
+                                                 C.POINTER(OptDesc), C.POINTER(PeerDesc), C.c_void_p]),
     "hoir_adam_step": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_longlong, C.c_void_p]),

@@ -853,10 +853,13 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
 namespace {
 
 __global__ void __launch_bounds__(256) opt_tail_kernel(const OptTail t) {
+  if (t.world > 1) hoir::peer_exchange_barrier(t);     // stream order: this GPU's gradient is complete
   hoir::opt_tail_rows(t, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), (int)((gridDim.x * blockDim.x) >> 5),
                       threadIdx.x & 31);
 }
 
+long long boundary_offset(const hoir_mlp_desc* m, int layer);
+long long boundary_offset_fwd(const hoir_mlp_desc* m) { return boundary_offset(m, m->num_layers); }
 long long boundary_offset(const hoir_mlp_desc* m, int layer) {
   long long off = 0;
   for (int l = 0; l < layer; ++l)
@@ -864,13 +867,18 @@ long long boundary_offset(const hoir_mlp_desc* m, int layer) {
   return off;
 }
 
-int fill_tail(const hoir_mlp_desc* m, const hoir_opt_desc* o, OptTail* t, const char* where) {
+long long peer_stride(const hoir_mlp_desc* m) {
+  return (boundary_offset_fwd(m) + 1 + 63) / 64 * 64;
+}
+
+int fill_tail(const hoir_mlp_desc* m, const hoir_opt_desc* o, OptTail* t, const char* where,
+              const hoir_peer_desc* peers = nullptr) {
   memset(t, 0, sizeof(*t));
   if (!mlp_desc_ok(m)) return hoir_set_error(HOIR_EINVAL, "bad network descriptor", where);
   if (!o) return hoir_set_error(HOIR_EINVAL, "null optimizer descriptor", where);
   if (o->kind != HOIR_OPT_ADAM && o->kind != HOIR_OPT_SPARSE_LION)
     return hoir_set_error(HOIR_EINVAL, "optimizer kind not recognized", where);
-  if (!o->flat_w || !o->flat_g || !o->exp_avg || !o->packed || (o->kind == HOIR_OPT_ADAM && !o->exp_avg_sq))
+  if (!o->flat_w || (!o->flat_g && !peers) || !o->exp_avg || !o->packed || (o->kind == HOIR_OPT_ADAM && !o->exp_avg_sq))
     return hoir_set_error(HOIR_EINVAL, "null optimizer state pointer", where);
   if (o->step < 1) return hoir_set_error(HOIR_EINVAL, "step must be >= 1", where);
   t->kind = o->kind;
@@ -898,9 +906,31 @@ int fill_tail(const hoir_mlp_desc* m, const hoir_opt_desc* o, OptTail* t, const 
   t->wd = o->weight_decay;
   t->bc1 = (float)(1.0 - pow((double)o->beta1, (double)o->step));
   t->bc2_sqrt = (float)sqrt(1.0 - pow((double)o->beta2, (double)o->step));
+  if (peers != nullptr) {
+    if (peers->world < 2 || peers->world > HOIR_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
+      return hoir_set_error(HOIR_EINVAL, "bad peer descriptor", where);
+    if (o->keep_grad) return hoir_set_error(HOIR_EINVAL, "keep_grad is not available with the peer exchange", where);
+    const long long stride = peer_stride(m);
+    const int parity = (int)(o->step & 1);
+    t->world = peers->world;
+    t->rank = peers->rank;
+    t->flag_value = (unsigned int)o->step;
+    for (int r = 0; r < peers->world; ++r) {
+      if (!peers->block[r]) return hoir_set_error(HOIR_EINVAL, "null peer block", where);
+      float* base = static_cast<float*>(peers->block[r]);
+      t->peer_g[r] = base + parity * stride;
+      t->peer_flag[r] = reinterpret_cast<unsigned int*>(base + 2 * stride);
+    }
+    float* own = static_cast<float*>(peers->block[peers->rank]);
+    t->g = own + parity * stride;
+    t->zero_buf = own + (parity ^ 1) * stride;
+  }
   return HOIR_OK;
 }
 
+int launch_tail(const OptTail& t, cudaStream_t stream);
+}  // namespace
+namespace {
 int launch_tail(const OptTail& t, cudaStream_t stream) {
   long long grid = (t.woff[t.num_layers] + 255) / 256;
   if (grid > num_sms_fused() * 8) grid = num_sms_fused() * 8;
@@ -919,7 +949,10 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
   if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", where);
   FusedParams p;
   if (int err = fill_params(m, B, x, mesh, packed, &p, where)) return err;
-  if (B == 0) return HOIR_OK;
+  if (B == 0) {   // nothing to add; with peers the exchange must still happen (the other ranks wait for it)
+    if (tail != nullptr && tail->world > 1) return launch_tail(*tail, (cudaStream_t)stream);
+    return HOIR_OK;
+  }
   if (!gw) return hoir_set_error(HOIR_EINVAL, "null gradient pointer table", where);
   for (int l = 0; l < m->num_layers; ++l) {
     if (!gw[l]) return hoir_set_error(HOIR_EINVAL, "null gradient pointer", where);
@@ -1016,4 +1049,22 @@ extern "C" int hoir_mlp_train_step_fused(const hoir_mlp_desc* m, long long B, co
   for (int l = 0; l < m->num_layers; ++l) gw[l] = opt->flat_g + t.woff[l];
   return train_launch(m, B, x, mesh, target_kind, target, nullptr, opt->packed, gw,
                       opt->flat_g + t.woff[m->num_layers], loss_scale, &t, stream, "hoir_mlp_train_step_fused");
+}
+
+extern "C" long long hoir_peer_stride(const hoir_mlp_desc* m) { return mlp_desc_ok(m) ? peer_stride(m) : -1; }
+extern "C" long long hoir_peer_block_floats(const hoir_mlp_desc* m) {
+  return mlp_desc_ok(m) ? 2 * peer_stride(m) + 64 : -1;
+}
+
+extern "C" int hoir_mlp_train_step_fused_peer(const hoir_mlp_desc* m, long long B, const float* x,
+                                              const hoir_mesh_desc* mesh, int target_kind, const void* target,
+                                              float loss_scale, const hoir_opt_desc* opt,
+                                              const hoir_peer_desc* peers, void* stream) {
+  if (!peers) return hoir_set_error(HOIR_EINVAL, "null peer descriptor", "hoir_mlp_train_step_fused_peer");
+  OptTail t;
+  if (int err = fill_tail(m, opt, &t, "hoir_mlp_train_step_fused_peer", peers)) return err;
+  float* gw[HOIR_MAX_LAYERS] = {};
+  for (int l = 0; l < m->num_layers; ++l) gw[l] = t.g + t.woff[l];
+  return train_launch(m, B, x, mesh, target_kind, target, nullptr, opt->packed, gw, t.g + t.woff[m->num_layers],
+                      loss_scale, &t, stream, "hoir_mlp_train_step_fused_peer");
 }

@@ -26,6 +26,12 @@ struct OptTail {
   float* loss_out;
   float lr, b1, b2, eps, wd, bc1, bc2_sqrt;
   unsigned int* sync;                     // [2] arrive / depart counters of the in-kernel grid barrier
+  // peer exchange (world > 1): the gradient is the rank-ordered sum over every rank's symmetric buffer
+  int world, rank;
+  const float* peer_g[HOIR_MAX_PEERS];    // this step's gradient buffer of every rank (g == peer_g[rank])
+  unsigned int* peer_flag[HOIR_MAX_PEERS];   // flag array of every rank; slot [rank] is ours to write
+  unsigned int flag_value;                // the step number
+  float* zero_buf;                        // own other-parity buffer, zeroed for the step after next
 };
 
 namespace hoir {
@@ -63,6 +69,35 @@ __device__ __forceinline__ void grid_barrier_depart(unsigned int* sync) {
   }
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f32(const float* p) {   // peer memory over NVLink: never from L1
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+// Cross-GPU rendezvous of one step.  Precondition: every gradient add of THIS GPU is complete and visible
+// to the calling CTA 0 (grid barrier, or kernel boundary).  CTA 0 publishes the flag to every rank; every CTA
+// waits until all ranks have published theirs.
+__device__ __forceinline__ void peer_exchange_barrier(const OptTail& t) {
+  if (blockIdx.x == 0 && threadIdx.x < t.world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.peer_flag[threadIdx.x] + t.rank), "r"(t.flag_value) : "memory");
+  }
+  if (threadIdx.x < t.world) {
+    const unsigned int* mine = t.peer_flag[t.rank] + threadIdx.x;
+    unsigned int spins = 0;
+    while (ld_acquire_sys_u32(mine) < t.flag_value) {
+      __nanosleep(64);
+      if (++spins > (1u << 26)) __trap();   // a peer never arrived: fail loudly instead of hanging
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void opt_tail_rows(const OptTail& t, int gwarp, int nwarps, int lane) {
   const float one_m_b1 = 1.f - t.b1, one_m_b2 = 1.f - t.b2, step_size = t.lr / t.bc1;
   const long long n = t.woff[t.num_layers];
@@ -77,7 +112,14 @@ __device__ __forceinline__ void opt_tail_rows(const OptTail& t, int gwarp, int n
     const int nodes = t.nodes[l], in_f = t.in_f[l], op = t.out_pad[l];
     const int r = e / nodes, q = e - r * nodes;
     const int o = r / in_f, i = r - o * in_f;
-    float gk = __ldcg(t.g + k);           // written by other SMs' atomics: read at L2
+    float gk;
+    if (t.world > 1) {                    // rank-ordered sum over the peers' buffers: identical on every rank
+      gk = 0.f;
+      for (int r = 0; r < t.world; ++r) gk += ld_peer_f32(t.peer_g[r] + k);
+      t.zero_buf[k] = 0.f;
+    } else {
+      gk = __ldcg(t.g + k);               // written by other SMs' atomics: read at L2
+    }
     float wk = t.w[k];
     if (t.kind == HOIR_OPT_ADAM) {
       if (t.wd != 0.f) gk = fmaf(t.wd, wk, gk);
@@ -98,12 +140,19 @@ __device__ __forceinline__ void opt_tail_rows(const OptTail& t, int gwarp, int n
       t.w[k] = wk;
       t.m[k] = ea * t.b2 + gk * one_m_b2;
     }
-    if (!t.keep_grad) t.g[k] = 0.f;
+    if (!t.keep_grad && t.world <= 1) t.g[k] = 0.f;
     t.packed[t.poff[l] + ((long long)i * nodes + q) * op + o] = wk;
   }
   if (gwarp == 0 && lane == 0) {
-    if (t.loss_out != nullptr) t.loss_out[0] = __ldcg(t.g + n);
-    if (!t.keep_grad) t.g[n] = 0.f;
+    if (t.world > 1) {
+      float ls = 0.f;
+      for (int r = 0; r < t.world; ++r) ls += ld_peer_f32(t.peer_g[r] + n);
+      if (t.loss_out != nullptr) t.loss_out[0] = ls;
+      t.zero_buf[n] = 0.f;
+    } else {
+      if (t.loss_out != nullptr) t.loss_out[0] = __ldcg(t.g + n);
+      if (!t.keep_grad) t.g[n] = 0.f;
+    }
   }
 }
 
@@ -111,6 +160,7 @@ __device__ __forceinline__ void opt_tail_rows(const OptTail& t, int gwarp, int n
 __device__ __forceinline__ void opt_tail_in_kernel(const OptTail& t) {
   if (t.kind == 0) return;
   grid_barrier_arrive_wait(t.sync);
+  if (t.world > 1) peer_exchange_barrier(t);
   const int wpb = blockDim.x >> 5;
   opt_tail_rows(t, blockIdx.x * wpb + (threadIdx.x >> 5), gridDim.x * wpb, threadIdx.x & 31);
   grid_barrier_depart(t.sync);

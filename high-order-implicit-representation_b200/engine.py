@@ -56,7 +56,25 @@ class FusedTrainer:
         sizes = [l.w.numel() for l in self.layers]
         self.n_params = sum(sizes)
         self.flat_w = torch.empty(self.n_params, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(self.n_params + 1, device=dev, dtype=torch.float32)  # [-1] = loss accumulator
+        # multi-GPU: gradients live in a symmetric block mapped by every peer and are exchanged inside the
+        # optimizer tail over NVLink (two alternating buffers); otherwise one flat vector (+ NCCL if world > 1)
+        self.peer = None
+        if self.world > 1 and not keep_grads:
+            self.peer = parallel.try_peer_block(int(self.lib.hoir_peer_block_floats(self.desc)), dev, process_group)
+            agree = torch.tensor([1 if self.peer is not None else 0], device=dev)
+            torch.distributed.all_reduce(agree, op=torch.distributed.ReduceOp.MIN, group=process_group)
+            if int(agree.item()) == 0:
+                self.peer = None
+        if self.peer is not None:
+            stride = int(self.lib.hoir_peer_stride(self.desc))
+            self._peer_bufs = [self.peer.tensor[k * stride:k * stride + self.n_params + 1] for k in range(2)]
+            self._peer_desc = _lib.PeerDesc()
+            self._peer_desc.world, self._peer_desc.rank = self.peer.world, self.peer.rank
+            for r, ptr in enumerate(self.peer.ptrs):
+                self._peer_desc.block[r] = ptr
+            self.flat_g = self._peer_bufs[1]          # step 1 uses parity 1
+        else:
+            self.flat_g = torch.zeros(self.n_params + 1, device=dev, dtype=torch.float32)  # [-1] = loss accumulator
         self.loss_out = torch.zeros(1, device=dev, dtype=torch.float32)
         self.w_views, self.g_views = [], []
         off = 0
@@ -84,7 +102,7 @@ class FusedTrainer:
         self._opt.packed = self.packed.data_ptr()
         self._opt.loss_out = self.loss_out.data_ptr()
         #: kernels launched by the last train step
-        self.launches_per_step = 1 if self.world == 1 else 2
+        self.launches_per_step = 1 if (self.world == 1 or self.peer is not None) else 2
         #: set to a list to collect (start, end) CUDA events around the fused training kernel
         self.kernel_events = None
 
@@ -130,6 +148,13 @@ class FusedTrainer:
         if self.world == 1:
             _lib.check(lib.hoir_mlp_train_step_fused(self.desc, B, x_ptr, mesh, target_kind, target_ptr,
                                                      scale, _lib.C.byref(self._opt_desc()), st))
+        elif self.peer is not None:
+            # ONE launch per step on every rank: the gradient exchange over NVLink peer memory and the update
+            # run in the kernel's tail (no NCCL call on the step path)
+            self.flat_g = self._peer_bufs[self.step_count & 1]
+            _lib.check(lib.hoir_mlp_train_step_fused_peer(self.desc, B, x_ptr, mesh, target_kind, target_ptr,
+                                                          scale, _lib.C.byref(self._opt_desc()),
+                                                          _lib.C.byref(self._peer_desc), st))
         else:
             _lib.check(lib.hoir_mlp_train_step(self.desc, B, x_ptr, mesh, target_kind, target_ptr, None,
                                                _lib.dptr(self.packed), self._g_table, self._loss_ptr,
@@ -137,7 +162,7 @@ class FusedTrainer:
         if ev is not None:
             ev[1].record()
             self.kernel_events.append(ev)
-        if self.world > 1:
+        if self.world > 1 and self.peer is None:
             parallel.allreduce_sum_(self.flat_g, self.group)
             _lib.check(lib.hoir_mlp_optimizer_tail(self.desc, _lib.C.byref(self._opt_desc()), st))
         return self.loss_out     # 1-element tensor: MSE(mean) of this step over all ranks

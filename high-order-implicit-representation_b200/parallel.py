@@ -43,3 +43,39 @@ def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+class PeerBlock:
+    """This rank's symmetric gradient block (include/hoir.h: hoir_peer_desc) and its peers' mappings, obtained
+    through ``torch.distributed._symmetric_memory`` (CUDA IPC / fabric handles exchanged over the process
+    group's store) -- plumbing only: the exchange itself happens inside the training kernel's optimizer tail
+    with release / acquire flags over NVLink, no NCCL call on the step path."""
+
+    def __init__(self, n_floats: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.tensor = symm.empty(n_floats, dtype=torch.float32, device=device)
+        self.tensor.zero_()
+        self.handle = symm.rendezvous(self.tensor, self.group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self.ptrs) != self.world or any(p == 0 for p in self.ptrs):
+            raise RuntimeError("symmetric-memory rendezvous returned no peer mappings")
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)          # every rank's block is zeroed before anyone's first step
+
+
+def try_peer_block(n_floats: int, device: torch.device, group=None):
+    """PeerBlock, or None when peer memory is not available (single rank, gloo, no P2P, HOIR_NO_PEER=1):
+    the caller then falls back to one NCCL all-reduce per step."""
+    import os
+    if os.environ.get("HOIR_NO_PEER") or not (dist.is_available() and dist.is_initialized()):
+        return None
+    if dist.get_world_size(group) < 2 or dist.get_backend(group) != "nccl" or dist.get_world_size(group) > 16:
+        return None
+    try:
+        return PeerBlock(n_floats, device, group)
+    except Exception as e:  # noqa: BLE001 -- any failure of the optional plumbing means "use NCCL"
+        import logging
+        logging.getLogger(__name__).warning("peer-memory gradient exchange unavailable (%s); using NCCL all-reduce", e)
+        return None

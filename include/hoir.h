@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HOIR_VERSION 101
+#define HOIR_VERSION 102
 #define HOIR_MAX_LAYERS 8
 #define HOIR_MAX_N 32          /* max basis functions per segment / Fourier terms          */
 #define HOIR_MAX_ROTATIONS 8
@@ -193,6 +193,34 @@ int hoir_mlp_optimizer_tail(const hoir_mlp_desc* m, const hoir_opt_desc* opt, vo
 int hoir_mlp_train_step_fused(const hoir_mlp_desc* m, long long B, const float* x,
                               const hoir_mesh_desc* mesh, int target_kind, const void* target,
                               float loss_scale, const hoir_opt_desc* opt, void* stream);
+
+/* ---- multi-GPU: gradient exchange over NVLink / NVSwitch peer memory INSIDE the training step ----------
+ * Data-parallel training sums the flat gradient (tens of KB) over the ranks once per step.  Instead of a
+ * separate NCCL all-reduce, every rank keeps its gradient in a SYMMETRIC block that all peers of the node
+ * have mapped (CUDA IPC / fabric handles; the host side obtains the mappings, e.g. through
+ * torch.distributed._symmetric_memory), and the optimizer tail of the step
+ *   1. publishes "my gradient of step s is complete" into every peer's flag array (st.release.sys),
+ *   2. waits for the same flag from every peer (ld.acquire.sys),
+ *   3. reads all ranks' gradients in rank order (bit-identical sums on every rank => replicated weights
+ *      stay bit-identical without a broadcast), applies the update, re-packs the weights,
+ *   4. zeroes its OTHER parity buffer for the step after next (two gradient buffers alternate, so no
+ *      second barrier is needed before a buffer is reused).
+ * Block layout (floats): [gradient parity 0: stride][gradient parity 1: stride][flags: 64 x u32],
+ * stride = hoir_peer_stride(m) >= n_params + 1; the block must be zero before the first step. */
+#define HOIR_MAX_PEERS 16
+typedef struct hoir_peer_desc {
+  int world, rank;
+  void* block[HOIR_MAX_PEERS];  /* block[r]: rank r's block as mapped into THIS process            */
+} hoir_peer_desc;
+long long hoir_peer_stride(const hoir_mlp_desc* m);        /* floats per gradient buffer, or -1   */
+long long hoir_peer_block_floats(const hoir_mlp_desc* m);  /* 2 * stride + 64, or -1              */
+/* hoir_mlp_train_step_fused with the exchange above; opt->flat_g is ignored (the gradient lives in
+ * block[rank], parity opt->step & 1) and opt->keep_grad must be 0.  Every rank must call it for every
+ * step with the same opt->step. */
+int hoir_mlp_train_step_fused_peer(const hoir_mlp_desc* m, long long B, const float* x,
+                                   const hoir_mesh_desc* mesh, int target_kind, const void* target,
+                                   float loss_scale, const hoir_opt_desc* opt,
+                                   const hoir_peer_desc* peers, void* stream);
 
 /* ---- optimizers on flat fp32 vectors --------------------------------------------------------
  * torch.optim.Adam (networks.py:94-97) and SparseLion (networks.py:99-102). */

@@ -17,7 +17,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, no_peer):
+    if no_peer:
+        os.environ["HOIR_NO_PEER"] = "1"
     import torch.distributed as dist
     import hoir_b200 as H
     from helpers import MLP_KW
@@ -37,19 +39,20 @@ def _worker(rank, world, port, q):
     for step in range(3):
         loss = tr.train_step_mesh(img, 2, rank * per, per)
         losses.append(loss.item())
-    q.put((rank, losses, tr.flat_w.cpu()))
+    q.put((rank, losses, tr.flat_w.cpu(), tr.peer is not None, tr.launches_per_step))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_data_parallel_matches_single_gpu():
+@pytest.mark.parametrize("no_peer", [False, True], ids=["nvlink-peer-exchange", "nccl-allreduce"])
+def test_two_gpu_data_parallel_matches_single_gpu(no_peer):
     import hoir_b200 as H
     from helpers import MLP_KW
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, no_peer)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
@@ -57,6 +60,10 @@ def test_two_gpu_data_parallel_matches_single_gpu():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert torch.equal(res[0][2], res[1][2])          # replicated weights stay bit-identical
+    if no_peer:
+        assert not res[0][3] and res[0][4] == 2       # kernel + tail, NCCL all-reduce in between
+    else:                                             # gradient exchange inside the kernel: one launch per step
+        assert res[0][3] and res[1][3] and res[0][4] == 1, "peer-memory exchange was not active"
     assert res[0][1] == res[1][1]
     torch.manual_seed(0)
     net = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW["C2"])
