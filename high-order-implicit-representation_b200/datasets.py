@@ -30,7 +30,9 @@ def image_to_dataset(filename: Union[str, Tensor], peano: bool = False, rotation
     lines = positions_from_mesh(width=img.shape[0], height=img.shape[1], device=device,
                                 rotations=rotations, normalize=True)
     pos = torch.stack(lines, dim=2).reshape(-1, 2 * rotations)
-    flat = img.reshape(-1, 3) * 2.0 / 255.0 - 1
+    # u*2/255-1 (single_image_dataset.py:49) with an IEEE division: torch's CUDA "divide by a Python scalar"
+    # multiplies by the reciprocal (1 ulp off the reference's CPU result); a tensor divisor divides
+    flat = (img.reshape(-1, 3) * 2.0) / torch.tensor(255.0, device=img.device) - 1
     return flat, pos, img
 
 

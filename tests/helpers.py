@@ -58,3 +58,22 @@ def adversarial_inputs(segments: int) -> torch.Tensor:
     vals = [b, torch.nextafter(b, inf), torch.nextafter(b, -inf),
             torch.tensor([-1.5, -1.2, -1.0000001, 1.0000001, 1.2, 1.5, 0.0, -0.0, 1e-30, -1e-30, 1e-8, -1e-8])]
     return torch.cat(vals)
+
+
+class FixedModel(torch.nn.Module):
+    """The deterministic stand-in network of tests/golden/make_reference_golden.py (same definition)."""
+
+    def __init__(self, f_in: int, f_out: int):
+        super().__init__()
+        i = torch.arange(f_out, dtype=torch.float32).view(-1, 1)
+        j = torch.arange(f_in, dtype=torch.float32).view(1, -1)
+        self.register_buffer("w", torch.cos(0.37 * i + 0.11 * j) / f_in ** 0.5)
+
+    def forward(self, x):
+        return torch.tanh(x @ self.w.t())
+
+
+def reference_golden():
+    import os
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_own_v1.npz"))

@@ -97,3 +97,22 @@ def test_no_cpu_fallback():
     layer = H.high_order_fc_layers("continuous", n=3, in_features=2, out_features=2, segments=4)
     with pytest.raises(RuntimeError, match="no CPU path"):
         layer(torch.zeros(3, 2))
+
+
+def test_dependency_alias_package_exports_what_the_reference_imports():
+    """The reference reaches the hot path through `high_order_layers_torch.*` imports; the alias
+    package at the repository root must satisfy every one of them, star imports included (Quirk Q7)."""
+    ns = {}
+    exec("from high_order_layers_torch.layers import *\n"
+         "from high_order_layers_torch.networks import *\n"
+         "from high_order_layers_torch.sparse_optimizers import SparseLion\n"
+         "from high_order_layers_torch.layers import high_order_fc_layers\n"
+         "from high_order_layers_torch.utils import positions_from_mesh\n", ns)
+    for name in ("high_order_fc_layers", "MaxAbsNormalization", "HighOrderMLP", "initialize_network_polynomial_layers",
+                 "SparseLion", "positions_from_mesh", "torch", "math", "Tensor", "Any"):
+        assert name in ns, name
+    import hoir_b200 as H
+    assert ns["HighOrderMLP"] is H.HighOrderMLP and ns["high_order_fc_layers"] is H.high_order_fc_layers
+    # host-side use exactly as single_image_dataset.py:39-45 does (CPU tensors: dataset preparation)
+    lines = ns["positions_from_mesh"](width=4, height=3, device="cpu", rotations=2, normalize=True)
+    assert len(lines) == 4 and lines[0].shape == (4, 3)
