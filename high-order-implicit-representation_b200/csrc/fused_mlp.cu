@@ -838,7 +838,7 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
     HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd_tc));
     const long long tiles_tc = (B + tc::TS - 1) / tc::TS;
     const long long cap = 2LL * num_sms_fused();
-    e->fwd_tc<<<(int)(tiles_tc < cap ? tiles_tc : cap), tc::NTHREADS, e->smem_fwd_tc, (cudaStream_t)stream>>>(p);
+    e->fwd_tc<<<(int)(tiles_tc < cap ? tiles_tc : cap), tc::NTHREADS_FWD, e->smem_fwd_tc, (cudaStream_t)stream>>>(p);
     HOIR_CHECK_CUDA(cudaGetLastError());
     return HOIR_OK;
   }

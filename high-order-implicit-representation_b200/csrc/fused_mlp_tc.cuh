@@ -24,7 +24,9 @@ namespace tc {
 
 constexpr int TS = 128;          // samples per tile
 constexpr int NSAMPLE_THREADS = 256;   // 8 sample warps: 2 threads per sample
-constexpr int NTHREADS = 288;          // + 1 MMA warp
+constexpr int NHELPER = 96;            // 3 helper warps: stage the Phi1 units of the dL/dw1 product
+constexpr int NTHREADS = 384;          // 8 sample warps + 1 MMA warp + 3 helper warps (168 regs x 384 = 63 K)
+constexpr int NTHREADS_FWD = 288;      // forward-only kernel: 8 sample warps + 1 MMA warp
 constexpr int APITCH = 41;       // row pitch (floats) of the saved-activation tiles
 
 // Shape constants of the tensor path (continuous n = 3, 2 hidden/output segments, width 40)
@@ -63,7 +65,7 @@ struct TcPlan {
 };
 
 enum { B_FFULL0 = 0, B_FFULL1, B_FEMPTY0, B_FEMPTY1, B_D1FULL, B_D1EMPTY, B_GFULL, B_TFULL, B_GWDONE,
-       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_COUNT };
+       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_A1FULL, B_A1FREE, B_COUNT };
 
 // y[O] += sum_j l[j] * W[j * PITCH + 0..O)
 template <int N, int O, int PITCH, bool GLOBAL>
@@ -142,8 +144,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     mbar_init(&bars[B_FEMPTY0], 1);  mbar_init(&bars[B_FEMPTY1], 1);
     mbar_init(&bars[B_D1FULL], 1);   mbar_init(&bars[B_D1EMPTY], NSAMPLE_THREADS);
     mbar_init(&bars[B_GFULL], NSAMPLE_THREADS);  mbar_init(&bars[B_TFULL], 1);   mbar_init(&bars[B_GWDONE], 1);
-    mbar_init(&bars[B_UFULL0], NSAMPLE_THREADS); mbar_init(&bars[B_UFULL1], NSAMPLE_THREADS);
+    mbar_init(&bars[B_UFULL0], NHELPER); mbar_init(&bars[B_UFULL1], NHELPER);
     mbar_init(&bars[B_UEMPTY0], 1);  mbar_init(&bars[B_UEMPTY1], 1);
+    mbar_init(&bars[B_A1FULL], NSAMPLE_THREADS); mbar_init(&bars[B_A1FREE], NHELPER);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   {
@@ -247,6 +250,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         __syncwarp();
       }
     }
+  } else if (warp > 8) {
+    // =========================== helper warps ===============================================
+    // Stage Phi1 (densified basis of the hidden-layer inputs a1, raw + tf32 residual) for the dL/dw1 product in
+    // units of 16 samples, double-buffered.  Thread = (input i, half of the unit): its K-columns are fixed, the
+    // row swizzle is a compile-time constant per step.  The sample warps never touch the units.
+    const int ht = tid - (NSAMPLE_THREADS + 32);
+    const int i = ht % HID, sh = ht / HID;            // sh = 0, 1: samples 8 sh .. 8 sh + 7 of a unit; sh = 2: idle
+    const LagrangeTable& lag = p.lag;
+    const int kb = P::kbase(i);
+    uint32_t coff[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) coff[k] = ((uint32_t)((kb + k) & 31) << 2) | (((uint32_t)(kb + k) >> 5) << 16);
+    uint32_t q_unit = 0, n_tile = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+      mbar_wait(&bars[B_A1FULL], n_tile & 1);
+      for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
+        const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
+        mbar_wait(&bars[B_UEMPTY0 + buf], ph ^ 1);
+        if (sh < 2) {
+          uint8_t* ur = sU + buf * 2 * P::U_BYTES;
+          uint8_t* ul = ur + P::U_BYTES;
+#pragma unroll
+          for (int t = 0; t < P::UNIT / 2; ++t) {
+            const int sl = sh * (P::UNIT / 2) + t;   // (sl & 3) == (t & 3): compile-time swizzle
+            const float x = sA1[(u * P::UNIT + sl) * APITCH + i];
+            int id;
+            float xi, l[N];
+            locate2(x, id, xi);
+            hoir::lagrange<N>(lag.X, lag.D, xi, l);
+            const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+            const uint32_t rowoff = (uint32_t)(t & 3) * 128u + (uint32_t)(sl >> 2) * P::U_RS;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) {
+              const uint32_t off = rowoff + ((coff[k] & 0xffffu) ^ ((uint32_t)(t & 3) << 5)) + (coff[k] >> 16) * 512u;
+              *reinterpret_cast<float*>(ur + off) = c5[k];
+              *reinterpret_cast<float*>(ul + off) = tf32_lo(c5[k]);
+            }
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(&bars[B_UFULL0 + buf]);
+      }
+      mbar_arrive(&bars[B_A1FREE]);                   // done reading this tile's a1 rows
+    }
   } else {
     // =========================== sample warps ===============================================
     const int hf = warp >> 2;                         // which 20 hidden units this thread owns
@@ -311,8 +358,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       const int kidx0 = kidxN;
 #pragma unroll
       for (int i = 0; i < IN; ++i) rec0[i] = recN[i];
+      if (n_tile > 0) mbar_wait(&bars[B_A1FREE], (n_tile - 1) & 1);   // helpers are done with the previous a1 tile
 #pragma unroll
       for (int j = 0; j < HH; ++j) a1[hf * HH + j] = hN[j];
+      mbar_arrive(&bars[B_A1FULL]);                                   // (release) helpers may stage Phi1 units
       // ---- hidden layer forward on the tensor cores: stage this thread's 4 inputs of every chunk into TMEM
       for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
         const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
@@ -411,27 +460,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         for (int q = 0; q < N; ++q) gx = fmaf(d[q], t[q], gx);
         gx *= 2.f;                                   // d xi / d x = segments
         dot = fmaf(gx, x, dot);
-        a2[i] = gx;                                  // a2 now holds dL/da2
-        // densified basis row x dL/dy: 5 x 3 products (+1 pad), reduce-scatter over the warp
-        const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
-        float r[16];
-#pragma unroll
-        for (int k = 0; k < ND; ++k)
-#pragma unroll
-          for (int o = 0; o < OUT; ++o) r[k * OUT + o] = c5[k] * gy[o];
-        r[15] = 0.f;
-#pragma unroll
-        for (int st = 16, n = 8; st >= 2; st >>= 1, n >>= 1) {
-          const bool up = (lane & st) != 0;
-#pragma unroll
-          for (int m = 0; m < n; ++m) {
-            const float send = up ? r[m] : r[m + n];
-            const float keep = up ? r[m + n] : r[m];
-            r[m] = keep + __shfl_xor_sync(0xffffffffu, send, st);
-          }
-        }
-        r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-        acc2[j] += r[0];   // this lane's element e(lane) of input i, summed over the warp's 32 samples
+        g[j] = gx;                                   // dL/da2 (a2 keeps the activations for the dL/dw2 pass below)
       }
       if (p.normalize) {
         xs[0] = dot;
@@ -442,13 +471,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         const float sgn = kidx_sign(kidx1);
 #pragma unroll
         for (int j = 0; j < HH; ++j) {
-          float gi = a2[hf * HH + j];
+          float gi = g[j];
           if (j == k) gi -= sgn * dot;
           g[j] = gi * inv_d1;
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < HH; ++j) g[j] = a2[hf * HH + j];
       }
       // ---- stage G (own 20 units): TMEM (A operand of GX) and smem G^T (B operand of GW)
       if (n_tile > 0) mbar_wait(&bars[B_GWDONE], (n_tile - 1) & 1);   // previous tile's GW done with G^T
@@ -471,63 +497,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       fence_async_smem();
       fence_before();
       mbar_arrive(&bars[B_GFULL]);
-      bar_samples();     // every sample's a1 row is visible to the GW staging below
-      // ---- GW staging: units of 16 samples, (sample, input) items spread over the 256 threads
+      // ---- dL/dw2 while the tensor pipe computes T = G * W1^T: densified basis row x dL/dy, 5 x 3 products
+      //      (+1 pad), reduce-scatter over the warp's 32 samples
+#pragma unroll
+      for (int j = 0; j < HH; ++j) {
+        int id;
+        float xi, l[N];
+        locate2(a2[hf * HH + j], id, xi);
+        hoir::lagrange<N>(lag.X, lag.D, xi, l);
+        const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+        float r[16];
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) r[k * OUT + o] = c5[k] * gy[o];
+        r[15] = 0.f;
+#pragma unroll
+        for (int st = 16, n = 8; st >= 2; st >>= 1, n >>= 1) {
+          const bool up = (lane & st) != 0;
+#pragma unroll
+          for (int m = 0; m < n; ++m) {
+            const float send = up ? r[m] : r[m + n];
+            const float keep = up ? r[m + n] : r[m];
+            r[m] = keep + __shfl_xor_sync(0xffffffffu, send, st);
+          }
+        }
+        r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+        acc2[j] += r[0];   // this lane's element e(lane) of input i, summed over the warp's 32 samples
+      }
+      // ---- T epilogue (own 4 inputs per chunk): dL/da1 = slope * sum_j l'_j * T[kbase(i) + window + j]
       dot = 0.f;
+      mbar_wait(&bars[B_TFULL], n_tile & 1);
+      fence_after();
 #pragma unroll
-      for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
-        // T epilogue chunk c = u - 2 (own 4 inputs): dL/da1 = slope * sum_j l'_j * T[kbase(i) + window + j];
-        // interleaved with the staging so that the waits on the tensor pipe are filled with work
-        if (u >= 2 && u - 2 < P::NCH) {
-          const int c = u - 2;
-          if (c == 0) {
-            mbar_wait(&bars[B_TFULL], n_tile & 1);
-            fence_after();
-          }
-          float t[P::HK];
-          tmem_ld20(tm_lane + P::T_COL + c * P::CH_K + hf * P::HK, t);
-          tmem_wait_ld();
+      for (int c = 0; c < P::NCH; ++c) {
+        float t[P::HK];
+        tmem_ld20(tm_lane + P::T_COL + c * P::CH_K + hf * P::HK, t);
+        tmem_wait_ld();
 #pragma unroll
-          for (int m = 0; m < P::QI; ++m) {
-            const float x = a1[hf * HH + c * P::QI + m];
-            int id;
-            float xi, l[N], d[N];
-            locate2(x, id, xi);
-            hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
-            const float t0 = id ? t[m * ND + 2] : t[m * ND + 0];
-            const float t1 = id ? t[m * ND + 3] : t[m * ND + 1];
-            const float t2 = id ? t[m * ND + 4] : t[m * ND + 2];
-            const float gx = fmaf(d[2], t2, fmaf(d[1], t1, d[0] * t0)) * 2.f;
-            dot = fmaf(gx, x, dot);
-            g[c * P::QI + m] = gx;
-          }
+        for (int m = 0; m < P::QI; ++m) {
+          const float x = a1[hf * HH + c * P::QI + m];
+          int id;
+          float xi, l[N], d[N];
+          locate2(x, id, xi);
+          hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
+          const float t0 = id ? t[m * ND + 2] : t[m * ND + 0];
+          const float t1 = id ? t[m * ND + 3] : t[m * ND + 1];
+          const float t2 = id ? t[m * ND + 4] : t[m * ND + 2];
+          const float gx = fmaf(d[2], t2, fmaf(d[1], t1, d[0] * t0)) * 2.f;
+          dot = fmaf(gx, x, dot);
+          g[c * P::QI + m] = gx;
         }
-        const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
-        mbar_wait(&bars[B_UEMPTY0 + buf], ph ^ 1);
-        uint8_t* ur = sU + buf * 2 * P::U_BYTES;
-        uint8_t* ul = ur + P::U_BYTES;
-#pragma unroll
-        for (int j = 0; j < (P::UNIT * HID + NSAMPLE_THREADS - 1) / NSAMPLE_THREADS; ++j) {
-          const int f = tid + NSAMPLE_THREADS * j;
-          if (f < P::UNIT * HID) {
-            const int sl = f / HID, i = f - sl * HID;
-            const float x = sA1[(u * P::UNIT + sl) * APITCH + i];
-            int id;
-            float xi, l[N];
-            locate2(x, id, xi);
-            hoir::lagrange<N>(lag.X, lag.D, xi, l);
-            const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
-            const int kb = P::kbase(i);
-#pragma unroll
-            for (int k = 0; k < ND; ++k) {
-              const uint32_t off = sw4_off(sl, kb + k, P::U_RS);
-              *reinterpret_cast<float*>(ur + off) = c5[k];
-              *reinterpret_cast<float*>(ul + off) = tf32_lo(c5[k]);
-            }
-          }
-        }
-        fence_async_smem();
-        mbar_arrive(&bars[B_UFULL0 + buf]);
       }
       fence_before();
       if (p.normalize) {
@@ -563,6 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         continue;
       }
       // ---- otherwise: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
+      mbar_wait(&bars[B_A1FREE], n_tile & 1);         // helpers are done with sA1 (aliased below)
       bar_samples();                                  // everyone is done reading sA1 / sA2
       {
         float* sG0 = sA1;                             // [s][GPITCH] dL/d(layer-0 output)
@@ -680,7 +701,7 @@ struct TcFwdPlan {
 };
 
 template <class S>
-__global__ void __launch_bounds__(NTHREADS, 2) fused_mlp_tc_fwd_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(NTHREADS_FWD, 2) fused_mlp_tc_fwd_kernel(const FusedParams p) {
   using P = TcPlan<S>;
   using F = TcFwdPlan<S>;
   constexpr int N = S::N, IN = S::IN, HID = S::HID, OUT = S::OUT, HP = S::HP, OP = S::OP, ND = P::ND, HH = P::HH;
@@ -706,12 +727,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) fused_mlp_tc_fwd_kernel(const Fus
   }
   {
     const float* w1 = p.packed + p.off[1];
-    for (uint32_t k = tid; k < (uint32_t)(P::W1_BYTES / 4); k += NTHREADS) {
+    for (uint32_t k = tid; k < (uint32_t)(P::W1_BYTES / 4); k += NTHREADS_FWD) {
       reinterpret_cast<float*>(sW1R)[k] = 0.f;
       reinterpret_cast<float*>(sW1L)[k] = 0.f;
     }
     __syncthreads();
-    for (int k = tid; k < P::KH * HID; k += NTHREADS) {
+    for (int k = tid; k < P::KH * HID; k += NTHREADS_FWD) {
       const int o = k % HID, r = k / HID, i = r / ND, q = r - i * ND;
       const float v = __ldg(w1 + (size_t)r * HP + o);
       const uint32_t off = sw4_off(o, P::kbase(i) + q, P::W1_RS);
@@ -719,7 +740,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) fused_mlp_tc_fwd_kernel(const Fus
       *reinterpret_cast<float*>(sW1L + off) = tf32_lo(v);
     }
     const float* w2 = p.packed + p.off[2];
-    for (int k = tid; k < S::WO; k += NTHREADS) sW2[k] = __ldg(w2 + k);
+    for (int k = tid; k < S::WO; k += NTHREADS_FWD) sW2[k] = __ldg(w2 + k);
   }
   fence_async_smem();
   fence_before();
