@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
       // ---- FWD: D1 = Phi1 * W1, five chunks of 8 inputs
-      if (n_tile > 0) mbar_wait(&bars[B_D1EMPTY], (n_tile - 1) & 1);
+      if (n_tile > 0) mbar_wait_backoff(&bars[B_D1EMPTY], (n_tile - 1) & 1, 32);
       for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
         const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
         mbar_wait(&bars[B_FFULL0 + buf], ph);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         __syncwarp();
       }
       // ---- GX: T = G * W1^T
-      mbar_wait(&bars[B_GFULL], n_tile & 1);
+      mbar_wait_backoff(&bars[B_GFULL], n_tile & 1, 32);
       fence_after();
       if (leader) {
 #pragma unroll
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       // ---- GW: gW1 += Phi1^T * G, eight units of 16 samples
       for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
         const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
-        mbar_wait(&bars[B_UFULL0 + buf], ph);
+        mbar_wait_backoff(&bars[B_UFULL0 + buf], ph, 64);
         fence_after();
         if (leader) {
           const uint32_t ubase = smem_u32(sU + buf * 2 * P::U_BYTES);
@@ -264,10 +264,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     for (int k = 0; k < ND; ++k) coff[k] = ((uint32_t)((kb + k) & 31) << 2) | (((uint32_t)(kb + k) >> 5) << 16);
     uint32_t q_unit = 0, n_tile = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
-      mbar_wait(&bars[B_A1FULL], n_tile & 1);
+      mbar_wait_backoff(&bars[B_A1FULL], n_tile & 1, 128);
       for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
         const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
-        mbar_wait(&bars[B_UEMPTY0 + buf], ph ^ 1);
+        mbar_wait_backoff(&bars[B_UEMPTY0 + buf], ph ^ 1, 128);
         if (sh < 2) {
           uint8_t* ur = sU + buf * 2 * P::U_BYTES;
           uint8_t* ul = ur + P::U_BYTES;
@@ -309,11 +309,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     float loss_local = 0.f;
     uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
     // layer 0 (FFMA, weights through L1) of one tile: this thread's 20 outputs, MaxAbs over the pair
-    auto layer0 = [&](long long tile_, float* h_, float4* rec_, float& inv_d_, int& kidx_) {
+    // (also fetches the tile's targets / external dL/dy: their DRAM latency hides behind the previous tile)
+    auto layer0 = [&](long long tile_, float* h_, float4* rec_, float& inv_d_, int& kidx_, float* tg_) {
       const long long b_ = tile_ * TS + s;
       float x0[IN];
 #pragma unroll
       for (int i = 0; i < IN; ++i) x0[i] = 0.f;
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) tg_[o] = 0.f;
+      if (b_ < p.B) {
+        if (p.gy_ext != nullptr) {
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) tg_[o] = __ldg(p.gy_ext + b_ * OUT + o);
+        } else if (p.target_kind == HOIR_TARGET_U8_IMAGE) {
+          const unsigned char* img = static_cast<const unsigned char*>(p.target);
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) tg_[o] = (float)__ldg(img + (p.mesh.first_pixel + b_) * OUT + o);
+        } else {
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) tg_[o] = __ldg(static_cast<const float*>(p.target) + b_ * OUT + o);
+        }
+      }
       if (b_ < p.B) {
         if (p.x != nullptr) {
 #pragma unroll
@@ -343,10 +359,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     float4 recN[IN];
     float invN = 1.f;
     int kidxN = 0;
+    float tgN[OUT];
     float acc2[HH];                                   // dL/dw2 partial sums owned by this lane (see below)
 #pragma unroll
     for (int j = 0; j < HH; ++j) acc2[j] = 0.f;
-    if ((long long)blockIdx.x < tiles) layer0(blockIdx.x, hN, recN, invN, kidxN);
+    if ((long long)blockIdx.x < tiles) layer0(blockIdx.x, hN, recN, invN, kidxN, tgN);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
       const long long b = tile * TS + s;
       const bool live = b < p.B;
@@ -356,6 +373,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       int kidx1 = 0;
       const float inv_d0 = invN;
       const int kidx0 = kidxN;
+      float tg0[OUT];
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) tg0[o] = tgN[o];
 #pragma unroll
       for (int i = 0; i < IN; ++i) rec0[i] = recN[i];
       if (n_tile > 0) mbar_wait(&bars[B_A1FREE], (n_tile - 1) & 1);   // helpers are done with the previous a1 tile
@@ -391,7 +411,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         mbar_arrive(&bars[B_FFULL0 + buf]);
       }
       // ---- while the tensor pipe finishes D1: layer 0 of the NEXT tile (kept in registers)
-      if (tile + gridDim.x < tiles) layer0(tile + gridDim.x, hN, recN, invN, kidxN);
+      if (tile + gridDim.x < tiles) layer0(tile + gridDim.x, hN, recN, invN, kidxN, tgN);
       // ---- D1 epilogue: hidden pre-activation (own 20 columns) -> MaxAbs -> a2
       mbar_wait(&bars[B_D1FULL], n_tile & 1);
       fence_after();
@@ -425,18 +445,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       if (live) {
         if (p.gy_ext != nullptr) {
 #pragma unroll
-          for (int o = 0; o < OUT; ++o) gy[o] = __ldg(p.gy_ext + b * OUT + o);
+          for (int o = 0; o < OUT; ++o) gy[o] = tg0[o];
         } else {
 #pragma unroll
           for (int o = 0; o < OUT; ++o) {
-            float t;
-            if (p.target_kind == HOIR_TARGET_U8_IMAGE) {
-              const unsigned char* img = static_cast<const unsigned char*>(p.target);
-              const float u = (float)img[(p.mesh.first_pixel + b) * OUT + o];
-              t = __fsub_rn(__fdiv_rn(__fmul_rn(u, 2.f), 255.f), 1.f);
-            } else {
-              t = __ldg(static_cast<const float*>(p.target) + b * OUT + o);
-            }
+            const float t = p.target_kind == HOIR_TARGET_U8_IMAGE
+                                ? __fsub_rn(__fdiv_rn(__fmul_rn(tg0[o], 2.f), 255.f), 1.f) : tg0[o];
             const float diff = yo[o] - t;
             if (hf == 0) loss_local = fmaf(diff, diff, loss_local);
             gy[o] = 2.f * diff * p.loss_scale;
