@@ -16,6 +16,8 @@ int hoir_dense_tc_backward(const void* entry, const hoir_layer_desc* d, long lon
 
 // slab_kernels.cu: shared-memory slab kernels for piecewise layers with many segments
 bool hoir_slab_eligible(const hoir_layer_desc* d, long long B);
+bool hoir_slab_forward_eligible(const hoir_layer_desc* d, long long B);
+int hoir_slab_forward(const hoir_layer_desc* d, long long B, const float* x, const float* wp, float* y, cudaStream_t stream);
 int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, const float* gy, float* gw, cudaStream_t stream);
 
 namespace {
@@ -405,6 +407,7 @@ extern "C" int hoir_layer_forward(const hoir_layer_desc* d, long long B, const f
     return hoir_set_error(HOIR_EUNSUPPORTED, "in_features*(n+2) exceeds the shared-memory tile", "hoir_layer_forward");
   float* wp = nullptr;
   if (int e = pack_weights(p, w, &wp, (cudaStream_t)stream)) return e;
+  if (hoir_slab_forward_eligible(d, B)) return hoir_slab_forward(d, B, x, wp, y, (cudaStream_t)stream);
   int TB = (int)min((size_t)64, (size_t)kSmemBudget / per_sample);
   if ((long long)TB > B) TB = (int)B;
   const size_t smem = per_sample * TB;
@@ -484,7 +487,7 @@ static int maxabs_launch(long long B, int width, float eps, const float* x, cons
   if (B < 0 || width < 1) return hoir_set_error(HOIR_EINVAL, "bad shape", where);
   if (B == 0) return HOIR_OK;
   if (!x || !out) return hoir_set_error(HOIR_EINVAL, "null device pointer", where);
-  int grid = (int)min((B + 7) / 8, (long long)num_sms() * 8);
+  int grid = (int)min((B + 7) / 8, (long long)num_sms() * 128);   // one row per warp: latency-bound, so many warps
   maxabs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, width, eps, x, gy, out);
   HOIR_CHECK_CUDA(cudaGetLastError());
   return HOIR_OK;

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "hoir_common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -30,8 +31,8 @@ struct SlabParams {
   LagrangeTable lag;
 };
 
-template <int N>
-__device__ __forceinline__ void slab_eval(const SlabParams& p, float xv, int& base, float* l) {
+template <int N, class PARAMS>
+__device__ __forceinline__ void slab_eval(const PARAMS& p, float xv, int& base, float* l) {
   const int id = hoir::segment_index(xv, 1.f, 2.f, p.segf, p.segments);
   const float xi = p.pow2 ? hoir::local_coordinate<true>(xv, id, 1.f, 2.f, p.segf, p.inv_segf)
                           : hoir::local_coordinate<false>(xv, id, 1.f, 2.f, p.segf, p.inv_segf);
@@ -151,6 +152,134 @@ __global__ void __launch_bounds__(SLAB_THREADS) slab_gw_kernel(const SlabParams 
   }
 }
 
+// ---- forward of a many-segment layer: weight slabs streamed through shared memory ------------------------
+// CTA = tile of 512 samples (16 compute warps x 32 samples) + 1 loader warp, persistent grid.  The packed
+// weights [in][node][OP4] are cut into groups of GI inputs; the loader streams group after group into a
+// 3-stage shared-memory ring with cp.async.bulk (+ mbarrier transaction count), every compute warp consumes
+// each group for its 32 samples: basis records evaluated lane-parallel (one sample per lane), broadcast
+// through a per-warp smem slot, node rows read with conflict-free LDS.64 (lane <-> outputs 2*lane, 2*lane+1),
+// the 32 x 2 partial sums live in registers across all groups; y is written once, coalesced.  Per tile the
+// whole weight table crosses L2 -> smem once (2.2 MB per 512 samples for the interpolator's input layer).
+constexpr int FW_WARPS = 16, FW_TILE = FW_WARPS * 32, FW_THREADS = (FW_WARPS + 1) * 32, FW_STAGES = 3;
+
+struct FwdParams {
+  long long B;
+  int n, segments, stride, in_f, out_f, nodes, op4, gi, ngroups;
+  float segf, inv_segf, rescale;
+  int pow2;
+  uint32_t stage_bytes;
+  const float* x;
+  const float* wp;      // packed [in][node][op4]
+  float* y;
+  LagrangeTable lag;
+};
+
+template <int N>
+__global__ void __launch_bounds__(FW_THREADS, 1) slab_fwd_kernel(const FwdParams p) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  float4* sRec = reinterpret_cast<float4*>(fsm + (size_t)FW_STAGES * p.stage_bytes);     // [FW_WARPS][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRec + FW_WARPS * 32);                    // full[ST], empty[ST]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (tid == 0) {
+    for (int s = 0; s < FW_STAGES; ++s) {
+      tc::mbar_init(&bars[s], 1);
+      tc::mbar_init(&bars[FW_STAGES + s], FW_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncthreads();
+  const long long tiles = (p.B + FW_TILE - 1) / FW_TILE;
+  const size_t per_input = (size_t)p.nodes * p.op4;          // floats
+  if (warp == FW_WARPS) {
+    if (tc::elect_one()) {
+      uint32_t q = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int g = 0; g < p.ngroups; ++g, ++q) {
+          const uint32_t st = q % FW_STAGES, ph = (q / FW_STAGES) & 1;
+          tc::mbar_wait_backoff(&bars[FW_STAGES + st], ph ^ 1, 64);
+          const int gi = min(p.gi, p.in_f - g * p.gi);
+          const uint32_t bytes = (uint32_t)(gi * per_input * sizeof(float));
+          tc::mbar_expect_tx(&bars[st], bytes);
+          tc::bulk_g2s(fsm + (size_t)st * p.stage_bytes, p.wp + (size_t)g * p.gi * per_input, bytes, &bars[st]);
+        }
+      }
+    }
+    return;
+  }
+  float4* myrec = sRec + warp * 32;
+  const bool act = 2 * lane < p.out_f, act1 = 2 * lane + 1 < p.out_f;
+  uint32_t q = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long b0 = tile * FW_TILE + warp * 32;
+    const long long bl = b0 + lane;
+    const bool live = bl < p.B;
+    float2 acc[32];
+#pragma unroll
+    for (int s = 0; s < 32; ++s) acc[s] = make_float2(0.f, 0.f);
+    for (int g = 0; g < p.ngroups; ++g, ++q) {
+      const uint32_t st = q % FW_STAGES, ph = (q / FW_STAGES) & 1;
+      const int i0 = g * p.gi, gi = min(p.gi, p.in_f - i0);
+      // this lane's sample: the group's inputs (one 16-byte load when the group is 4 aligned inputs)
+      float xv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live) {
+        const float* xr = p.x + bl * p.in_f + i0;
+        if (gi == 4 && (p.in_f & 3) == 0 && (i0 & 3) == 0) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(xr));
+          xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+        } else {
+#pragma unroll
+          for (int il = 0; il < 4; ++il)
+            if (il < gi) xv[il] = __ldg(xr + il);
+        }
+      }
+      tc::mbar_wait(&bars[st], ph);
+      const float* slab = reinterpret_cast<const float*>(fsm + (size_t)st * p.stage_bytes) + 2 * lane;
+#pragma unroll
+      for (int il = 0; il < 4; ++il) {
+        if (il < gi) {
+          int base = 0;
+          float l[N];
+          slab_eval<N>(p, xv[il], base, l);
+          __syncwarp();
+          myrec[lane] = make_float4(__int_as_float((il * p.nodes + base) * p.op4), l[0], N > 1 ? l[1] : 0.f, N > 2 ? l[2] : 0.f);
+          __syncwarp();
+          if (act) {
+#pragma unroll
+            for (int s = 0; s < 32; ++s) {
+              const float4 rc = myrec[s];
+              const float lj[3] = {rc.y, rc.z, rc.w};
+              const float* row = slab + __float_as_int(rc.x);
+#pragma unroll
+              for (int j = 0; j < N; ++j) {
+                const float2 w2 = *reinterpret_cast<const float2*>(row + j * p.op4);
+                acc[s].x = fmaf(lj[j], w2.x, acc[s].x);
+                acc[s].y = fmaf(lj[j], w2.y, acc[s].y);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars[FW_STAGES + st]);
+    }
+    if (act) {
+#pragma unroll
+      for (int s = 0; s < 32; ++s) {
+        if (b0 + s < p.B) {
+          float* yo = p.y + (b0 + s) * p.out_f + 2 * lane;
+          if (act1 && (p.out_f & 1) == 0) {
+            *reinterpret_cast<float2*>(yo) = make_float2(acc[s].x * p.rescale, acc[s].y * p.rescale);
+          } else {
+            yo[0] = acc[s].x * p.rescale;
+            if (act1) yo[1] = acc[s].y * p.rescale;
+          }
+        }
+      }
+    }
+  }
+}
+
 int slab_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -229,4 +358,48 @@ int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, cons
     case 2: return slab_launch(slab_gw_kernel<2>, p, stream, extra);
     default: return slab_launch(slab_gw_kernel<3>, p, stream, extra);
   }
+}
+
+// forward through the streamed-slab kernel; wp = packed weights [in][node][out_pad4] (layer_pack_kernel)
+int hoir_slab_forward(const hoir_layer_desc* d, long long B, const float* x, const float* wp, float* y,
+                      cudaStream_t stream) {
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.n = d->n;
+  p.segments = d->segments;
+  p.stride = hoir::piecewise_stride(d->kind, d->n);
+  p.in_f = d->in_features;
+  p.out_f = d->out_features;
+  p.nodes = hoir_layer_nodes(d);
+  p.op4 = (d->out_features + 3) & ~3;
+  p.segf = (float)d->segments;
+  p.inv_segf = 1.f / (float)d->segments;
+  p.rescale = d->rescale == 0.f ? 1.f : d->rescale;
+  p.pow2 = hoir::is_pow2(d->segments);
+  hoir_make_lagrange_table(d->n, 1.f, &p.lag);
+  p.x = x;
+  p.wp = wp;
+  p.y = y;
+  const size_t per_input = (size_t)p.nodes * p.op4 * sizeof(float);
+  int gi = (int)((48 * 1024) / per_input);
+  gi = gi < 1 ? 1 : (gi > 4 ? 4 : gi);
+  if (gi == 3) gi = 2;
+  p.gi = gi;
+  p.ngroups = (p.in_f + gi - 1) / gi;
+  p.stage_bytes = (uint32_t)((gi * per_input + 127) / 128 * 128);
+  const size_t smem = (size_t)FW_STAGES * p.stage_bytes + FW_WARPS * 32 * sizeof(float4) + 2 * FW_STAGES * sizeof(uint64_t) + 64;
+  auto kern = d->n == 2 ? slab_fwd_kernel<2> : slab_fwd_kernel<3>;
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long tiles = (B + FW_TILE - 1) / FW_TILE;
+  const int grid = (int)(tiles < slab_sms() ? tiles : slab_sms());
+  kern<<<grid, FW_THREADS, smem, stream>>>(p);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+bool hoir_slab_forward_eligible(const hoir_layer_desc* d, long long B) {
+  if (!hoir_slab_eligible(d, B)) return false;
+  const size_t per_input = (size_t)hoir_layer_nodes(d) * ((d->out_features + 3) & ~3) * sizeof(float);
+  return per_input <= 64 * 1024 && (per_input % 16) == 0;
 }

@@ -140,18 +140,23 @@ def test_positions_from_mesh_bit_exact(rows, cols, rot):
 
 
 @pytest.mark.parametrize("kind,n,in_f,out_f,seg", [("continuous", 2, 24, 50, 50), ("continuous", 3, 4, 40, 100),
-                                                   ("discontinuous", 3, 5, 33, 17)])
+                                                   ("discontinuous", 3, 5, 33, 17), ("continuous", 2, 216, 50, 50),
+                                                   ("discontinuous", 2, 7, 64, 9)])
 def test_large_batch_many_segments_gradient(kind, n, in_f, out_f, seg):
-    """B >= 4096 with many segments routes dL/dw through the input-owner kernel (per-warp private accumulators)."""
+    """B >= 4096 with many segments routes the forward through the streamed-slab kernel and dL/dw through the
+    shared-memory slab kernel (slab_kernels.cu)."""
     ref, lay = make_layers(kind, n, in_f, out_f, seg)
     B = 5000
     g = torch.Generator().manual_seed(B)
     x = torch.rand(B, in_f, generator=g) * 2.2 - 1.1
     gy = torch.randn(B, out_f, generator=g)
     xr = x.clone().requires_grad_(True)
-    ref(xr).backward(gy)
+    yr = ref(xr)
+    yr.backward(gy)
     xc = x.cuda().requires_grad_(True)
-    lay(xc).backward(gy.cuda())
+    yc = lay(xc)
+    yc.backward(gy.cuda())
+    assert rel_err(yc, yr) <= 1e-5
     assert rel_err(xc.grad, xr.grad) <= 1e-5
     assert rel_err(lay.w.grad, ref.w.grad) <= 1e-5
 
