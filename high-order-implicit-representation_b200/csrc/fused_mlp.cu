@@ -639,7 +639,58 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
     if (key >= 0) s_ent[base + __popc(peers & ((1u << lane) - 1u))] = ((unsigned)key << 14) | (unsigned)t;
   }
   __syncthreads();
-  // every warp reduces blocks of consecutive sorted entries; a segment change inside a block flushes to the slab
+  // reduction over the sorted entries.  hid % 8 == 0 (the 40-wide family): a group of 4 lanes owns a contiguous
+  // range of the sorted list, each lane hid/4 outputs -- per entry one broadcast record load, hid/8 8-byte
+  // loads of the dL/dy row and 3 * hid/4 FMAs per lane (5 warp-instructions per entry instead of 30); a segment
+  // change flushes the group's registers into the CTA's slab.  Otherwise: warp per entry, lane <-> outputs.
+  if (hid == 40) {
+    constexpr int OPL = 10;                                   // outputs per lane
+    const int grp = threadIdx.x >> 2, sub = threadIdx.x & 3, ngrp = GW0_THREADS / 4;
+    const int per = (n + ngrp - 1) / ngrp;
+    const int k0 = grp * per, k1 = min(n, k0 + per);
+    if (k0 < k1) {
+      int cur = (int)(s_ent[k0] >> 14);
+      float acc[N][OPL];
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int o = 0; o < OPL; ++o) acc[j][o] = 0.f;
+      auto flush = [&](int sg) {
+        float* dst = slab + (size_t)(sg * stride) * pitch + sub * OPL;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+          for (int o = 0; o < OPL; ++o) {
+            if (acc[j][o] != 0.f) atomicAdd(dst + j * pitch + o, acc[j][o]);
+            acc[j][o] = 0.f;
+          }
+      };
+#pragma unroll 2
+      for (int k = k0; k < k1; ++k) {
+        const unsigned e = s_ent[k];
+        const int t = (int)(e & 0x3fffu), sg = (int)(e >> 14);
+        const float4 rc = __ldg(rec + t);
+        const float2* grow = reinterpret_cast<const float2*>(ws_g0 + (size_t)(b0 + t) * 40 + sub * OPL);
+        float g[OPL];
+#pragma unroll
+        for (int o = 0; o < OPL / 2; ++o) {
+          const float2 v = __ldg(grow + o);
+          g[2 * o] = v.x;
+          g[2 * o + 1] = v.y;
+        }
+        if (sg != cur) {
+          flush(cur);
+          cur = sg;
+        }
+        const float l[3] = {rc.y, rc.z, rc.w};
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+          for (int o = 0; o < OPL; ++o) acc[j][o] = fmaf(l[j], g[o], acc[j][o]);
+      }
+      flush(cur);
+    }
+  } else {
   const bool hi = lane + 32 < hid, lo = lane < hid;
   for (int k0 = warp * GW0_BLOCK; k0 < n; k0 += GW0_WARPS * GW0_BLOCK) {
     const int k1 = k0 + GW0_BLOCK < n ? k0 + GW0_BLOCK : n;
@@ -676,6 +727,7 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
       }
     }
     flush(cur);
+  }
   }
   __syncthreads();
   for (int k = threadIdx.x; k < hid * nodes0; k += GW0_THREADS) {
