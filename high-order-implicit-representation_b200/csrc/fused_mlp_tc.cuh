@@ -65,7 +65,7 @@ struct TcPlan {
 };
 
 enum { B_FFULL0 = 0, B_FFULL1, B_FEMPTY0, B_FEMPTY1, B_D1FULL, B_D1EMPTY, B_GFULL, B_TFULL, B_GWDONE,
-       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_A1FULL, B_A1FREE, B_COUNT };
+       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_A1FULL, B_A1FREE, B_A2FULL, B_A2FREE, B_COUNT };
 
 // y[O] += sum_j l[j] * W[j * PITCH + 0..O)
 template <int N, int O, int PITCH, bool GLOBAL>
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
   float* sA1 = reinterpret_cast<float*>(smem + P::OFF_A1);
   float* sA2 = reinterpret_cast<float*>(smem + P::OFF_A2);
   float* sW2 = reinterpret_cast<float*>(smem + P::OFF_W2);
-  float* sAcc2 = reinterpret_cast<float*>(smem + P::OFF_ACC2);
+  float* sGY = reinterpret_cast<float*>(smem + P::OFF_ACC2);   // [TS][4] dL/dy rows for the helpers' dL/dw2 pass
   float* sX = reinterpret_cast<float*>(smem + P::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + B_COUNT);
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     mbar_init(&bars[B_UFULL0], NHELPER); mbar_init(&bars[B_UFULL1], NHELPER);
     mbar_init(&bars[B_UEMPTY0], 1);  mbar_init(&bars[B_UEMPTY1], 1);
     mbar_init(&bars[B_A1FULL], NSAMPLE_THREADS); mbar_init(&bars[B_A1FREE], NHELPER);
+    mbar_init(&bars[B_A2FULL], NSAMPLE_THREADS); mbar_init(&bars[B_A2FREE], NHELPER);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   {
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       *reinterpret_cast<float*>(sW1L + off) = tf32_lo(v);
     }
     const float* w2 = p.packed + p.off[2];
-    for (int k = tid; k < S::WO; k += NTHREADS) { sW2[k] = __ldg(w2 + k); sAcc2[k] = 0.f; }
+    for (int k = tid; k < S::WO; k += NTHREADS) sW2[k] = __ldg(w2 + k);
+    static_assert(TS * 4 * 4 <= (int)P::W2_BYTES, "dL/dy tile fits the slot behind W2");
   }
   fence_async_smem();
   fence_before();
@@ -262,10 +264,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     uint32_t coff[ND];
 #pragma unroll
     for (int k = 0; k < ND; ++k) coff[k] = ((uint32_t)((kb + k) & 31) << 2) | (((uint32_t)(kb + k) >> 5) << 16);
+    // dL/dw2 (output layer): the same thread owns input i for one half of the tile's samples and keeps the
+    // 5 nodes x 3 outputs sums in registers for the WHOLE kernel -- no warp shuffles, no per-tile reduction
+    float acc2[ND][OUT];
+#pragma unroll
+    for (int k = 0; k < ND; ++k)
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) acc2[k][o] = 0.f;
     uint32_t q_unit = 0, n_tile = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
       mbar_wait_backoff(&bars[B_A1FULL], n_tile & 1, 128);
       for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
+        if (u == 2) {   // two units are staged ahead; now the hidden activations a2 and dL/dy of this tile are due
+          mbar_wait_backoff(&bars[B_A2FULL], n_tile & 1, 64);
+          if (sh < 2) {
+#pragma unroll 4
+            for (int t = 0; t < TS / 2; ++t) {
+              const int sl = sh * (TS / 2) + t;
+              const float x = sA2[sl * APITCH + i];
+              const float4 gy4 = *reinterpret_cast<const float4*>(sGY + sl * 4);
+              int id;
+              float xi, l[N];
+              locate2(x, id, xi);
+              hoir::lagrange<N>(lag.X, lag.D, xi, l);
+              const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+              const float gyv[3] = {gy4.x, gy4.y, gy4.z};
+#pragma unroll
+              for (int k = 0; k < ND; ++k)
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) acc2[k][o] = fmaf(c5[k], gyv[o], acc2[k][o]);
+            }
+          }
+          mbar_arrive(&bars[B_A2FREE]);
+        }
         const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
         mbar_wait_backoff(&bars[B_UEMPTY0 + buf], ph ^ 1, 128);
         if (sh < 2) {
@@ -293,6 +324,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         mbar_arrive(&bars[B_UFULL0 + buf]);
       }
       mbar_arrive(&bars[B_A1FREE]);                   // done reading this tile's a1 rows
+    }
+    if (sh < 2) {
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+#pragma unroll
+        for (int o = 0; o < OUT; ++o)
+          if (acc2[k][o] != 0.f) hoir::red_add(p.gw[2] + ((size_t)o * HID + i) * S::NODES_O + k, acc2[k][o]);
     }
   } else {
     // =========================== sample warps ===============================================
@@ -360,9 +398,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     float invN = 1.f;
     int kidxN = 0;
     float tgN[OUT];
-    float acc2[HH];                                   // dL/dw2 partial sums owned by this lane (see below)
-#pragma unroll
-    for (int j = 0; j < HH; ++j) acc2[j] = 0.f;
     if ((long long)blockIdx.x < tiles) layer0(blockIdx.x, hN, recN, invN, kidxN, tgN);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
       const long long b = tile * TS + s;
@@ -420,6 +455,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       fence_before();
       mbar_arrive(&bars[B_D1EMPTY]);
       if (p.normalize) maxabs_pair<HH>(h, hf, p.norm_eps, xs, xo, warp, inv_d1, kidx1);
+      if (n_tile > 0) mbar_wait(&bars[B_A2FREE], (n_tile - 1) & 1);   // helpers are done with the previous a2 / dL/dy
 #pragma unroll
       for (int j = 0; j < HH; ++j) a2[hf * HH + j] = h[j];
       // ---- output layer forward (FFMA) over own 20 inputs, pair sum, loss, dL/dy
@@ -457,7 +493,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
           }
         }
       }
-      // ---- output layer backward (FFMA) over own 20 inputs: dL/da2 and dL/dw2
+      if (hf == 0) *reinterpret_cast<float4*>(sGY + s * 4) = make_float4(gy[0], gy[1], gy[2], 0.f);
+      mbar_arrive(&bars[B_A2FULL]);                   // (release) a2 row + dL/dy: the helpers accumulate dL/dw2
+      // ---- output layer backward (FFMA) over own 20 inputs: dL/da2
       float g[HH];
       float dot = 0.f;
 #pragma unroll
@@ -511,34 +549,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       fence_async_smem();
       fence_before();
       mbar_arrive(&bars[B_GFULL]);
-      // ---- dL/dw2 while the tensor pipe computes T = G * W1^T: densified basis row x dL/dy, 5 x 3 products
-      //      (+1 pad), reduce-scatter over the warp's 32 samples
-#pragma unroll
-      for (int j = 0; j < HH; ++j) {
-        int id;
-        float xi, l[N];
-        locate2(a2[hf * HH + j], id, xi);
-        hoir::lagrange<N>(lag.X, lag.D, xi, l);
-        const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
-        float r[16];
-#pragma unroll
-        for (int k = 0; k < ND; ++k)
-#pragma unroll
-          for (int o = 0; o < OUT; ++o) r[k * OUT + o] = c5[k] * gy[o];
-        r[15] = 0.f;
-#pragma unroll
-        for (int st = 16, n = 8; st >= 2; st >>= 1, n >>= 1) {
-          const bool up = (lane & st) != 0;
-#pragma unroll
-          for (int m = 0; m < n; ++m) {
-            const float send = up ? r[m] : r[m + n];
-            const float keep = up ? r[m + n] : r[m];
-            r[m] = keep + __shfl_xor_sync(0xffffffffu, send, st);
-          }
-        }
-        r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-        acc2[j] += r[0];   // this lane's element e(lane) of input i, summed over the warp's 32 samples
-      }
       // ---- T epilogue (own 4 inputs per chunk): dL/da1 = slope * sum_j l'_j * T[kbase(i) + window + j]
       dot = 0.f;
       mbar_wait(&bars[B_TFULL], n_tile & 1);
@@ -597,7 +607,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         continue;
       }
       // ---- otherwise: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
-      mbar_wait(&bars[B_A1FREE], n_tile & 1);         // helpers are done with sA1 (aliased below)
+      mbar_wait(&bars[B_A1FREE], n_tile & 1);         // helpers are done with sA1 / sA2 (aliased below)
+      mbar_wait(&bars[B_A2FREE], n_tile & 1);
       bar_samples();                                  // everyone is done reading sA1 / sA2
       {
         float* sG0 = sA1;                             // [s][GPITCH] dL/d(layer-0 output)
@@ -664,16 +675,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     if (p.gy_ext == nullptr && hf == 0) {
       const float sum = hoir::warp_sum(loss_local) * p.loss_scale;
       if (lane == 0 && sum != 0.f) hoir::red_add(p.loss_sum, sum);
-    }
-    {
-      // after the reduce-scatter lane L holds element e(L) = (node k, output o) of every input it walked
-      const int e = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-      if ((lane & 1) == 0 && e < ND * OUT) {
-        const int k = e / OUT, o = e - k * OUT;
-#pragma unroll
-        for (int j = 0; j < HH; ++j)
-          if (acc2[j] != 0.f) hoir::red_add(p.gw[2] + ((size_t)o * HID + hf * HH + j) * S::NODES_O + k, acc2[j]);
-      }
     }
     if (n_tile > 0) {
       mbar_wait(&bars[B_GWDONE], (n_tile - 1) & 1);
