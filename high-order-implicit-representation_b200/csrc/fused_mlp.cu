@@ -770,7 +770,8 @@ constexpr FusedEntry make_entry_tc() {
 // C1 (10-wide, 2 hidden layers), continuous and discontinuous, n = 3; plus n = 2 variants.
 const FusedEntry kEntries[] = {
     make_entry_tc<Shape<HOIR_CONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
-    make_entry<Shape<HOIR_DISCONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
+    make_entry_tc<Shape<HOIR_DISCONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
+    make_entry_tc<Shape<HOIR_DISCONTINUOUS, 3, 2, 40, 3, 1, 2, 2>>(),
     make_entry_tc<Shape<HOIR_CONTINUOUS, 3, 2, 40, 3, 1, 2, 2>>(),
     make_entry<Shape<HOIR_CONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),
     make_entry<Shape<HOIR_DISCONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),

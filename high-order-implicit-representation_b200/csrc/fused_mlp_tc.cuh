@@ -34,14 +34,17 @@ template <class S>
 struct TcPlan {
   static constexpr int HID = S::HID, ND = S::NODES_H, KH = HID * ND;       // 40, 5, 200
   static constexpr int HH = HID / 2;                                       // hidden units owned by one thread of a pair
-  static constexpr int QI = 4, CH_IN = 2 * QI, NCH = HH / QI;              // FWD chunk: 4 inputs of each half
-  static constexpr int HK = QI * ND, CH_K = 2 * HK;                        // 20 K-columns per half, 40 per chunk
+  // FWD chunk: QI inputs of each half.  continuous (5 slots per input): 4 inputs, 40 K-columns per chunk;
+  // discontinuous (6 slots): 2 inputs, 24 K-columns per chunk -- keeps the double-buffered A staging plus the
+  // 240-column T accumulator inside the 512 TMEM columns
+  static constexpr int QI = S::CONT ? 4 : 2, CH_IN = 2 * QI, NCH = HH / QI;
+  static constexpr int HK = QI * ND, CH_K = 2 * HK;                        // K-columns per half / per chunk
   static constexpr int KP = (KH + 31) / 32 * 32;                            // 224: W1 columns padded to atoms
   static constexpr int TN = (KH + 15) / 16 * 16;                            // 208: N of the GX product
-  static constexpr int UNIT = 16, NUNIT = TS / UNIT;                        // GW: samples per smem unit
+  static constexpr int UNIT = S::CONT ? 16 : 8, NUNIT = TS / UNIT;          // GW: samples per smem unit (smem budget)
   static constexpr int GPITCH = 44;                                         // layer-0 dL/dy tile [s][44]
   // TMEM columns
-  static constexpr int D1_COL = 0, FA_COL = 64, G_COL = 64, T_COL = 224, GW_COL = 432;
+  static constexpr int D1_COL = 0, FA_COL = 64, G_COL = 64, T_COL = FA_COL + 4 * CH_K, GW_COL = T_COL + TN;
   // shared memory (bytes)
   static constexpr uint32_t W1_RS = KP / 32 * 512, W1_BYTES = HID / 4 * W1_RS;          // 3584, 35840
   static constexpr uint32_t GT_RS = TS / 32 * 512, GT_BYTES = HID / 4 * GT_RS;          // 2048, 20480
@@ -55,9 +58,9 @@ struct TcPlan {
                             OFF_ACC2 = OFF_W2 + W2_BYTES, OFF_X = OFF_ACC2 + W2_BYTES, OFF_BAR = OFF_X + X_BYTES,
                             SMEM_BYTES = OFF_BAR + 256;
   static constexpr uint32_t G0_BYTES = TS * GPITCH * 4;                                 // aliases A1 (+ start of A2)
-  static_assert(S::KIND == HOIR_CONTINUOUS && S::N == 3 && S::SEGH == 2 && S::SEGO == 2 && S::NH == 1, "tensor path: C2 family");
+  static_assert(S::N == 3 && S::SEGH == 2 && S::SEGO == 2 && S::NH == 1, "tensor path: C2 / C3 family");
   static_assert(HID == 40 && HH % QI == 0 && HK % 4 == 0 && CH_K % 8 == 0 && KH <= 256, "tensor path shape");
-  static_assert(FA_COL + 4 * CH_K <= T_COL && T_COL + TN <= GW_COL && GW_COL + 2 * HID <= 512, "TMEM plan");
+  static_assert(G_COL + 2 * HID <= T_COL && GW_COL + 2 * HID <= 512 && UNIT % 8 == 0 && (UNIT / 2) % 4 == 0, "TMEM / unit plan");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan");
   static_assert(G0_BYTES + S::IN * 16 * TS <= 2 * A_BYTES, "layer-0 dL/dw tiles alias A1/A2");
   // K-column of node 0 of hidden-layer input i: chunk c = (i % 20) / 4 holds [half 0: 4 inputs | half 1: 4 inputs]
@@ -83,6 +86,37 @@ __device__ __forceinline__ void contract_fwd_p(const float* __restrict__ wrow, c
       acc[4 * q + 3] = fmaf(l[j], w.w, acc[4 * q + 3]);
     }
   }
+}
+
+// Densified basis row of one input: the N = 3 Lagrange values of segment id (0 / 1) scattered into the ND node
+// slots (continuous: the two segments share node 2; discontinuous: slots 0-2 / 3-5), zeros elsewhere.
+template <class S, int ND>
+__device__ __forceinline__ void densify(int id, const float* __restrict__ l, float* __restrict__ v) {
+#pragma unroll
+  for (int q = 0; q < ND; ++q) {
+    const float lower = q < 3 ? l[q < 3 ? q : 0] : 0.f;
+    const float upper = (q >= S::STRIDE && q - S::STRIDE < 3) ? l[(q >= S::STRIDE && q - S::STRIDE < 3) ? q - S::STRIDE : 0] : 0.f;
+    v[q] = id ? upper : lower;
+  }
+}
+// the 3 entries of a densified row t[ND] that belong to segment id
+template <class S>
+__device__ __forceinline__ void window3(int id, const float* __restrict__ t, float& t0, float& t1, float& t2) {
+  t0 = id ? t[S::STRIDE + 0] : t[0];
+  t1 = id ? t[S::STRIDE + 1] : t[1];
+  t2 = id ? t[S::STRIDE + 2] : t[2];
+}
+template <int K>
+__device__ __forceinline__ void tmem_stK(uint32_t addr, const float* v) {
+  static_assert(K % 4 == 0, "column groups of 4");
+#pragma unroll
+  for (int q = 0; q < K / 4; ++q) tmem_st4(addr + 4 * q, v + 4 * q);
+}
+template <int K>
+__device__ __forceinline__ void tmem_ldK(uint32_t addr, float* v) {
+  static_assert(K % 4 == 0, "column groups of 4");
+#pragma unroll
+  for (int q = 0; q < K / 4; ++q) tmem_ld4(addr + 4 * q, v + 4 * q);
 }
 
 // MaxAbsNormalization of a 40-wide row split over a thread pair (20 values each); first index wins ties.
@@ -287,7 +321,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
               float xi, l[N];
               locate2(x, id, xi);
               hoir::lagrange<N>(lag.X, lag.D, xi, l);
-              const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+              float c5[ND];
+            densify<S, ND>(id, l, c5);
               const float gyv[3] = {gy4.x, gy4.y, gy4.z};
 #pragma unroll
               for (int k = 0; k < ND; ++k)
@@ -310,7 +345,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
             float xi, l[N];
             locate2(x, id, xi);
             hoir::lagrange<N>(lag.X, lag.D, xi, l);
-            const float c5[ND] = {id ? 0.f : l[0], id ? 0.f : l[1], id ? l[0] : l[2], id ? l[1] : 0.f, id ? l[2] : 0.f};
+            float c5[ND];
+            densify<S, ND>(id, l, c5);
             const uint32_t rowoff = (uint32_t)(t & 3) * 128u + (uint32_t)(sl >> 2) * P::U_RS;
 #pragma unroll
             for (int k = 0; k < ND; ++k) {
@@ -430,17 +466,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
           float xi, l[N];
           locate2(x, id, xi);
           hoir::lagrange<N>(lag.X, lag.D, xi, l);
-          v[m * ND + 0] = id ? 0.f : l[0];
-          v[m * ND + 1] = id ? 0.f : l[1];
-          v[m * ND + 2] = id ? l[0] : l[2];
-          v[m * ND + 3] = id ? l[1] : 0.f;
-          v[m * ND + 4] = id ? l[2] : 0.f;
+          densify<S, ND>(id, l, v + m * ND);
         }
 #pragma unroll
         for (int j = 0; j < P::HK; ++j) lo[j] = tf32_lo(v[j]);
         const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K + hf * P::HK;
-        tmem_st20(col, v);
-        tmem_st20(col + P::CH_K, lo);
+        tmem_stK<P::HK>(col, v);
+        tmem_stK<P::HK>(col + P::CH_K, lo);
         tmem_wait_st();
         fence_before();
         mbar_arrive(&bars[B_FFULL0 + buf]);
@@ -556,7 +588,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
 #pragma unroll
       for (int c = 0; c < P::NCH; ++c) {
         float t[P::HK];
-        tmem_ld20(tm_lane + P::T_COL + c * P::CH_K + hf * P::HK, t);
+        tmem_ldK<P::HK>(tm_lane + P::T_COL + c * P::CH_K + hf * P::HK, t);
         tmem_wait_ld();
 #pragma unroll
         for (int m = 0; m < P::QI; ++m) {
@@ -565,9 +597,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
           float xi, l[N], d[N];
           locate2(x, id, xi);
           hoir::lagrange_deriv<N>(lag.X, lag.D, xi, l, d);
-          const float t0 = id ? t[m * ND + 2] : t[m * ND + 0];
-          const float t1 = id ? t[m * ND + 3] : t[m * ND + 1];
-          const float t2 = id ? t[m * ND + 4] : t[m * ND + 2];
+          float t0, t1, t2;
+          window3<S>(id, t + m * ND, t0, t1, t2);
           const float gx = fmaf(d[2], t2, fmaf(d[1], t1, d[0] * t0)) * 2.f;
           dot = fmaf(gx, x, dot);
           g[c * P::QI + m] = gx;
@@ -845,19 +876,15 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 2) fused_mlp_tc_fwd_kernel(const
           float xi, l[N];
           locate2(hN[c * P::QI + m], id, xi);
           hoir::lagrange<N>(lag.X, lag.D, xi, l);
-          v[m * ND + 0] = id ? 0.f : l[0];
-          v[m * ND + 1] = id ? 0.f : l[1];
-          v[m * ND + 2] = id ? l[0] : l[2];
-          v[m * ND + 3] = id ? l[1] : 0.f;
-          v[m * ND + 4] = id ? l[2] : 0.f;
+          densify<S, ND>(id, l, v + m * ND);
         }
 #pragma unroll
         for (int j = 0; j < P::HK; ++j) lo[j] = tf32_lo(v[j]);
         mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);
         fence_after();
         const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K + hf * P::HK;
-        tmem_st20(col, v);
-        tmem_st20(col + P::CH_K, lo);
+        tmem_stK<P::HK>(col, v);
+        tmem_stK<P::HK>(col + P::CH_K, lo);
         tmem_wait_st();
         fence_before();
         mbar_arrive(&bars[B_FFULL0 + buf]);

@@ -120,7 +120,7 @@ if __name__ == "__main__":
     tr = None
     if "c1" in which: c1()
     if "c2" in which or "c5" in which: tr = fused("C2 continuous n=3 4-40-40-3 (tcgen05 kernel)", 32880, **C2)
-    if "c3d" in which: fused("C3 discontinuous n=3 4-40-40-3 (fused FFMA kernel)", 32880, **dict(C2, layer_type="discontinuous"))
+    if "c3d" in which: fused("C3 discontinuous n=3 4-40-40-3 (tcgen05 kernel, 6 slots per input)", 32880, **dict(C2, layer_type="discontinuous"))
     if "c3f" in which: c3f()
     if "c4" in which: c4()
     if "c5" in which: c5(tr)

@@ -223,11 +223,11 @@ def test_ffma_peak_microbenchmark_runs():
         assert 5.0 < tflops < 120.0
 
 
-@pytest.mark.parametrize("coherent", [False, True])
-def test_two_pass_layer0_gradient_matches_in_kernel_path(coherent, monkeypatch):
+@pytest.mark.parametrize("coherent,name", [(False, "C2"), (True, "C2"), (False, "C3d")])
+def test_two_pass_layer0_gradient_matches_in_kernel_path(coherent, name, monkeypatch):
     """Large generic batches route the layer-0 dL/dw through the segment-owner kernel; it must agree with the
     oracle on a sub-sample and with full-batch linearity (the oracle cannot run 2^16 samples quickly)."""
-    ref, net = make_pair("C2")
+    ref, net = make_pair(name)
     tr = H.FusedTrainer(net, lr=0.0, keep_grads=True)
     B = 1 << 16
     g = torch.Generator().manual_seed(9)
@@ -251,7 +251,7 @@ def test_two_pass_layer0_gradient_matches_in_kernel_path(coherent, monkeypatch):
     # fp32 or the fp64 evaluation of the oracle as the reference for the summed gradient.
     tr.train_step(x[:4096].cuda(), y[:4096].cuda())
     O.mse_training_step(ref, x[:4096], y[:4096]).backward()
-    ref64 = O.HighOrderMLP(normalization=O.MaxAbsNormalization, **MLP_KW["C2"]).double()
+    ref64 = O.HighOrderMLP(normalization=O.MaxAbsNormalization, **MLP_KW[name]).double()
     ref64.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
     O.mse_training_step(ref64, x[:4096].double(), y[:4096].double()).backward()
     for gv, q, q64 in zip(tr.g_views, ref.parameters(), ref64.parameters()):
