@@ -890,7 +890,8 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
   if (e->fwd_tc != nullptr && !no_tc_fwd && B >= 4 * tc::TS) {
     HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd_tc));
     const long long tiles_tc = (B + tc::TS - 1) / tc::TS;
-    const long long cap = 2LL * num_sms_fused();
+    static const bool one_cta = getenv("HOIR_FWD_ONE_CTA") != nullptr;   // A/B: one CTA per SM
+    const long long cap = (one_cta ? 1LL : 2LL) * num_sms_fused();
     e->fwd_tc<<<(int)(tiles_tc < cap ? tiles_tc : cap), tc::NTHREADS_FWD, e->smem_fwd_tc, (cudaStream_t)stream>>>(p);
     HOIR_CHECK_CUDA(cudaGetLastError());
     return HOIR_OK;

@@ -477,8 +477,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         fence_before();
         mbar_arrive(&bars[B_FFULL0 + buf]);
       }
-      // ---- while the tensor pipe finishes D1: layer 0 of the NEXT tile (kept in registers)
-      if (tile + gridDim.x < tiles) layer0(tile + gridDim.x, hN, recN, invN, kidxN, tgN);
       // ---- D1 epilogue: hidden pre-activation (own 20 columns) -> MaxAbs -> a2
       mbar_wait(&bars[B_D1FULL], n_tile & 1);
       fence_after();
@@ -581,6 +579,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       fence_async_smem();
       fence_before();
       mbar_arrive(&bars[B_GFULL]);
+      // ---- while the tensor pipe computes T = G * W1^T (the longest product): layer 0 of the NEXT tile
+      if (tile + gridDim.x < tiles) layer0(tile + gridDim.x, hN, recN, invN, kidxN, tgN);
       // ---- T epilogue (own 4 inputs per chunk): dL/da1 = slope * sum_j l'_j * T[kbase(i) + window + j]
       dot = 0.f;
       mbar_wait(&bars[B_TFULL], n_tile & 1);
