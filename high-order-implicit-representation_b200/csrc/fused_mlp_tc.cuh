@@ -41,7 +41,10 @@ struct TcPlan {
   static constexpr int HK = QI * ND, CH_K = 2 * HK;                        // K-columns per half / per chunk
   static constexpr int KP = (KH + 31) / 32 * 32;                            // 224: W1 columns padded to atoms
   static constexpr int TN = (KH + 15) / 16 * 16;                            // 208: N of the GX product
-  static constexpr int UNIT = S::CONT ? 16 : 8, NUNIT = TS / UNIT;          // GW: samples per smem unit (smem budget)
+  static constexpr int UNIT = 8, NUNIT = TS / UNIT;                         // GW: samples per smem unit (smem budget)
+  // continuous: the layer-0 dL/dw tiles (dL/dy rows + basis records) get their own shared memory, so the owner
+  // walk does not have to wait until the helpers are done with a1 / a2; discontinuous (larger W1): they alias a1 / a2
+  static constexpr bool OWN_G0 = S::CONT;
   static constexpr int GPITCH = 44;                                         // layer-0 dL/dy tile [s][44]
   // TMEM columns
   static constexpr int D1_COL = 0, FA_COL = 64, G_COL = 64, T_COL = FA_COL + 4 * CH_K, GW_COL = T_COL + TN;
@@ -55,14 +58,15 @@ struct TcPlan {
   static constexpr uint32_t OFF_W1R = 0, OFF_W1L = OFF_W1R + W1_BYTES, OFF_GTR = OFF_W1L + W1_BYTES,
                             OFF_GTL = OFF_GTR + GT_BYTES, OFF_U = OFF_GTL + GT_BYTES,   // [2][raw|lo]
                             OFF_A1 = OFF_U + 4 * U_BYTES, OFF_A2 = OFF_A1 + A_BYTES, OFF_W2 = OFF_A2 + A_BYTES,
-                            OFF_ACC2 = OFF_W2 + W2_BYTES, OFF_X = OFF_ACC2 + W2_BYTES, OFF_BAR = OFF_X + X_BYTES,
-                            SMEM_BYTES = OFF_BAR + 256;
-  static constexpr uint32_t G0_BYTES = TS * GPITCH * 4;                                 // aliases A1 (+ start of A2)
+                            OFF_ACC2 = OFF_W2 + W2_BYTES, OFF_X = OFF_ACC2 + W2_BYTES, OFF_G0 = OFF_X + X_BYTES;
+  static constexpr uint32_t G0_BYTES = TS * GPITCH * 4;                                 // [s][GPITCH] dL/d(layer-0 output)
+  static constexpr uint32_t REC_BYTES = S::IN * 16 * TS;                                // [IN][TS] basis records
+  static constexpr uint32_t OFF_BAR = OFF_G0 + (OWN_G0 ? G0_BYTES + REC_BYTES : 0), SMEM_BYTES = OFF_BAR + 256;
   static_assert(S::N == 3 && S::SEGH == 2 && S::SEGO == 2 && S::NH == 1, "tensor path: C2 / C3 family");
   static_assert(HID == 40 && HH % QI == 0 && HK % 4 == 0 && CH_K % 8 == 0 && KH <= 256, "tensor path shape");
   static_assert(G_COL + 2 * HID <= T_COL && GW_COL + 2 * HID <= 512 && UNIT % 8 == 0 && (UNIT / 2) % 4 == 0, "TMEM / unit plan");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan");
-  static_assert(G0_BYTES + S::IN * 16 * TS <= 2 * A_BYTES, "layer-0 dL/dw tiles alias A1/A2");
+  static_assert(OWN_G0 || G0_BYTES + REC_BYTES <= 2 * A_BYTES, "layer-0 dL/dw tiles alias A1/A2");
   // K-column of node 0 of hidden-layer input i: chunk c = (i % 20) / 4 holds [half 0: 4 inputs | half 1: 4 inputs]
   __host__ __device__ static constexpr int kbase(int i) { return ((i % HH) / QI) * CH_K + (i / HH) * HK + (i % QI) * ND; }
 };
@@ -638,12 +642,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         continue;
       }
       // ---- otherwise: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
-      mbar_wait(&bars[B_A1FREE], n_tile & 1);         // helpers are done with sA1 / sA2 (aliased below)
-      mbar_wait(&bars[B_A2FREE], n_tile & 1);
-      bar_samples();                                  // everyone is done reading sA1 / sA2
+      if (!P::OWN_G0) {
+        mbar_wait(&bars[B_A1FREE], n_tile & 1);       // helpers are done with sA1 / sA2 (aliased below)
+        mbar_wait(&bars[B_A2FREE], n_tile & 1);
+        bar_samples();                                // everyone is done reading sA1 / sA2
+      }
       {
-        float* sG0 = sA1;                             // [s][GPITCH] dL/d(layer-0 output)
-        float4* sRec = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sA1) + P::G0_BYTES);   // [IN][TS]
+        uint8_t* g0base = P::OWN_G0 ? smem + P::OFF_G0 : reinterpret_cast<uint8_t*>(sA1);
+        float* sG0 = reinterpret_cast<float*>(g0base);                                // [s][GPITCH] dL/d(layer-0 output)
+        float4* sRec = reinterpret_cast<float4*>(g0base + P::G0_BYTES);               // [IN][TS]
 #pragma unroll
         for (int q = 0; q < HH / 4; ++q)
           *reinterpret_cast<float4*>(sG0 + s * P::GPITCH + hf * HH + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
