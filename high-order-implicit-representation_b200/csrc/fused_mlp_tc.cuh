@@ -44,8 +44,14 @@ struct TcPlan {
   static constexpr int UNIT = 8, NUNIT = TS / UNIT;                         // GW: samples per smem unit (smem budget)
   // continuous: the layer-0 dL/dw tiles (dL/dy rows + basis records) get their own shared memory, so the owner
   // walk does not have to wait until the helpers are done with a1 / a2; discontinuous (larger W1): they alias a1 / a2
-  static constexpr bool OWN_G0 = S::CONT;
-  static constexpr int GPITCH = 44;                                         // layer-0 dL/dy tile [s][44]
+  static constexpr bool OWN_G0 = S::CONT;   // (basis records only; the dL/dy tile aliases the idle a1 buffer)
+  // continuous: the a1 tile is DOUBLE-BUFFERED (the helpers may stage the Phi1 units of tile n while the sample
+  // warps already work on tile n + 1 -- measured: 3.4 k of 31 k cycles per tile were spent waiting for them), the
+  // layer-0 dL/dy tile of the owner walk aliases the idle a1 buffer, the basis records get 8 KB of their own.
+  // discontinuous (W1 is 10 KB larger): single a1 buffer, both owner-walk tiles alias a1 / a2.
+  static constexpr bool A1_DOUBLE = S::CONT;
+  static constexpr int NA1 = A1_DOUBLE ? 2 : 1;
+  static constexpr int GPITCH = A1_DOUBLE ? 40 : 44;                        // layer-0 dL/dy tile [s][GPITCH]
   // TMEM columns
   static constexpr int D1_COL = 0, FA_COL = 64, G_COL = 64, T_COL = FA_COL + 4 * CH_K, GW_COL = T_COL + TN;
   // shared memory (bytes)
@@ -57,22 +63,23 @@ struct TcPlan {
   static constexpr uint32_t X_BYTES = 2 * TS * 4 * 4;                                   // pair exchange slots
   static constexpr uint32_t OFF_W1R = 0, OFF_W1L = OFF_W1R + W1_BYTES, OFF_GTR = OFF_W1L + W1_BYTES,
                             OFF_GTL = OFF_GTR + GT_BYTES, OFF_U = OFF_GTL + GT_BYTES,   // [2][raw|lo]
-                            OFF_A1 = OFF_U + 4 * U_BYTES, OFF_A2 = OFF_A1 + A_BYTES, OFF_W2 = OFF_A2 + A_BYTES,
+                            OFF_A1 = OFF_U + 4 * U_BYTES, OFF_A2 = OFF_A1 + NA1 * A_BYTES, OFF_W2 = OFF_A2 + A_BYTES,
                             OFF_ACC2 = OFF_W2 + W2_BYTES, OFF_X = OFF_ACC2 + W2_BYTES, OFF_G0 = OFF_X + X_BYTES;
   static constexpr uint32_t G0_BYTES = TS * GPITCH * 4;                                 // [s][GPITCH] dL/d(layer-0 output)
   static constexpr uint32_t REC_BYTES = S::IN * 16 * TS;                                // [IN][TS] basis records
-  static constexpr uint32_t OFF_BAR = OFF_G0 + (OWN_G0 ? G0_BYTES + REC_BYTES : 0), SMEM_BYTES = OFF_BAR + 256;
+  static constexpr uint32_t OFF_BAR = OFF_G0 + (OWN_G0 ? REC_BYTES : 0), SMEM_BYTES = OFF_BAR + 256;
   static_assert(S::N == 3 && S::SEGH == 2 && S::SEGO == 2 && S::NH == 1, "tensor path: C2 / C3 family");
   static_assert(HID == 40 && HH % QI == 0 && HK % 4 == 0 && CH_K % 8 == 0 && KH <= 256, "tensor path shape");
   static_assert(G_COL + 2 * HID <= T_COL && GW_COL + 2 * HID <= 512 && UNIT % 8 == 0 && (UNIT / 2) % 4 == 0, "TMEM / unit plan");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan");
-  static_assert(OWN_G0 || G0_BYTES + REC_BYTES <= 2 * A_BYTES, "layer-0 dL/dw tiles alias A1/A2");
+  static_assert(A1_DOUBLE ? G0_BYTES <= A_BYTES : G0_BYTES + REC_BYTES <= 2 * A_BYTES, "layer-0 dL/dw tiles alias a1 (/ a2)");
+  static_assert(GPITCH % 4 == 0 && GPITCH >= HID, "dL/dy rows are read as float4");
   // K-column of node 0 of hidden-layer input i: chunk c = (i % 20) / 4 holds [half 0: 4 inputs | half 1: 4 inputs]
   __host__ __device__ static constexpr int kbase(int i) { return ((i % HH) / QI) * CH_K + (i / HH) * HK + (i % QI) * ND; }
 };
 
 enum { B_FFULL0 = 0, B_FFULL1, B_FEMPTY0, B_FEMPTY1, B_D1FULL, B_D1EMPTY, B_GFULL, B_TFULL, B_GWDONE,
-       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_A1FULL, B_A1FREE, B_A2FULL, B_A2FREE, B_COUNT };
+       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_A1FULL, B_A1FREE0, B_A1FREE1, B_A2FULL, B_A2FREE, B_COUNT };
 
 // y[O] += sum_j l[j] * W[j * PITCH + 0..O)
 template <int N, int O, int PITCH, bool GLOBAL>
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     mbar_init(&bars[B_GFULL], NSAMPLE_THREADS);  mbar_init(&bars[B_TFULL], 1);   mbar_init(&bars[B_GWDONE], 1);
     mbar_init(&bars[B_UFULL0], NHELPER); mbar_init(&bars[B_UFULL1], NHELPER);
     mbar_init(&bars[B_UEMPTY0], 1);  mbar_init(&bars[B_UEMPTY1], 1);
-    mbar_init(&bars[B_A1FULL], NSAMPLE_THREADS); mbar_init(&bars[B_A1FREE], NHELPER);
+    mbar_init(&bars[B_A1FULL], NSAMPLE_THREADS); mbar_init(&bars[B_A1FREE0], NHELPER); mbar_init(&bars[B_A1FREE1], NHELPER);
     mbar_init(&bars[B_A2FULL], NSAMPLE_THREADS); mbar_init(&bars[B_A2FREE], NHELPER);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
@@ -223,32 +230,88 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     constexpr uint32_t ID_GW = make_idesc(128, HID, 1, 0);         // A: Phi unit MN-major, B: G^T K-major
     const uint64_t dW1[2] = {make_desc(smem_u32(sW1R), P::W1_RS), make_desc(smem_u32(sW1L), P::W1_RS)};
     const uint64_t dGT[2] = {make_desc(smem_u32(sGTR), P::GT_RS), make_desc(smem_u32(sGTL), P::GT_RS)};
-    uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
-      // ---- FWD: D1 = Phi1 * W1, five chunks of 8 inputs
-      if (n_tile > 0) mbar_wait_backoff(&bars[B_D1EMPTY], (n_tile - 1) & 1, 32);
-      for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
-        const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
-        mbar_wait(&bars[B_FFULL0 + buf], ph);
-        fence_after();
-        if (leader) {
+    // The tensor pipe executes in issue order, so the warp issues whichever product has its operands ready:
+    // the dL/dw1 units of tile n - 1 (paced by the helper warps) are interleaved with the forward chunks of
+    // tile n instead of blocking them (measured: 4 k of 31 k cycles per tile were spent waiting on FEMPTY).
+    uint32_t q_chunk = 0, q_unit = 0, n_tile = 0, gw_pending = 0;
+    auto issue_fwd = [&](int c, uint32_t buf) {
+      fence_after();
+      if (leader) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+          for (int j = 0; j < P::CH_K / 8; ++j) {
+            const uint32_t ks = (uint32_t)(c * (P::CH_K / 8) + j);
+            const uint32_t koff = (ks >> 2) * 512u + (ks & 3u) * 32u;
+            mma_ts(tmem + P::D1_COL, tmem + P::FA_COL + buf * 2 * P::CH_K + (pass == 1 ? P::CH_K : 0) + j * 8,
+                   dW1[pass == 2] + (uint64_t)(koff >> 4), ID_FWD, (c | pass | j) != 0);
+          }
+        }
+        umma_commit(&bars[B_FEMPTY0 + buf]);
+        if (c == P::NCH - 1) umma_commit(&bars[B_D1FULL]);
+      }
+      __syncwarp();
+    };
+    // one unit of dL/dw1 (gW1 += Phi1^T * G); q_unit counts units over the whole kernel
+    auto issue_gw = [&]() {
+      const uint32_t buf = q_unit & 1, u = q_unit % P::NUNIT;
+      fence_after();
+      if (leader) {
+        const uint32_t ubase = smem_u32(sU + buf * 2 * P::U_BYTES);
+        const uint64_t dU[2] = {make_desc(ubase, P::U_RS), make_desc(ubase + P::U_BYTES, P::U_RS)};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-            for (int j = 0; j < P::CH_K / 8; ++j) {
-              const uint32_t ks = (uint32_t)(c * (P::CH_K / 8) + j);
+            for (int j = 0; j < P::UNIT / 8; ++j) {
+              const uint32_t ks = u * (P::UNIT / 8) + j;
               const uint32_t koff = (ks >> 2) * 512u + (ks & 3u) * 32u;
-              mma_ts(tmem + P::D1_COL, tmem + P::FA_COL + buf * 2 * P::CH_K + (pass == 1 ? P::CH_K : 0) + j * 8,
-                     dW1[pass == 2] + (uint64_t)(koff >> 4), ID_FWD, (c | pass | j) != 0);
+              mma_ss(tmem + P::GW_COL + half * HID,
+                     dU[pass == 1] + (uint64_t)((j * 2 * P::U_RS + half * 4 * 512) >> 4),
+                     dGT[pass == 2] + (uint64_t)(koff >> 4), ID_GW, (q_unit | pass | j) != 0);
             }
           }
-          umma_commit(&bars[B_FEMPTY0 + buf]);
-          if (c == P::NCH - 1) umma_commit(&bars[B_D1FULL]);
         }
-        __syncwarp();
+        umma_commit(&bars[B_UEMPTY0 + buf]);
+        if (u == P::NUNIT - 1) umma_commit(&bars[B_GWDONE]);
       }
-      // ---- GX: T = G * W1^T
-      mbar_wait_backoff(&bars[B_GFULL], n_tile & 1, 32);
+      __syncwarp();
+      ++q_unit;
+      --gw_pending;
+    };
+    auto gw_ready = [&]() { return gw_pending > 0 && mbar_test(&bars[B_UFULL0 + (q_unit & 1)], (q_unit >> 1) & 1); };
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
+      // ---- FWD: D1 = Phi1 * W1 chunk by chunk (priority), pending dL/dw1 units of the previous tile in between
+      bool d1_free = n_tile == 0;
+      uint32_t spins = 0;
+      for (int c = 0; c < P::NCH;) {
+        if (!d1_free) d1_free = mbar_test(&bars[B_D1EMPTY], (n_tile - 1) & 1);
+        const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
+        if (d1_free && mbar_test(&bars[B_FFULL0 + buf], ph)) {
+          issue_fwd(c, buf);
+          ++c;
+          ++q_chunk;
+          spins = 0;
+        } else if (gw_ready()) {
+          issue_gw();
+          spins = 0;
+        } else {
+          __nanosleep(20);
+          if (++spins > (1u << 26)) __trap();
+        }
+      }
+      // ---- GX: T = G * W1^T.  The sample warps stage G only after GWDONE of the previous tile: keep issuing units.
+      spins = 0;
+      while (!mbar_test(&bars[B_GFULL], n_tile & 1)) {
+        if (gw_ready()) {
+          issue_gw();
+          spins = 0;
+        } else {
+          __nanosleep(20);
+          if (++spins > (1u << 26)) __trap();
+        }
+      }
       fence_after();
       if (leader) {
 #pragma unroll
@@ -262,33 +325,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         umma_commit(&bars[B_TFULL]);
       }
       __syncwarp();
-      // ---- GW: gW1 += Phi1^T * G, eight units of 16 samples
-      for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
-        const uint32_t buf = q_unit & 1, ph = (q_unit >> 1) & 1;
-        mbar_wait_backoff(&bars[B_UFULL0 + buf], ph, 64);
-        fence_after();
-        if (leader) {
-          const uint32_t ubase = smem_u32(sU + buf * 2 * P::U_BYTES);
-          const uint64_t dU[2] = {make_desc(ubase, P::U_RS), make_desc(ubase + P::U_BYTES, P::U_RS)};
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll
-              for (int j = 0; j < P::UNIT / 8; ++j) {
-                const uint32_t ks = (uint32_t)(u * (P::UNIT / 8) + j);
-                const uint32_t koff = (ks >> 2) * 512u + (ks & 3u) * 32u;
-                mma_ss(tmem + P::GW_COL + half * HID,
-                       dU[pass == 1] + (uint64_t)((j * 2 * P::U_RS + half * 4 * 512) >> 4),
-                       dGT[pass == 2] + (uint64_t)(koff >> 4), ID_GW, (n_tile | (uint32_t)u | pass | j) != 0);
-              }
-            }
-          }
-          umma_commit(&bars[B_UEMPTY0 + buf]);
-          if (u == P::NUNIT - 1) umma_commit(&bars[B_GWDONE]);
-        }
-        __syncwarp();
-      }
+      gw_pending += P::NUNIT;      // this tile's dL/dw1 units: issued as they arrive, here and in the next tile's loops
+    }
+    while (gw_pending > 0) {
+      mbar_wait_backoff(&bars[B_UFULL0 + (q_unit & 1)], (q_unit >> 1) & 1, 32);
+      issue_gw();
     }
   } else if (warp > 8) {
     // =========================== helper warps ===============================================
@@ -312,6 +353,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     uint32_t q_unit = 0, n_tile = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
       mbar_wait_backoff(&bars[B_A1FULL], n_tile & 1, 128);
+      const uint32_t a1buf = P::A1_DOUBLE ? (n_tile & 1) : 0;
+      const float* sA1t = sA1 + a1buf * (P::A_BYTES / 4);
       for (int u = 0; u < P::NUNIT; ++u, ++q_unit) {
         if (u == 2) {   // two units are staged ahead; now the hidden activations a2 and dL/dy of this tile are due
           mbar_wait_backoff(&bars[B_A2FULL], n_tile & 1, 64);
@@ -344,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
 #pragma unroll
           for (int t = 0; t < P::UNIT / 2; ++t) {
             const int sl = sh * (P::UNIT / 2) + t;   // (sl & 3) == (t & 3): compile-time swizzle
-            const float x = sA1[(u * P::UNIT + sl) * APITCH + i];
+            const float x = sA1t[(u * P::UNIT + sl) * APITCH + i];
             int id;
             float xi, l[N];
             locate2(x, id, xi);
@@ -363,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         fence_async_smem();
         mbar_arrive(&bars[B_UFULL0 + buf]);
       }
-      mbar_arrive(&bars[B_A1FREE]);                   // done reading this tile's a1 rows
+      mbar_arrive(&bars[B_A1FREE0 + a1buf]);          // done reading this tile's a1 rows
     }
     if (sh < 2) {
 #pragma unroll
@@ -380,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     const float* w0 = p.packed + p.off[0] + hf * HH;
     const LagrangeTable& lag = p.lag;
     const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* a1 = sA1 + s * APITCH;
+    float* a1 = sA1 + s * APITCH;                     // re-pointed per tile when a1 is double-buffered
     float* a2 = sA2 + s * APITCH;
     float* xs = sX + (hf * TS + s) * 4;
     const float* xo = sX + ((hf ^ 1) * TS + s) * 4;
@@ -453,7 +496,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       for (int o = 0; o < OUT; ++o) tg0[o] = tgN[o];
 #pragma unroll
       for (int i = 0; i < IN; ++i) rec0[i] = recN[i];
-      if (n_tile > 0) mbar_wait(&bars[B_A1FREE], (n_tile - 1) & 1);   // helpers are done with the previous a1 tile
+      {   // the a1 buffer of this tile: free once the helpers have staged its previous occupant
+        const uint32_t a1buf = P::A1_DOUBLE ? (n_tile & 1) : 0, use = P::A1_DOUBLE ? (n_tile >> 1) : n_tile;
+        a1 = sA1 + a1buf * (P::A_BYTES / 4) + s * APITCH;
+        if (use > 0) mbar_wait(&bars[B_A1FREE0 + a1buf], (use - 1) & 1);
+      }
 #pragma unroll
       for (int j = 0; j < HH; ++j) a1[hf * HH + j] = hN[j];
       mbar_arrive(&bars[B_A1FULL]);                                   // (release) helpers may stage Phi1 units
@@ -642,15 +689,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         continue;
       }
       // ---- otherwise: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
-      if (!P::OWN_G0) {
-        mbar_wait(&bars[B_A1FREE], n_tile & 1);       // helpers are done with sA1 / sA2 (aliased below)
+      if (P::A1_DOUBLE) {
+        // the dL/dy tile aliases the a1 buffer of tile n + 1: free once the helpers are done with tile n - 1
+        const uint32_t ob = (n_tile + 1) & 1, use = (n_tile + 1) >> 1;
+        if (use > 0) mbar_wait(&bars[B_A1FREE0 + ob], (use - 1) & 1);
+      } else {
+        mbar_wait(&bars[B_A1FREE0], n_tile & 1);      // helpers are done with sA1 / sA2 (aliased below)
         mbar_wait(&bars[B_A2FREE], n_tile & 1);
         bar_samples();                                // everyone is done reading sA1 / sA2
       }
       {
-        uint8_t* g0base = P::OWN_G0 ? smem + P::OFF_G0 : reinterpret_cast<uint8_t*>(sA1);
-        float* sG0 = reinterpret_cast<float*>(g0base);                                // [s][GPITCH] dL/d(layer-0 output)
-        float4* sRec = reinterpret_cast<float4*>(g0base + P::G0_BYTES);               // [IN][TS]
+        float* sG0 = P::A1_DOUBLE ? sA1 + ((n_tile + 1) & 1) * (P::A_BYTES / 4) : sA1;      // [s][GPITCH] dL/d(layer-0 output)
+        float4* sRec = P::OWN_G0 ? reinterpret_cast<float4*>(smem + P::OFF_G0)              // [IN][TS]
+                                 : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sA1) + P::G0_BYTES);
 #pragma unroll
         for (int q = 0; q < HH / 4; ++q)
           *reinterpret_cast<float4*>(sG0 + s * P::GPITCH + hf * HH + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
