@@ -79,7 +79,7 @@ struct TcPlan {
 };
 
 enum { B_FFULL0 = 0, B_FFULL1, B_FEMPTY0, B_FEMPTY1, B_D1FULL, B_D1EMPTY, B_GFULL, B_TFULL, B_GWDONE,
-       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_A1FULL, B_A1FREE0, B_A1FREE1, B_A2FULL, B_A2FREE, B_COUNT };
+       B_UFULL0, B_UFULL1, B_UEMPTY0, B_UEMPTY1, B_A1FULL, B_A1FREE0, B_A1FREE1, B_A2FULL, B_A2FREE, B_OWNDONE, B_COUNT };
 
 // y[O] += sum_j l[j] * W[j * PITCH + 0..O)
 template <int N, int O, int PITCH, bool GLOBAL>
@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     mbar_init(&bars[B_UEMPTY0], 1);  mbar_init(&bars[B_UEMPTY1], 1);
     mbar_init(&bars[B_A1FULL], NSAMPLE_THREADS); mbar_init(&bars[B_A1FREE0], NHELPER); mbar_init(&bars[B_A1FREE1], NHELPER);
     mbar_init(&bars[B_A2FULL], NSAMPLE_THREADS); mbar_init(&bars[B_A2FREE], NHELPER);
+    mbar_init(&bars[B_OWNDONE], NSAMPLE_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   {
@@ -496,15 +497,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       for (int o = 0; o < OUT; ++o) tg0[o] = tgN[o];
 #pragma unroll
       for (int i = 0; i < IN; ++i) rec0[i] = recN[i];
-      {   // the a1 buffer of this tile: free once the helpers have staged its previous occupant
-        const uint32_t a1buf = P::A1_DOUBLE ? (n_tile & 1) : 0, use = P::A1_DOUBLE ? (n_tile >> 1) : n_tile;
-        a1 = sA1 + a1buf * (P::A_BYTES / 4) + s * APITCH;
-        if (use > 0) mbar_wait(&bars[B_A1FREE0 + a1buf], (use - 1) & 1);
-      }
+      // ---- hidden layer forward on the tensor cores: stage this thread's inputs of every chunk (straight from
+      //      the layer-0 registers) into TMEM
 #pragma unroll
-      for (int j = 0; j < HH; ++j) a1[hf * HH + j] = hN[j];
-      mbar_arrive(&bars[B_A1FULL]);                                   // (release) helpers may stage Phi1 units
-      // ---- hidden layer forward on the tensor cores: stage this thread's 4 inputs of every chunk into TMEM
       for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
         const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
         mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);
@@ -512,7 +507,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         float v[P::HK], lo[P::HK];
 #pragma unroll
         for (int m = 0; m < P::QI; ++m) {
-          const float x = a1[hf * HH + c * P::QI + m];
+          const float x = hN[c * P::QI + m];
           int id;
           float xi, l[N];
           locate2(x, id, xi);
@@ -528,6 +523,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         fence_before();
         mbar_arrive(&bars[B_FFULL0 + buf]);
       }
+      // ---- a1 tile for the helpers (dL/dw1 units) and the T epilogue.  Its buffer is free once the helpers have
+      //      staged its previous occupant and every owner of the previous tile's layer-0 walk is done (the walk
+      //      tiles alias the a1 / a2 buffers) -- both long past by now, so neither wait stalls.
+      {
+        const uint32_t a1buf = P::A1_DOUBLE ? (n_tile & 1) : 0, use = P::A1_DOUBLE ? (n_tile >> 1) : n_tile;
+        a1 = sA1 + a1buf * (P::A_BYTES / 4) + s * APITCH;
+        if (use > 0) mbar_wait(&bars[B_A1FREE0 + a1buf], (use - 1) & 1);
+        if (n_tile > 0) mbar_wait(&bars[B_OWNDONE], (n_tile - 1) & 1);
+      }
+#pragma unroll
+      for (int j = 0; j < HH; ++j) a1[hf * HH + j] = hN[j];
+      mbar_arrive(&bars[B_A1FULL]);                                   // (release) helpers may stage Phi1 units
       // ---- D1 epilogue: hidden pre-activation (own 20 columns) -> MaxAbs -> a2
       mbar_wait(&bars[B_D1FULL], n_tile & 1);
       fence_after();
@@ -685,7 +692,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
             }
           }
         }
-        bar_samples();   // all GW staging reads of sA1 are done before the next tile overwrites it
+        mbar_arrive(&bars[B_OWNDONE]);
         continue;
       }
       // ---- otherwise: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
@@ -758,7 +765,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
           }
         }
       }
-      bar_samples();                                  // owners done before the next tile reuses sA1 / sA2
+      mbar_arrive(&bars[B_OWNDONE]);                  // (release) this thread is done with the walk tiles; the next
+                                                      // tile waits for all 256 before it rewrites a1 / a2
     }
     // ---- flush: loss, dL/dw2 (smem), dL/dw1 (TMEM accumulators)
     if (p.gy_ext == nullptr && hf == 0) {
