@@ -502,8 +502,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
 #pragma unroll
       for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
         const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
-        mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);
-        fence_after();
         float v[P::HK], lo[P::HK];
 #pragma unroll
         for (int m = 0; m < P::QI; ++m) {
@@ -516,6 +514,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         }
 #pragma unroll
         for (int j = 0; j < P::HK; ++j) lo[j] = tf32_lo(v[j]);
+        mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);     // (after the arithmetic: the buffer is usually free by now)
+        fence_after();
         const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K + hf * P::HK;
         tmem_stK<P::HK>(col, v);
         tmem_stK<P::HK>(col + P::CH_K, lo);
