@@ -391,6 +391,20 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
     for (int u = 0; u < units; ++u) {
       const uint32_t buf = u & 1, ph = (u >> 1) & 1;
       const long long b0 = b_lo + (long long)u * GW_UNIT;
+      // dL/dy rows of the unit: issued first (16-byte loads when the rows allow it) so that their latency hides
+      // behind the basis evaluation below; element (output o, sample sl) -> G^T smem, sl fastest (conflict-free)
+      const bool gvec = (p.out_f & 3) == 0;
+      constexpr int GV = 4;                                  // float4 per thread: 32 samples x (outp <= 64) / 4 / 128 threads
+      float4 gpre[GV];
+      if (gvec) {
+#pragma unroll
+        for (int r = 0; r < GV; ++r) {
+          const int it = tid + r * GW_WORKERS, sl = it % GW_UNIT, o4 = it / GW_UNIT;
+          const long long b = b0 + sl;
+          gpre[r] = (b < b_hi && 4 * o4 < p.out_f) ? __ldg(reinterpret_cast<const float4*>(p.gy + b * p.out_f) + o4)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       mbar_wait(&bars[GB_UEMPTY0 + buf], ph ^ 1);
       uint8_t* ur = sU + buf * 2 * GW_U_BYTES;
       uint8_t* ul = ur + GW_U_BYTES;
@@ -434,16 +448,31 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
           *reinterpret_cast<float*>(ul + off) = 0.f;
         }
       }
-      // G^T unit: element (output o, sample sl); sl fastest (conflict-free smem writes)
       uint8_t* gr = sG + buf * 2 * 8192;
       uint8_t* gl = gr + g_bytes;
-      for (int it = tid; it < p.outp * GW_UNIT; it += GW_WORKERS) {
-        const int sl = it % GW_UNIT, o = it / GW_UNIT;
-        const long long b = b0 + sl;
-        const float v = (b < b_hi && o < p.out_f) ? __ldg(p.gy + b * p.out_f + o) * p.rescale : 0.f;
-        const uint32_t off = chunk_off((uint32_t)o, (uint32_t)sl);
-        *reinterpret_cast<float*>(gr + off) = v;
-        *reinterpret_cast<float*>(gl + off) = tf32_lo(v);
+      if (gvec) {
+#pragma unroll
+        for (int r = 0; r < GV; ++r) {
+          const int it = tid + r * GW_WORKERS, sl = it % GW_UNIT, o4 = it / GW_UNIT;
+          if (4 * o4 < p.outp) {
+            const float v4[4] = {gpre[r].x * p.rescale, gpre[r].y * p.rescale, gpre[r].z * p.rescale, gpre[r].w * p.rescale};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t off = chunk_off((uint32_t)(4 * o4 + c), (uint32_t)sl);
+              *reinterpret_cast<float*>(gr + off) = v4[c];
+              *reinterpret_cast<float*>(gl + off) = tf32_lo(v4[c]);
+            }
+          }
+        }
+      } else {
+        for (int it = tid; it < p.outp * GW_UNIT; it += GW_WORKERS) {
+          const int sl = it % GW_UNIT, o = it / GW_UNIT;
+          const long long b = b0 + sl;
+          const float v = (b < b_hi && o < p.out_f) ? __ldg(p.gy + b * p.out_f + o) * p.rescale : 0.f;
+          const uint32_t off = chunk_off((uint32_t)o, (uint32_t)sl);
+          *reinterpret_cast<float*>(gr + off) = v;
+          *reinterpret_cast<float*>(gl + off) = tf32_lo(v);
+        }
       }
       fence_async_smem();
       mbar_arrive(&bars[GB_UFULL0 + buf]);
