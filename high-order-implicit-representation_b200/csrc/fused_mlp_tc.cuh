@@ -48,8 +48,8 @@ struct TcPlan {
   // continuous: the a1 tile is DOUBLE-BUFFERED (the helpers may stage the Phi1 units of tile n while the sample
   // warps already work on tile n + 1 -- measured: 3.4 k of 31 k cycles per tile were spent waiting for them), the
   // layer-0 dL/dy tile of the owner walk aliases the idle a1 buffer, the basis records get 8 KB of their own.
-  // discontinuous (W1 is 10 KB larger): single a1 buffer, both owner-walk tiles alias a1 / a2.
-  static constexpr bool A1_DOUBLE = S::CONT;
+  // discontinuous (W1 is 10 KB larger): same, but the basis records alias the a2 tile (dead by then).
+  static constexpr bool A1_DOUBLE = true;
   static constexpr int NA1 = A1_DOUBLE ? 2 : 1;
   static constexpr int GPITCH = A1_DOUBLE ? 40 : 44;                        // layer-0 dL/dy tile [s][GPITCH]
   // TMEM columns
@@ -72,7 +72,7 @@ struct TcPlan {
   static_assert(HID == 40 && HH % QI == 0 && HK % 4 == 0 && CH_K % 8 == 0 && KH <= 256, "tensor path shape");
   static_assert(G_COL + 2 * HID <= T_COL && GW_COL + 2 * HID <= 512 && UNIT % 8 == 0 && (UNIT / 2) % 4 == 0, "TMEM / unit plan");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan");
-  static_assert(A1_DOUBLE ? G0_BYTES <= A_BYTES : G0_BYTES + REC_BYTES <= 2 * A_BYTES, "layer-0 dL/dw tiles alias a1 (/ a2)");
+  static_assert(G0_BYTES <= A_BYTES && REC_BYTES <= A_BYTES, "layer-0 dL/dw tiles alias the idle a1 buffer / a2");
   static_assert(GPITCH % 4 == 0 && GPITCH >= HID, "dL/dy rows are read as float4");
   // K-column of node 0 of hidden-layer input i: chunk c = (i % 20) / 4 holds [half 0: 4 inputs | half 1: 4 inputs]
   __host__ __device__ static constexpr int kbase(int i) { return ((i % HH) / QI) * CH_K + (i / HH) * HK + (i % QI) * ND; }
@@ -696,19 +696,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         continue;
       }
       // ---- otherwise: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
-      if (P::A1_DOUBLE) {
+      {
         // the dL/dy tile aliases the a1 buffer of tile n + 1: free once the helpers are done with tile n - 1
         const uint32_t ob = (n_tile + 1) & 1, use = (n_tile + 1) >> 1;
         if (use > 0) mbar_wait(&bars[B_A1FREE0 + ob], (use - 1) & 1);
-      } else {
-        mbar_wait(&bars[B_A1FREE0], n_tile & 1);      // helpers are done with sA1 / sA2 (aliased below)
-        mbar_wait(&bars[B_A2FREE], n_tile & 1);
-        bar_samples();                                // everyone is done reading sA1 / sA2
+        // without room for their own 8 KB the basis records alias the a2 tile: the helpers are done with it
+        // (A2FREE) and every sample thread is past its last a2 read (all 256 arrived on GFULL before T existed)
+        if (!P::OWN_G0) mbar_wait(&bars[B_A2FREE], n_tile & 1);
       }
       {
-        float* sG0 = P::A1_DOUBLE ? sA1 + ((n_tile + 1) & 1) * (P::A_BYTES / 4) : sA1;      // [s][GPITCH] dL/d(layer-0 output)
-        float4* sRec = P::OWN_G0 ? reinterpret_cast<float4*>(smem + P::OFF_G0)              // [IN][TS]
-                                 : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sA1) + P::G0_BYTES);
+        float* sG0 = sA1 + ((n_tile + 1) & 1) * (P::A_BYTES / 4);                          // [s][GPITCH] dL/d(layer-0 output)
+        float4* sRec = P::OWN_G0 ? reinterpret_cast<float4*>(smem + P::OFF_G0) : reinterpret_cast<float4*>(sA2);   // [IN][TS]
 #pragma unroll
         for (int q = 0; q < HH / 4; ++q)
           *reinterpret_cast<float4*>(sG0 + s * P::GPITCH + hf * HH + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
