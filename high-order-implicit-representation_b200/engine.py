@@ -192,6 +192,38 @@ class FusedTrainer:
                               global_batch)
 
     # ------------------------------------------------------------------------------------------
+    def optimizer_state_dict(self) -> dict:
+        """The optimizer state in ``torch.optim.Optimizer.state_dict()`` layout (one entry per ``w`` tensor, in
+        layer order), as a Lightning checkpoint stores it under ``optimizer_states[0]``."""
+        state, off = {}, 0
+        for k, l in enumerate(self.layers):
+            n = l.w.numel()
+            st = {"step": torch.tensor(float(self.step_count)),
+                  "exp_avg": self.exp_avg[off:off + n].view_as(l.w).detach().cpu().clone()}
+            if self.exp_avg_sq is not None:
+                st["exp_avg_sq"] = self.exp_avg_sq[off:off + n].view_as(l.w).detach().cpu().clone()
+            state[k] = st
+            off += n
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "params": list(range(len(self.layers)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        off = 0
+        with torch.no_grad():
+            for k, l in enumerate(self.layers):
+                n = l.w.numel()
+                st = sd["state"].get(k, sd["state"].get(str(k)))
+                if st is not None:
+                    self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    if self.exp_avg_sq is not None and "exp_avg_sq" in st:
+                        self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    self.step_count = int(float(st["step"]))
+                off += n
+        g = sd["param_groups"][0]
+        self.lr = float(g["lr"])
+
+    # ------------------------------------------------------------------------------------------
     def forward(self, x: Tensor) -> Tensor:
         x2 = x.reshape(x.shape[0], -1).contiguous()
         y = torch.empty((x2.shape[0], self.out_features), device=self.device, dtype=torch.float32)

@@ -153,7 +153,8 @@ class ImageTrainer:
     def fit(self, max_epochs: Optional[int] = None,
             on_epoch_end: Optional[Callable[["ImageTrainer", int, float], None]] = None) -> List[float]:
         epochs = int(max_epochs if max_epochs is not None else self.cfg.max_epochs)
-        for epoch in range(epochs):
+        first = int(self.net.current_epoch)                  # > 0 after load_checkpoint: epochs keep counting
+        for epoch in range(first, first + epochs):
             loss = self.train_epoch()
             self.history.append(loss)
             self.net.current_epoch = epoch + 1
@@ -177,4 +178,30 @@ class ImageTrainer:
         return 10.0 * math.log10(1.0 / max(mse, 1e-12))
 
     def save_checkpoint(self, path: str) -> None:
-        self.net.save_checkpoint(path)
+        """Lightning-format checkpoint: ``state_dict`` + ``hyper_parameters`` (what ``Net.load_from_checkpoint``
+        reads) plus ``optimizer_states`` / ``lr_schedulers`` / ``epoch`` / ``global_step`` so a run can resume."""
+        ckpt = self.net.checkpoint_dict()
+        if self.fused is not None:
+            ckpt["optimizer_states"] = [self.fused.optimizer_state_dict()]
+        else:
+            ckpt["optimizer_states"] = [self.optimizer.state_dict()]
+        ckpt["lr_schedulers"] = [dict(kind=self.schedule.kind, lr=self.schedule.lr, best=self.schedule.best,
+                                      num_bad_epochs=self.schedule.bad)]
+        ckpt["train_loss_history"] = list(self.history)
+        torch.save(ckpt, path)
+
+    def load_checkpoint(self, path: str) -> None:
+        """Resume: weights, optimizer moments and step, lr schedule, epoch counters."""
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        self.net.load_state_dict(ckpt["state_dict"])      # in-place into the flat parameter vector
+        self.net.current_epoch = ckpt.get("epoch", 0)
+        self.net.global_step = ckpt.get("global_step", 0)
+        if ckpt.get("optimizer_states"):
+            if self.fused is not None:
+                self.fused.load_optimizer_state_dict(ckpt["optimizer_states"][0])
+            else:
+                self.optimizer.load_state_dict(ckpt["optimizer_states"][0])
+        for sch in ckpt.get("lr_schedulers", [])[:1]:
+            self.schedule.lr, self.schedule.best, self.schedule.bad = sch["lr"], sch["best"], sch["num_bad_epochs"]
+            self._set_lr(self.schedule.lr)
+        self.history = list(ckpt.get("train_loss_history", []))

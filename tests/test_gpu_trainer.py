@@ -68,3 +68,28 @@ def test_plateau_schedule_matches_torch():
     for m in [1.0, 0.9, 0.95, 0.96, 0.97, 0.98, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]:
         ref.step(m)
         assert abs(mine.step(m) - ref_opt.param_groups[0]["lr"]) < 1e-12
+
+
+def test_resume_from_checkpoint_continues_the_same_trajectory(tmp_path):
+    """Train 2 + 2 epochs with a save / load in between == train 4 epochs straight (same shuffles, same Adam moments,
+    same bias-correction step): the checkpoint carries weights, optimizer state, lr schedule and counters."""
+    cfg = _cfg(max_epochs=4)
+    a = H.ImageTrainer(cfg, _card(64, 64), sampling="tiles", seed=3)
+    b = H.ImageTrainer(cfg, _card(64, 64), sampling="tiles", seed=3)
+    b.net.load_state_dict(a.net.state_dict())
+    hist_a = a.fit(4)
+    b.fit(2)
+    path = os.path.join(tmp_path, "mid.ckpt")
+    b.save_checkpoint(path)
+    c = H.ImageTrainer(cfg, _card(64, 64), sampling="tiles", seed=3)
+    c.load_checkpoint(path)
+    c.gen.set_state(b.gen.get_state())                     # the data order is the caller's business
+    assert c.fused.step_count == b.fused.step_count and c.net.current_epoch == 2
+    hist_c = c.fit(2)
+    assert c.net.current_epoch == 4
+    # fp32 atomics make runs differ in the last bits; Adam keeps them close over a few epochs
+    for x, y in zip(hist_a[2:], hist_c[2:]):
+        assert abs(x - y) <= 2e-3 * abs(x)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck["optimizer_states"][0]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert ck["optimizer_states"][0]["state"][0]["exp_avg"].shape == a.net.model.model[0].w.shape
