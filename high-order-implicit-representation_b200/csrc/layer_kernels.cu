@@ -5,6 +5,7 @@
 // TB samples: phase 1 evaluates, once per (sample, input), the node window and the n basis
 // values (+ derivatives in backward) into shared memory; phase 2 contracts them with the
 // gathered weights w[out][in][window].  Algorithm: SURVEY.md A.3-A.5 / oracle/hol_oracle.py.
+#include <stdint.h>
 #include "hoir_common.cuh"
 
 // dense_tc.cu: tensor-core path for layers whose densified basis expansion is a dense contraction
@@ -482,11 +483,90 @@ extern "C" int hoir_segment_index(const hoir_layer_desc* d, long long B, const f
   return HOIR_OK;
 }
 
+// Thread-per-row variant for the common widths (40, 50, 64, ...): the row lives in registers (vector loads of V
+// floats, every byte of every sector used), no shuffles; same arithmetic and tie rule as maxabs_kernel.
+template <int V> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <int V> __device__ __forceinline__ void vec_unpack(const typename VecT<V>::type& t, float* v);
+template <> __device__ __forceinline__ void vec_unpack<4>(const float4& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+template <> __device__ __forceinline__ void vec_unpack<2>(const float2& t, float* v) { v[0] = t.x; v[1] = t.y; }
+template <int V> __device__ __forceinline__ typename VecT<V>::type vec_pack(const float* v);
+template <> __device__ __forceinline__ float4 vec_pack<4>(const float* v) { return make_float4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ float2 vec_pack<2>(const float* v) { return make_float2(v[0], v[1]); }
+
+template <int W, int V>
+__global__ void __launch_bounds__(128)
+maxabs_row_kernel(long long B, float eps, const float* __restrict__ x, const float* __restrict__ gy,
+                  float* __restrict__ out) {
+  using vec = typename VecT<V>::type;
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float v[W];
+  const vec* xr = reinterpret_cast<const vec*>(x + b * W);
+#pragma unroll
+  for (int q = 0; q < W / V; ++q) vec_unpack<V>(__ldg(xr + q), v + V * q);
+  float m = -1.f;
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const float a = fabsf(v[i]);
+    if (a > m || (a != a && m == m)) { m = a; k = i; }
+  }
+  const float d = __fadd_rn(m, eps);
+  vec* orow = reinterpret_cast<vec*>(out + b * W);
+  if (gy == nullptr) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = __fdiv_rn(v[i], d);
+#pragma unroll
+    for (int q = 0; q < W / V; ++q) orow[q] = vec_pack<V>(v + V * q);
+  } else {
+    float g[W];
+    const vec* gr = reinterpret_cast<const vec*>(gy + b * W);
+#pragma unroll
+    for (int q = 0; q < W / V; ++q) vec_unpack<V>(__ldg(gr + q), g + V * q);
+    float dot = 0.f, xk = 0.f;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      dot = fmaf(g[i], __fdiv_rn(v[i], d), dot);
+      xk = (i == k) ? v[i] : xk;
+    }
+    const float sgn = xk > 0.f ? 1.f : (xk < 0.f ? -1.f : 0.f);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      float gi = g[i];
+      if (i == k) gi -= sgn * dot;
+      g[i] = __fdiv_rn(gi, d);
+    }
+#pragma unroll
+    for (int q = 0; q < W / V; ++q) orow[q] = vec_pack<V>(g + V * q);
+  }
+}
+
+template <int W, int V>
+static bool maxabs_row_launch(long long B, int width, float eps, const float* x, const float* gy, float* out,
+                              cudaStream_t stream) {
+  if (width != W) return false;
+  maxabs_row_kernel<W, V><<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(B, eps, x, gy, out);
+  return true;
+}
+
 static int maxabs_launch(long long B, int width, float eps, const float* x, const float* gy,
                          float* out, void* stream, const char* where) {
   if (B < 0 || width < 1) return hoir_set_error(HOIR_EINVAL, "bad shape", where);
   if (B == 0) return HOIR_OK;
   if (!x || !out) return hoir_set_error(HOIR_EINVAL, "null device pointer", where);
+  // the hidden widths of the reference configs (40, 50, 10) and a few round ones; rows must be vector-aligned
+  const uintptr_t ptrs = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | (gy ? reinterpret_cast<uintptr_t>(gy) : 0);
+  if (B >= 1024 && (ptrs & 15) == 0) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (maxabs_row_launch<40, 4>(B, width, eps, x, gy, out, st) || maxabs_row_launch<50, 2>(B, width, eps, x, gy, out, st) ||
+        maxabs_row_launch<64, 4>(B, width, eps, x, gy, out, st) || maxabs_row_launch<32, 4>(B, width, eps, x, gy, out, st) ||
+        maxabs_row_launch<20, 4>(B, width, eps, x, gy, out, st) || maxabs_row_launch<10, 2>(B, width, eps, x, gy, out, st)) {
+      HOIR_CHECK_CUDA(cudaGetLastError());
+      return HOIR_OK;
+    }
+  }
   int grid = (int)min((B + 7) / 8, (long long)num_sms() * 128);   // one row per warp: latency-bound, so many warps
   maxabs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, width, eps, x, gy, out);
   HOIR_CHECK_CUDA(cudaGetLastError());

@@ -106,7 +106,8 @@ def test_empty_batch():
     assert norm(torch.empty(0, 40, device="cuda")).shape == (0, 40)
 
 
-@pytest.mark.parametrize("B,width", [(1, 40), (1000, 40), (33, 10), (64, 50), (5, 3)])
+@pytest.mark.parametrize("B,width", [(1, 40), (1000, 40), (33, 10), (64, 50), (5, 3), (4099, 40), (2048, 50), (1500, 64),
+                                     (1024, 10), (3000, 27)])
 def test_maxabs_parity(B, width):
     g = torch.Generator().manual_seed(B + width)
     x = torch.randn(B, width, generator=g)
