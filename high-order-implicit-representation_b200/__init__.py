@@ -3,7 +3,7 @@ jloveric/high-order-implicit-representation.  Importable as ``hoir_b200`` (see t
 ``hoir_b200.py`` at the repository root; the directory name carries hyphens)."""
 from . import _lib, config, datasets, parallel, spec  # noqa: F401
 from ._lib import HoirUnsupported, build  # noqa: F401
-from .config import Config, apply_overrides, images_config, to_cfg  # noqa: F401
+from .config import Config, apply_overrides, images_config, neighborhood_config, to_cfg  # noqa: F401
 from .datasets import image_neighborhood_dataset, image_to_dataset, neighborhood_gather  # noqa: F401
 from .engine import FusedTrainer, HostBatchStepper  # noqa: F401
 from .rendering import generate_sequence, neighborhood_sample_generator, render_image  # noqa: F401
@@ -13,7 +13,7 @@ from .layers import (FourierSeries, HighOrderLayer, MaxAbsNormalization,  # noqa
 from .networks import (Adam, HighOrderMLP, Net, initialize_network_polynomial_layers,  # noqa: F401
                        node_positions)
 from .sparse_optimizers import SparseLion  # noqa: F401
-from .trainer import ImageTrainer  # noqa: F401
+from .trainer import ImageTrainer, NeighborhoodTrainer  # noqa: F401
 from .utils import positions_from_mesh  # noqa: F401
 
 __version__ = "0.1.0"

@@ -100,3 +100,22 @@ def images_config(**overrides) -> Config:
     for k, v in overrides.items():
         cfg[k] = v
     return cfg
+
+
+def neighborhood_config(**overrides) -> Config:
+    """Defaults of /root/reference/config/neighborhood_config.yaml + optimizer/adam.yaml (keys that reach the
+    hot path); ``mlp.input.width`` / ``mlp.output.width`` are derived from ``data.width`` / ``data.outside`` by the
+    caller, as examples/implicit_neighborhood.py:36-41 does."""
+    cfg = Config({
+        "images": ["images/newt.jpg", "images/jupiter.jpg", "images/mountains.jpg"],
+        "mlp": dict(layer_type="continuous", n=3, n_in=None, n_out=None, n_hidden=None,
+                    periodicity=2.0, rescale_output=False, scale=2.0,
+                    input=dict(segments=1, width=None), output=dict(segments=1, width=None),
+                    hidden=dict(segments=2, layers=1, width=10)),
+        "data": dict(width=3, outside=3),      # ("data" is also the name of Config's positional argument)
+        "max_epochs": 50, "gpus": 1, "accelerator": "cuda", "lr": 1e-3, "batch_size": 256, "train": True,
+        "checkpoint": None,
+        "optimizer": dict(name="adam", lr=1e-4, scheduler="plateau", patience=5, factor=0.1, gamma=0.9)})
+    for k, v in overrides.items():
+        cfg[k] = v
+    return cfg

@@ -205,3 +205,96 @@ class ImageTrainer:
             self.schedule.lr, self.schedule.best, self.schedule.bad = sch["lr"], sch["best"], sch["num_bad_epochs"]
             self._set_lr(self.schedule.lr)
         self.history = list(ckpt.get("train_loss_history", []))
+
+
+class NeighborhoodTrainer:
+    """``examples/implicit_neighborhood.py`` without Lightning: fit ``Net(cfg)`` to predict the inner
+    ``width x width`` block of every patch of one or more images from its donut of ``outside`` pixels
+    (ImageNeighborhoodDataModule, /root/reference/high_order_implicit_representation/
+    single_image_dataset.py:336-389; config/neighborhood_config.yaml), then iterate the trained interpolator
+    (generate_sequence, rendering.py:98-126).  Patches are never materialised as a dataset: every step gathers its
+    batch of patches from the image resident in HBM (``hoir_neighborhood_gather`` with a first patch / count)."""
+
+    def __init__(self, cfg, images, device: str = "cuda", seed: int = 0):
+        self.cfg = to_cfg(cfg)
+        self.device = torch.device(device)
+        self.width, self.outside = int(self.cfg.data.width), int(self.cfg.data.outside)
+        total = self.width + 2 * self.outside
+        self.cfg.mlp.input.width = (total * total - self.width * self.width) * 3
+        self.cfg.mlp.output.width = 3 * self.width * self.width
+        self.batch_size = int(self.cfg.batch_size)
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        self.images = []
+        for im in images:                                   # [3, H, W] in [-1, 1] (ToTensor() * 2 - 1)
+            if isinstance(im, str):
+                im = _load_image_u8(im).permute(2, 0, 1).float() / 255.0 * 2 - 1
+            self.images.append(im.to(self.device).contiguous().float())
+        self.net = Net(self.cfg).to(self.device)
+        conf = self.net.configure_optimizers()
+        self.optimizer = conf[0][0] if isinstance(conf, tuple) else conf
+        self.schedule = _LrSchedule(self.cfg.optimizer, float(self.cfg.optimizer.lr))
+        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.history: List[float] = []
+
+    def _patch_batches(self):
+        """(image index, first patch, count) blocks of at most batch_size consecutive patches, shuffled."""
+        from .datasets import neighborhood_patches
+        blocks = []
+        for k, im in enumerate(self.images):
+            nr, nc = neighborhood_patches(im.shape[1], im.shape[2], self.width, self.outside, 1)
+            total = nr * nc
+            blocks += [(k, f, min(self.batch_size, total - f)) for f in range(0, total, self.batch_size)]
+        order = torch.randperm(len(blocks), device=self.device, generator=self.gen).tolist()
+        return [blocks[j] for j in order]
+
+    def train_epoch(self) -> float:
+        lib = _lib.lib()
+        in_w, out_w = int(self.cfg.mlp.input.width), int(self.cfg.mlp.output.width)
+        feat = torch.empty((self.batch_size, in_w), device=self.device)
+        targ = torch.empty((self.batch_size, out_w), device=self.device)
+        total = torch.zeros(1, device=self.device)
+        steps = 0
+        for k, first, count in self._patch_batches():
+            im = self.images[k]
+            with torch.cuda.device(self.device):
+                _lib.check(lib.hoir_neighborhood_gather(_lib.dptr(im), 3, im.shape[1], im.shape[2], self.width,
+                                                        self.outside, 1, 0, first, count, _lib.dptr(feat),
+                                                        _lib.dptr(targ), _lib.stream_ptr(self.device)))
+            self.optimizer.zero_grad(set_to_none=True)
+            loss = self.net.training_step((feat[:count], targ[:count]), steps)
+            loss.backward()
+            self.optimizer.step()
+            total += loss.detach()
+            steps += 1
+        self.net.global_step += steps
+        return float(total.item()) / max(steps, 1)
+
+    def fit(self, max_epochs: Optional[int] = None) -> List[float]:
+        epochs = int(max_epochs if max_epochs is not None else self.cfg.max_epochs)
+        first = int(self.net.current_epoch)
+        for epoch in range(first, first + epochs):
+            loss = self.train_epoch()
+            self.history.append(loss)
+            self.net.current_epoch = epoch + 1
+            self.net.log("train_loss", loss)
+            lr = self.schedule.step(loss)
+            for g in self.optimizer.param_groups:
+                g["lr"] = lr
+            logger.info("epoch %d train_loss %.6f lr %.3g", epoch, loss, lr)
+        return self.history
+
+    def generate(self, image: Optional[Tensor] = None, frames: int = 25, skip: int = 5, alpha: float = 0.75,
+                 size=(180, 180)) -> Tensor:
+        """NeighborGenerator / the evaluation branch of the example: iterate the interpolator from an image or
+        from noise; returns the kept frames ``[k, 3, H, W]`` in [0, 1] on the host."""
+        from .rendering import generate_sequence
+        if image is None:
+            image = torch.rand(3, size[0], size[1], device=self.device, generator=self.gen) * 2 - 1
+        return generate_sequence(self.net, image.to(self.device), frames=frames, width=self.width,
+                                 outside=self.outside, batch_size=max(self.batch_size, 1 << 16), skip=skip, alpha=alpha)
+
+    def save_checkpoint(self, path: str) -> None:
+        ckpt = self.net.checkpoint_dict()
+        ckpt["optimizer_states"] = [self.optimizer.state_dict()]
+        torch.save(ckpt, path)

@@ -93,3 +93,23 @@ def test_resume_from_checkpoint_continues_the_same_trajectory(tmp_path):
     ck = torch.load(path, weights_only=False)
     assert set(ck["optimizer_states"][0]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
     assert ck["optimizer_states"][0]["state"][0]["exp_avg"].shape == a.net.model.model[0].w.shape
+
+
+def test_neighborhood_trainer_fits_and_generates():
+    """examples/implicit_neighborhood.py flow: patches gathered per step from the resident image, per-layer kernels
+    under autograd, then the iterated interpolator."""
+    cfg = H.neighborhood_config(batch_size=4096, max_epochs=3)
+    cfg.mlp.periodicity = None
+    cfg.mlp.n = 2
+    cfg.mlp.input.segments = 10
+    cfg.mlp.hidden.width = 20
+    u = torch.linspace(0, 1, 96).view(1, 1, 96)
+    v = torch.linspace(0, 1, 80).view(1, 80, 1)
+    img = torch.sin(9 * u + torch.tensor([0.0, 1.0, 2.0]).view(3, 1, 1)) * torch.cos(7 * v) * 0.8
+    torch.manual_seed(0)
+    tr = H.NeighborhoodTrainer(cfg, [img])
+    assert cfg.mlp.input.width == 216 and cfg.mlp.output.width == 27
+    hist = tr.fit()
+    assert len(hist) == 3 and hist[-1] < hist[0]
+    seq = tr.generate(image=img, frames=4, skip=2)
+    assert seq.shape == (3, 3, 80, 96) and torch.isfinite(seq).all()
