@@ -749,27 +749,41 @@ struct FusedEntry {
   size_t smem_tc;
   void (*fwd_tc)(const FusedParams);     // tensor-core forward kernel (2 CTAs per SM), or nullptr
   size_t smem_fwd_tc;
+  void (*train_tc4)(const FusedParams);  // tensor-core training kernel with four threads per sample, or nullptr
+  size_t smem_tc4;
+  int threads_tc, threads_tc4;
 };
 
 template <class S>
 constexpr FusedEntry make_entry() {
   return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
                     fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
-                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4, nullptr, 0, nullptr, 0};
+                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0};
 }
 template <class S>
 constexpr FusedEntry make_entry_tc() {
   return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
                     fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
                     (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4,
-                    tc::fused_mlp_tc_kernel<S>, (size_t)tc::TcPlan<S>::SMEM_BYTES,
-                    tc::fused_mlp_tc_fwd_kernel<S>, (size_t)tc::TcFwdPlan<S>::SMEM_BYTES};
+                    tc::fused_mlp_tc_kernel<S, 2>, (size_t)tc::TcPlan<S, 2>::SMEM_BYTES,
+                    tc::fused_mlp_tc_fwd_kernel<S>, (size_t)tc::TcFwdPlan<S>::SMEM_BYTES,
+                    nullptr, 0, tc::TcPlan<S, 2>::NT, 0};
+}
+template <class S>
+constexpr FusedEntry make_entry_tc4() {   // continuous: also the four-threads-per-sample variant
+  return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
+                    fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
+                    (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4,
+                    tc::fused_mlp_tc_kernel<S, 2>, (size_t)tc::TcPlan<S, 2>::SMEM_BYTES,
+                    tc::fused_mlp_tc_fwd_kernel<S>, (size_t)tc::TcFwdPlan<S>::SMEM_BYTES,
+                    tc::fused_mlp_tc_kernel<S, 4>, (size_t)tc::TcPlan<S, 4>::SMEM_BYTES,
+                    tc::TcPlan<S, 2>::NT, tc::TcPlan<S, 4>::NT};
 }
 
 // Instantiations: BASELINE.json configs C2/C3 (40-wide, 1 hidden layer, rotations 1 and 2) and
 // C1 (10-wide, 2 hidden layers), continuous and discontinuous, n = 3; plus n = 2 variants.
 const FusedEntry kEntries[] = {
-    make_entry_tc<Shape<HOIR_CONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
+    make_entry_tc4<Shape<HOIR_CONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
     make_entry_tc<Shape<HOIR_DISCONTINUOUS, 3, 4, 40, 3, 1, 2, 2>>(),
     make_entry_tc<Shape<HOIR_DISCONTINUOUS, 3, 2, 40, 3, 1, 2, 2>>(),
     make_entry_tc<Shape<HOIR_CONTINUOUS, 3, 2, 40, 3, 1, 2, 2>>(),
@@ -1048,9 +1062,11 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
     if (int err = hoir_get_workspace(2, 64, &ws)) return err;
     p.tail.sync = static_cast<unsigned int*>(ws);
   }
-  auto kern = use_tc ? e->train_tc : e->train;
-  const size_t smem = use_tc ? e->smem_tc : e->smem_train;
-  const int block = use_tc ? tc::NTHREADS : BT, ts = use_tc ? tc::TS : BT;
+  static const bool quad = getenv("HOIR_TC_QUAD") != nullptr;   // A/B: four threads per sample
+  const bool use_q = use_tc && quad && e->train_tc4 != nullptr;
+  auto kern = use_q ? e->train_tc4 : (use_tc ? e->train_tc : e->train);
+  const size_t smem = use_q ? e->smem_tc4 : (use_tc ? e->smem_tc : e->smem_train);
+  const int block = use_q ? e->threads_tc4 : (use_tc ? e->threads_tc : BT), ts = use_tc ? tc::TS : BT;
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (B + ts - 1) / ts;
   const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());

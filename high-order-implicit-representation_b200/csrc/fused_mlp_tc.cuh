@@ -23,22 +23,26 @@
 namespace tc {
 
 constexpr int TS = 128;          // samples per tile
-constexpr int NSAMPLE_THREADS = 256;   // 8 sample warps: 2 threads per sample
+constexpr int NSAMPLE_THREADS = 256;   // forward kernel: 8 sample warps, 2 threads per sample
 constexpr int NHELPER = 96;            // 3 helper warps: stage the Phi1 units of the dL/dw1 product
 constexpr int NTHREADS = 384;          // 8 sample warps + 1 MMA warp + 3 helper warps (168 regs x 384 = 63 K)
 constexpr int NTHREADS_FWD = 288;      // forward-only kernel: 8 sample warps + 1 MMA warp
 constexpr int APITCH = 41;       // row pitch (floats) of the saved-activation tiles
 
 // Shape constants of the tensor path (continuous n = 3, 2 hidden/output segments, width 40)
-template <class S>
+// NQ = threads per sample (2: pairs, 4: quads -- twice the sample warps per SM for the latency-bound CUDA-core
+// part; continuous only, the discontinuous chunks would not fit the TMEM plan).
+template <class S, int NQ_ = 2>
 struct TcPlan {
+  static constexpr int NQ = NQ_;
+  static constexpr int NSAMPLE = NQ * TS, NT = NSAMPLE + 32 + NHELPER, MMAW = NSAMPLE / 32;   // threads; MMA warp index
   static constexpr int HID = S::HID, ND = S::NODES_H, KH = HID * ND;       // 40, 5, 200
-  static constexpr int HH = HID / 2;                                       // hidden units owned by one thread of a pair
+  static constexpr int HH = HID / NQ;                                      // hidden units owned by one thread of a group
   // FWD chunk: QI inputs of each half.  continuous (5 slots per input): 4 inputs, 40 K-columns per chunk;
   // discontinuous (6 slots): 2 inputs, 24 K-columns per chunk -- keeps the double-buffered A staging plus the
   // 240-column T accumulator inside the 512 TMEM columns
-  static constexpr int QI = S::CONT ? 4 : 2, CH_IN = 2 * QI, NCH = HH / QI;
-  static constexpr int HK = QI * ND, CH_K = 2 * HK;                        // K-columns per half / per chunk
+  static constexpr int QI = (S::CONT ? 8 : 4) / NQ, CH_IN = NQ * QI, NCH = HH / QI;
+  static constexpr int HK = QI * ND, CH_K = NQ * HK;                       // K-columns per thread / per chunk
   static constexpr int KP = (KH + 31) / 32 * 32;                            // 224: W1 columns padded to atoms
   static constexpr int TN = (KH + 15) / 16 * 16;                            // 208: N of the GX product
   static constexpr int UNIT = 8, NUNIT = TS / UNIT;                         // GW: samples per smem unit (smem budget)
@@ -60,7 +64,7 @@ struct TcPlan {
   static constexpr uint32_t U_RS = 256 / 32 * 512, U_BYTES = UNIT / 4 * U_RS;           // 4096, 16384
   static constexpr uint32_t A_BYTES = TS * APITCH * 4;                                  // 20992
   static constexpr uint32_t W2_BYTES = S::WO * 4;
-  static constexpr uint32_t X_BYTES = 2 * TS * 4 * 4;                                   // pair exchange slots
+  static constexpr uint32_t X_BYTES = NQ * TS * 4 * 4;                                  // group exchange slots
   static constexpr uint32_t OFF_W1R = 0, OFF_W1L = OFF_W1R + W1_BYTES, OFF_GTR = OFF_W1L + W1_BYTES,
                             OFF_GTL = OFF_GTR + GT_BYTES, OFF_U = OFF_GTL + GT_BYTES,   // [2][raw|lo]
                             OFF_A1 = OFF_U + 4 * U_BYTES, OFF_A2 = OFF_A1 + NA1 * A_BYTES, OFF_W2 = OFF_A2 + A_BYTES,
@@ -69,7 +73,9 @@ struct TcPlan {
   static constexpr uint32_t REC_BYTES = S::IN * 16 * TS;                                // [IN][TS] basis records
   static constexpr uint32_t OFF_BAR = OFF_G0 + (OWN_G0 ? REC_BYTES : 0), SMEM_BYTES = OFF_BAR + 256;
   static_assert(S::N == 3 && S::SEGH == 2 && S::SEGO == 2 && S::NH == 1, "tensor path: C2 / C3 family");
-  static_assert(HID == 40 && HH % QI == 0 && HK % 4 == 0 && CH_K % 8 == 0 && KH <= 256, "tensor path shape");
+  static_assert(HID == 40 && HID % NQ == 0 && QI >= 1 && HH % QI == 0 && HK % 2 == 0 && HH % 2 == 0 && CH_K % 8 == 0 && KH <= 256,
+                "tensor path shape");
+  static_assert(NQ == 2 || NQ == 4, "pairs or quads");
   static_assert(G_COL + 2 * HID <= T_COL && GW_COL + 2 * HID <= 512 && UNIT % 8 == 0 && (UNIT / 2) % 4 == 0, "TMEM / unit plan");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan");
   static_assert(G0_BYTES <= A_BYTES && REC_BYTES <= A_BYTES, "layer-0 dL/dw tiles alias the idle a1 buffer / a2");
@@ -84,17 +90,30 @@ enum { B_FFULL0 = 0, B_FFULL1, B_FEMPTY0, B_FEMPTY1, B_D1FULL, B_D1EMPTY, B_GFUL
 // y[O] += sum_j l[j] * W[j * PITCH + 0..O)
 template <int N, int O, int PITCH, bool GLOBAL>
 __device__ __forceinline__ void contract_fwd_p(const float* __restrict__ wrow, const float* l, float* __restrict__ acc) {
-  static_assert(O % 4 == 0 && PITCH % 4 == 0, "vector width");
+  static_assert(O % 2 == 0 && PITCH % 4 == 0, "vector width");
+  if (O % 4 == 0) {
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const float4* wp = reinterpret_cast<const float4*>(wrow + j * PITCH);
+    for (int j = 0; j < N; ++j) {
+      const float4* wp = reinterpret_cast<const float4*>(wrow + j * PITCH);
 #pragma unroll
-    for (int q = 0; q < O / 4; ++q) {
-      const float4 w = GLOBAL ? __ldg(wp + q) : wp[q];
-      acc[4 * q + 0] = fmaf(l[j], w.x, acc[4 * q + 0]);
-      acc[4 * q + 1] = fmaf(l[j], w.y, acc[4 * q + 1]);
-      acc[4 * q + 2] = fmaf(l[j], w.z, acc[4 * q + 2]);
-      acc[4 * q + 3] = fmaf(l[j], w.w, acc[4 * q + 3]);
+      for (int q = 0; q < O / 4; ++q) {
+        const float4 w = GLOBAL ? __ldg(wp + q) : wp[q];
+        acc[4 * q + 0] = fmaf(l[j], w.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(l[j], w.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(l[j], w.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(l[j], w.w, acc[4 * q + 3]);
+      }
+    }
+  } else {   // the row slice starts on an 8-byte boundary only (quads: 10 outputs per thread)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float2* wp = reinterpret_cast<const float2*>(wrow + j * PITCH);
+#pragma unroll
+      for (int q = 0; q < O / 2; ++q) {
+        const float2 w = GLOBAL ? __ldg(wp + q) : wp[q];
+        acc[2 * q + 0] = fmaf(l[j], w.x, acc[2 * q + 0]);
+        acc[2 * q + 1] = fmaf(l[j], w.y, acc[2 * q + 1]);
+      }
     }
   }
 }
@@ -117,17 +136,87 @@ __device__ __forceinline__ void window3(int id, const float* __restrict__ t, flo
   t1 = id ? t[S::STRIDE + 1] : t[1];
   t2 = id ? t[S::STRIDE + 2] : t[2];
 }
+// K consecutive columns (K even; any column offset is legal for .x2 / .x4: csrc/probe/tmem_align_probe.cu)
 template <int K>
 __device__ __forceinline__ void tmem_stK(uint32_t addr, const float* v) {
-  static_assert(K % 4 == 0, "column groups of 4");
+  static_assert(K % 2 == 0, "column groups of 4 and a tail of 2");
 #pragma unroll
   for (int q = 0; q < K / 4; ++q) tmem_st4(addr + 4 * q, v + 4 * q);
+  if (K % 4 != 0)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};"
+                 ::"r"(addr + K - 2), "r"(__float_as_uint(v[K - 2])), "r"(__float_as_uint(v[K - 1])) : "memory");
 }
 template <int K>
 __device__ __forceinline__ void tmem_ldK(uint32_t addr, float* v) {
-  static_assert(K % 4 == 0, "column groups of 4");
+  static_assert(K % 2 == 0, "column groups of 4 and a tail of 2");
 #pragma unroll
   for (int q = 0; q < K / 4; ++q) tmem_ld4(addr + 4 * q, v + 4 * q);
+  if (K % 4 != 0) {
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr + K - 2));
+    v[K - 2] = __uint_as_float(r0);
+    v[K - 1] = __uint_as_float(r1);
+  }
+}
+
+// the NQ warps (w, w + 4, ...) that share 32 samples
+template <int NQ>
+__device__ __forceinline__ void bar_group(int warp) {
+  if (NQ == 2) {
+    bar_pair(warp);
+  } else {
+    switch (warp & 3) {
+      case 0: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
+      case 1: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
+      case 2: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+      default: asm volatile("bar.sync 5, 128;" ::: "memory"); break;
+    }
+  }
+}
+template <int NSAMPLE>
+__device__ __forceinline__ void bar_all_samples() {
+  if (NSAMPLE == 256) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 1, 512;" ::: "memory");
+}
+// sum of one float over the group's threads (exchange slots xsamp[q * TS * 4], q = 0 .. NQ-1, own slot = hf)
+template <int NQ>
+__device__ __forceinline__ float group_sum(float v, float* xsamp, int hf, int warp) {
+  xsamp[hf * TS * 4] = v;
+  bar_group<NQ>(warp);
+  float t = 0.f;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) t += xsamp[q * TS * 4];     // same order in every thread of the group
+  bar_group<NQ>(warp);
+  return t;
+}
+// MaxAbsNormalization of a 40-wide row split over a thread group (W values each); first index wins ties.
+template <int W, int NQ>
+__device__ __forceinline__ void maxabs_group(float* v, int hf, float eps, float* xsamp, int warp, float& inv_d, int& kidx) {
+  float m = -1.f, vk = 0.f;
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const float a = fabsf(v[i]);
+    if (a > m) { m = a; k = i; vk = v[i]; }
+  }
+  int kk = hf * W + k;
+  kk |= vk > 0.f ? 0 : (vk < 0.f ? 0x10000 : 0x20000);
+  xsamp[hf * TS * 4] = m;
+  xsamp[hf * TS * 4 + 1] = __int_as_float(kk);
+  bar_group<NQ>(warp);
+  float mg = -1.f;
+  int kg = 0;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {                           // ascending unit index, strict >: the first maximum wins
+    const float mo = xsamp[q * TS * 4];
+    const int ko = __float_as_int(xsamp[q * TS * 4 + 1]);
+    if (mo > mg) { mg = mo; kg = ko; }
+  }
+  bar_group<NQ>(warp);
+  kidx = kg;
+  inv_d = __fdiv_rn(1.f, __fadd_rn(mg, eps));
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] *= inv_d;
 }
 
 // MaxAbsNormalization of a 40-wide row split over a thread pair (20 values each); first index wins ties.
@@ -158,10 +247,11 @@ __device__ __forceinline__ void maxabs_pair(float* v, int hf, float eps, float* 
 }
 __device__ __forceinline__ float kidx_sign(int kidx) { return (kidx & 0x10000) ? -1.f : ((kidx & 0x20000) ? 0.f : 1.f); }
 
-template <class S>
-__global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedParams p) {
-  using P = TcPlan<S>;
+template <class S, int NQ>
+__global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(const FusedParams p) {
+  using P = TcPlan<S, NQ>;
   constexpr int N = S::N, IN = S::IN, HID = S::HID, OUT = S::OUT, HP = S::HP, OP = S::OP, ND = P::ND, HH = P::HH;
+  constexpr int NSAMPLE_THREADS = P::NSAMPLE, NTHREADS = P::NT, MMAW = P::MMAW;   // (shadow the pair constants)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW1R = smem + P::OFF_W1R;
   uint8_t* sW1L = smem + P::OFF_W1L;
@@ -180,7 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (uniform datapath)
 
   // ---- prologue: TMEM, barriers, weights -------------------------------------------------
-  if (warp == 8) {
+  if (warp == MMAW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -223,7 +313,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
   const uint32_t tmem = *tmem_base_s;
   const long long tiles = (p.B + TS - 1) / TS;
 
-  if (warp == 8) {
+  if (warp == MMAW) {
     // =========================== MMA warp ===================================================
     const uint32_t leader = elect_one();
     constexpr uint32_t ID_FWD = make_idesc(128, HID, 0, 0);        // A: TMEM (K-major), B: W1 K-major
@@ -332,7 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       mbar_wait_backoff(&bars[B_UFULL0 + (q_unit & 1)], (q_unit >> 1) & 1, 32);
       issue_gw();
     }
-  } else if (warp > 8) {
+  } else if (warp > MMAW) {
     // =========================== helper warps ===============================================
     // Stage Phi1 (densified basis of the hidden-layer inputs a1, raw + tf32 residual) for the dL/dw1 product in
     // units of 16 samples, double-buffered.  Thread = (input i, half of the unit): its K-columns are fixed, the
@@ -426,8 +516,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
     const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* a1 = sA1 + s * APITCH;                     // re-pointed per tile when a1 is double-buffered
     float* a2 = sA2 + s * APITCH;
-    float* xs = sX + (hf * TS + s) * 4;
-    const float* xo = sX + ((hf ^ 1) * TS + s) * 4;
+    float* xsamp = sX + s * 4;                        // exchange slots of this sample: [q][TS][4]
+    float* xs = xsamp + hf * TS * 4;
     float loss_local = 0.f;
     uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
     // layer 0 (FFMA, weights through L1) of one tile: this thread's 20 outputs, MaxAbs over the pair
@@ -475,13 +565,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       }
       inv_d_ = 1.f;
       kidx_ = 0;
-      if (p.normalize) maxabs_pair<HH>(h_, hf, p.norm_eps, xs, xo, warp, inv_d_, kidx_);
+      if (p.normalize) maxabs_group<HH, NQ>(h_, hf, p.norm_eps, xsamp, warp, inv_d_, kidx_);
     };
     float hN[HH];
     float4 recN[IN];
     float invN = 1.f;
     int kidxN = 0;
     float tgN[OUT];
+    constexpr int PRE = 2;                            // forward chunks of the next tile staged ahead
+    auto stage_chunk = [&](int c) {                   // densified basis of this thread's inputs of chunk c (from hN)
+      const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
+      float v[P::HK], lo[P::HK];
+#pragma unroll
+      for (int m = 0; m < P::QI; ++m) {
+        const float x = hN[c * P::QI + m];
+        int id;
+        float xi, l[N];
+        locate2(x, id, xi);
+        hoir::lagrange<N>(lag.X, lag.D, xi, l);
+        densify<S, ND>(id, l, v + m * ND);
+      }
+#pragma unroll
+      for (int j = 0; j < P::HK; ++j) lo[j] = tf32_lo(v[j]);
+      mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);       // (after the arithmetic: the buffer is usually free by now)
+      fence_after();
+      const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K + hf * P::HK;
+      tmem_stK<P::HK>(col, v);
+      tmem_stK<P::HK>(col + P::CH_K, lo);
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&bars[B_FFULL0 + buf]);
+      ++q_chunk;
+    };
     if ((long long)blockIdx.x < tiles) layer0(blockIdx.x, hN, recN, invN, kidxN, tgN);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
       const long long b = tile * TS + s;
@@ -498,30 +613,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
 #pragma unroll
       for (int i = 0; i < IN; ++i) rec0[i] = recN[i];
       // ---- hidden layer forward on the tensor cores: stage this thread's inputs of every chunk (straight from
-      //      the layer-0 registers) into TMEM
+      //      the layer-0 registers) into TMEM.  The first PRE chunks of every tile but the first were already staged
+      //      during the previous tile (right after its T arrived): the forward pipeline is 2 buffers deep, so its
+      //      latency (5 x (15 MMAs + hand-overs) ~ 4 k cycles) would otherwise sit on this path.
 #pragma unroll
-      for (int c = 0; c < P::NCH; ++c, ++q_chunk) {
-        const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
-        float v[P::HK], lo[P::HK];
-#pragma unroll
-        for (int m = 0; m < P::QI; ++m) {
-          const float x = hN[c * P::QI + m];
-          int id;
-          float xi, l[N];
-          locate2(x, id, xi);
-          hoir::lagrange<N>(lag.X, lag.D, xi, l);
-          densify<S, ND>(id, l, v + m * ND);
-        }
-#pragma unroll
-        for (int j = 0; j < P::HK; ++j) lo[j] = tf32_lo(v[j]);
-        mbar_wait(&bars[B_FEMPTY0 + buf], ph ^ 1);     // (after the arithmetic: the buffer is usually free by now)
-        fence_after();
-        const uint32_t col = tm_lane + P::FA_COL + buf * 2 * P::CH_K + hf * P::HK;
-        tmem_stK<P::HK>(col, v);
-        tmem_stK<P::HK>(col + P::CH_K, lo);
-        tmem_wait_st();
-        fence_before();
-        mbar_arrive(&bars[B_FFULL0 + buf]);
+      for (int c = 0; c < P::NCH; ++c) {
+        if (c >= PRE || n_tile == 0) stage_chunk(c);
       }
       // ---- a1 tile for the helpers (dL/dw1 units) and the T epilogue.  Its buffer is free once the helpers have
       //      staged its previous occupant and every owner of the previous tile's layer-0 walk is done (the walk
@@ -538,11 +635,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       // ---- D1 epilogue: hidden pre-activation (own 20 columns) -> MaxAbs -> a2
       mbar_wait(&bars[B_D1FULL], n_tile & 1);
       fence_after();
-      tmem_ld20(tm_lane + P::D1_COL + hf * HH, h);
+      tmem_ldK<HH>(tm_lane + P::D1_COL + hf * HH, h);
       tmem_wait_ld();
       fence_before();
       mbar_arrive(&bars[B_D1EMPTY]);
-      if (p.normalize) maxabs_pair<HH>(h, hf, p.norm_eps, xs, xo, warp, inv_d1, kidx1);
+      if (p.normalize) maxabs_group<HH, NQ>(h, hf, p.norm_eps, xsamp, warp, inv_d1, kidx1);
       if (n_tile > 0) mbar_wait(&bars[B_A2FREE], (n_tile - 1) & 1);   // helpers are done with the previous a2 / dL/dy
 #pragma unroll
       for (int j = 0; j < HH; ++j) a2[hf * HH + j] = h[j];
@@ -558,12 +655,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         contract_fwd<N, OUT, OP, false>(sW2 + ((size_t)i * S::NODES_O + id * S::STRIDE) * OP, l, yo);
       }
       *reinterpret_cast<float4*>(xs) = make_float4(yo[0], yo[1], yo[2], 0.f);
-      bar_pair(warp);
+      bar_group<NQ>(warp);
       {
-        const float4 o4 = *reinterpret_cast<const float4*>(xo);
-        yo[0] += o4.x; yo[1] += o4.y; yo[2] += o4.z;
+        float ys[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {                 // same order in every thread of the group
+          const float4 o4 = *reinterpret_cast<const float4*>(xsamp + q * TS * 4);
+          ys[0] += o4.x; ys[1] += o4.y; ys[2] += o4.z;
+        }
+        yo[0] = ys[0]; yo[1] = ys[1]; yo[2] = ys[2];
       }
-      bar_pair(warp);
+      bar_group<NQ>(warp);
 #pragma unroll
       for (int o = 0; o < OUT; ++o) gy[o] = 0.f;
       if (live) {
@@ -603,10 +705,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         g[j] = gx;                                   // dL/da2 (a2 keeps the activations for the dL/dw2 pass below)
       }
       if (p.normalize) {
-        xs[0] = dot;
-        bar_pair(warp);
-        dot += xo[0];
-        bar_pair(warp);
+        dot = group_sum<NQ>(dot, xsamp, hf, warp);
         const int k = (kidx1 & 0xffff) - hf * HH;
         const float sgn = kidx_sign(kidx1);
 #pragma unroll
@@ -624,8 +723,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
 #pragma unroll
         for (int j = 0; j < HH; ++j) lo[j] = tf32_lo(g[j]);
         const uint32_t col = tm_lane + P::G_COL + hf * HH;
-        tmem_st20(col, g);
-        tmem_st20(col + HID, lo);
+        tmem_stK<HH>(col, g);
+        tmem_stK<HH>(col + HID, lo);
 #pragma unroll
         for (int j = 0; j < HH; ++j) {
           const uint32_t off = sw4_off(hf * HH + j, s, P::GT_RS);
@@ -643,6 +742,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       dot = 0.f;
       mbar_wait(&bars[B_TFULL], n_tile & 1);
       fence_after();
+      // T exists, so the G staging columns (they alias the forward staging buffers) are free again: stage the
+      // first chunks of the next tile now (hN already holds its layer-0 output)
+      if (tile + gridDim.x < tiles) {
+#pragma unroll
+        for (int c = 0; c < PRE; ++c) stage_chunk(c);
+      }
 #pragma unroll
       for (int c = 0; c < P::NCH; ++c) {
         float t[P::HK];
@@ -664,10 +769,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       }
       fence_before();
       if (p.normalize) {
-        xs[0] = dot;
-        bar_pair(warp);
-        dot += xo[0];
-        bar_pair(warp);
+        dot = group_sum<NQ>(dot, xsamp, hf, warp);
         const int k = (kidx0 & 0xffff) - hf * HH;
         const float sgn = kidx_sign(kidx0);
 #pragma unroll
@@ -681,9 +783,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       //      ids to the workspace; gw0_owner_kernel finishes the job.
       if (p.ws_g0 != nullptr) {
         if (live) {
-          float4* dstg = reinterpret_cast<float4*>(p.ws_g0 + b * HID + hf * HH);
+          float2* dstg = reinterpret_cast<float2*>(p.ws_g0 + b * HID + hf * HH);
 #pragma unroll
-          for (int q = 0; q < HH / 4; ++q) dstg[q] = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+          for (int q = 0; q < HH / 2; ++q) dstg[q] = make_float2(g[2 * q], g[2 * q + 1]);
           if (hf == 0) {
 #pragma unroll
             for (int i = 0; i < IN; ++i) {
@@ -708,13 +810,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
         float* sG0 = sA1 + ((n_tile + 1) & 1) * (P::A_BYTES / 4);                          // [s][GPITCH] dL/d(layer-0 output)
         float4* sRec = P::OWN_G0 ? reinterpret_cast<float4*>(smem + P::OFF_G0) : reinterpret_cast<float4*>(sA2);   // [IN][TS]
 #pragma unroll
-        for (int q = 0; q < HH / 4; ++q)
-          *reinterpret_cast<float4*>(sG0 + s * P::GPITCH + hf * HH + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+        for (int q = 0; q < HH / 2; ++q)
+          *reinterpret_cast<float2*>(sG0 + s * P::GPITCH + hf * HH + 2 * q) = make_float2(g[2 * q], g[2 * q + 1]);
         if (hf == 0) {
 #pragma unroll
           for (int i = 0; i < IN; ++i) sRec[(size_t)i * TS + s] = rec0[i];
         }
-        bar_samples();
+        bar_all_samples<NSAMPLE_THREADS>();
         constexpr int NOQ = HID / 4, NGRP = NSAMPLE_THREADS / (IN * NOQ), SPG = (TS + NGRP - 1) / NGRP;
         if (tid < NGRP * IN * NOQ) {
           const int grp = tid / (IN * NOQ), pr = tid - grp * (IN * NOQ), i = pr / NOQ, oq = pr - i * NOQ;
@@ -775,23 +877,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const FusedPa
       mbar_wait(&bars[B_GWDONE], (n_tile - 1) & 1);
       fence_after();
       // accumulator row R = hf * 128 + s holds K-column R: chunk c = R / 40, half (R % 40) / 20, input 4c + ..., node R % 5
-      const int R = hf * 128 + s;
-      float v[HID];
-#pragma unroll
-      for (int g8 = 0; g8 < HID / 8; ++g8) tmem_ld8(tm_lane + P::GW_COL + hf * HID + g8 * 8, v + g8 * 8);
+      // (quads: threads q and q + 2 share accumulator half q & 1 and take 20 of its 40 columns each)
+      constexpr int NCP = NQ / 2, WCOLS = HID / NCP;
+      const int half = hf % 2, cpart = hf / 2;
+      const int R = half * 128 + s;
+      float v[WCOLS];
+      tmem_ldK<WCOLS>(tm_lane + P::GW_COL + half * HID + cpart * WCOLS, v);
       tmem_wait_ld();
       if (R < P::KH) {
         const int c = R / P::CH_K, rem = R - c * P::CH_K, hfi = rem / P::HK, r2 = rem - hfi * P::HK;
         const int i = hfi * HH + c * P::QI + r2 / ND, q = r2 % ND;
 #pragma unroll
-        for (int o = 0; o < HID; ++o)
-          if (v[o] != 0.f) hoir::red_add(p.gw[1] + ((size_t)o * HID + i) * ND + q, v[o]);
+        for (int o = 0; o < WCOLS; ++o)
+          if (v[o] != 0.f) hoir::red_add(p.gw[1] + ((size_t)(cpart * WCOLS + o) * HID + i) * ND + q, v[o]);
       }
       fence_before();
     }
   }
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (warp == MMAW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   hoir::opt_tail_in_kernel(p.tail);
 }
 

@@ -276,3 +276,17 @@ def test_host_batch_stepper_pipeline():
             got.append(r)
     got.append(st.flush())
     assert len(got) == 4 and all(abs(a - b) <= 1e-4 * abs(b) for a, b in zip(got, want))
+
+
+def test_quad_thread_variant_of_the_tensor_core_kernel():
+    """HOIR_TC_QUAD=1 selects the four-threads-per-sample instantiation of the training kernel (measured slower than
+    pairs, kept as an A/B switch): it must pass the same oracle parity.  The switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HOIR_TC_QUAD="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_fused.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "trainer_steps_match_oracle_training or mesh_mode_training_and_render or two_pass"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
