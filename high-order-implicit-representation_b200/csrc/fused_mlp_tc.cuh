@@ -572,7 +572,7 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
     float invN = 1.f;
     int kidxN = 0;
     float tgN[OUT];
-    constexpr int PRE = 2;                            // forward chunks of the next tile staged ahead
+    constexpr int PRE = P::NCH - 1 < 4 ? P::NCH - 1 : 4;   // forward chunks of the next tile staged ahead (see below)
     auto stage_chunk = [&](int c) {                   // densified basis of this thread's inputs of chunk c (from hN)
       const uint32_t buf = q_chunk & 1, ph = (q_chunk >> 1) & 1;
       float v[P::HK], lo[P::HK];
@@ -744,9 +744,10 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
       fence_after();
       // T exists, so the G staging columns (they alias the forward staging buffers) are free again: stage the
       // first chunks of the next tile now (hN already holds its layer-0 output)
-      if (tile + gridDim.x < tiles) {
+      const bool has_next = tile + gridDim.x < tiles;
+      if (has_next) {
 #pragma unroll
-        for (int c = 0; c < PRE; ++c) stage_chunk(c);
+        for (int c = 0; c < 2 && c < PRE; ++c) stage_chunk(c);
       }
 #pragma unroll
       for (int c = 0; c < P::NCH; ++c) {
@@ -768,6 +769,7 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
         }
       }
       fence_before();
+      if (has_next && PRE > 2) stage_chunk(2);        // its buffer (chunk 0 of the next tile) was consumed during the T epilogue
       if (p.normalize) {
         dot = group_sum<NQ>(dot, xsamp, hf, warp);
         const int k = (kidx0 & 0xffff) - hf * HH;
@@ -779,6 +781,7 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
           g[j] = gi * inv_d0;
         }
       }
+      if (has_next && PRE > 3) stage_chunk(3);
       // ---- layer 0 dL/dw.  Incoherent batches (two-pass mode): stream dL/dy rows, basis records and segment
       //      ids to the workspace; gw0_owner_kernel finishes the job.
       if (p.ws_g0 != nullptr) {
