@@ -1,22 +1,26 @@
-// fused_mlp_tc.cuh -- tensor-core (tcgen05 / TMEM) training kernel for the 40-wide implicit MLP.
-// Included by fused_mlp.cu (uses its FusedParams / SegConst / contract_* helpers).
+// fused_mlp_tc.cuh -- tensor-core (tcgen05 / TMEM) kernels for the 40-wide implicit MLP: the whole-network
+// training kernel (continuous and discontinuous n = 3) and the forward-only kernel.
+// Included by fused_mlp.cu (uses its FusedParams / SegConst / contract_* helpers).  DESIGN.md section 4.1.
 //
-// One CTA = 8 sample warps + 1 MMA warp, persistent grid.  A tile is 128 samples; sample s is
-// worked on by a PAIR of threads (s, s + 128) in warps w and w + 4 -- both map to TMEM lane s --
-// each owning 20 of the 40 hidden units (half hf owns units 20 hf .. 20 hf + 19), so that every
-// per-input / per-output loop is split in two and the SM holds 8 warps of CUDA-core work.  The hidden layer's three contractions are densified GEMMs
-// (K = 40 inputs x 5 nodes = 200) on tcgen05.mma kind::tf32 with a 3-pass hi/lo split
+// Training: one CTA = 8 sample warps + 1 MMA warp + 3 helper warps, persistent cooperative grid (1 CTA per SM).
+// A tile is 128 samples; sample s is worked on by a PAIR of threads (s, s + 128) in warps w and w + 4 -- both map
+// to TMEM lane s -- each owning 20 of the 40 hidden units.  The hidden layer's three contractions are densified
+// GEMMs (K = 40 inputs x 5 / 6 node slots) on tcgen05.mma kind::tf32 with a 3-pass hi/lo split
 // (A*B + Alo*B + A*Blo, fp32-level accuracy):
-//   FWD  D1[128 x 40]   = Phi1[128 x 200] * W1          A: TMEM (chunks of 8 inputs, double buffered)
-//                                                        B: smem W1, K-major view
-//   GX   T [128 x 208]  = G  [128 x 40]  * W1^T         A: TMEM, B: the same smem W1, MN-major view
-//   GW   gW1[200 x 40] += Phi1^T[200 x 16] * G[16 x 40] A: smem units of 16 samples (MN-major),
-//                                                        B: smem G^T (K-major); accumulators stay in
-//                                                        TMEM for the whole kernel
-// All shared-memory operands use the 128B_BASE32B layout (rows of 128 B, atoms of 4 rows, 32-byte
-// chunks XOR-ed with row%4), the one layout that tcgen05 accepts for tf32 in BOTH majors (probe:
-// csrc/probe/umma_probe.cu), so W1 and G are stored once.  Layer 0, the output layer, the basis,
-// MaxAbs and the loss stay on the CUDA cores (FFMA).
+//   FWD  D1[128 x 40]  = Phi1[128 x K] * W1         A: TMEM (chunks of 40 / 24 K-columns, double buffered, written
+//                                                     by the sample threads from the layer-0 registers; four of the
+//                                                     five chunks of tile n + 1 are staged during tile n)
+//                                                    B: smem W1, K-major view
+//   GX   T [128 x K]   = G  [128 x 40] * W1^T        A: TMEM, B: the same smem W1, MN-major view
+//   GW   gW1[K x 40]  += Phi1^T[K x 8] * G[8 x 40]   A: smem units of 8 samples (MN-major) staged by the HELPER warps,
+//                                                    B: smem G^T (K-major); accumulators stay in TMEM for the whole
+//                                                     kernel.  The MMA warp issues by readiness (units of tile n - 1
+//                                                     between the forward chunks of tile n).
+// All shared-memory operands use the 128B_BASE32B layout (rows of 128 B, atoms of 4 rows, 32-byte chunks XOR-ed
+// with row % 4), the one layout that tcgen05 accepts for tf32 in BOTH majors (csrc/probe/umma_probe.cu), so W1 and
+// G are stored once.  Layer 0, the output layer, the basis, MaxAbs and the loss stay on the CUDA cores; the helper
+// warps also own dL/dw2 (register sums for the whole kernel).  The kernel is templated on the threads per sample
+// (NQ = 2; NQ = 4 is a tested but slower variant).
 #pragma once
 #include "tc_common.cuh"
 
@@ -25,7 +29,6 @@ namespace tc {
 constexpr int TS = 128;          // samples per tile
 constexpr int NSAMPLE_THREADS = 256;   // forward kernel: 8 sample warps, 2 threads per sample
 constexpr int NHELPER = 96;            // 3 helper warps: stage the Phi1 units of the dL/dw1 product
-constexpr int NTHREADS = 384;          // 8 sample warps + 1 MMA warp + 3 helper warps (168 regs x 384 = 63 K)
 constexpr int NTHREADS_FWD = 288;      // forward-only kernel: 8 sample warps + 1 MMA warp
 constexpr int APITCH = 41;       // row pitch (floats) of the saved-activation tiles
 

@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include "hoir_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -20,9 +21,12 @@ struct Workspace {
 };
 constexpr int kSlots = 3;
 Workspace g_ws[16][kSlots];
+// forward calls arrive on the caller's thread, backward calls on autograd's device thread: the table is shared
+std::mutex g_ws_mutex;
 }  // namespace
 
 int hoir_get_workspace(int slot, size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
   int dev = 0;
   HOIR_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16 || slot < 0 || slot >= kSlots)
@@ -45,6 +49,7 @@ int hoir_get_workspace(int slot, size_t bytes, void** out) {
 }
 
 void hoir_free_workspaces() {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
   int cur = 0;
   cudaGetDevice(&cur);
   for (int d = 0; d < 16; ++d)
