@@ -56,6 +56,66 @@ __global__ void gather_kernel(const float* __restrict__ img, int C, int H, int W
   }
 }
 
+// Same gather, table-driven: the (channel, dh, dw) of every feature / target column is computed ONCE per CTA into
+// shared memory (the element order has ~10 runtime divisions per column); a warp then copies one patch at a time,
+// lanes over consecutive columns (coalesced stores, the image rows of a patch stay in L1/L2).
+__global__ void __launch_bounds__(256)
+gather_table_kernel(const float* __restrict__ img, int C, int H, int W, int width, int outside, int stride, int pad,
+                    int nW, long long first, long long count, float* __restrict__ features,
+                    float* __restrict__ targets) {
+  extern __shared__ int tab[];                      // [C * E] features then [C * WW] targets: c << 16 | dh << 8 | dw
+  const int T = width + 2 * outside, E = T * T - width * width, WW = width * width;
+  const int nfe = C * E, nte = C * WW;
+  for (int r = threadIdx.x; r < nfe + nte; r += blockDim.x) {
+    const bool is_t = r >= nfe;
+    const int rr = is_t ? r - nfe : r, cells = is_t ? WW : E;
+    const int c = rr / cells, e = rr - c * cells;
+    int dh, dw;
+    if (is_t) {
+      dh = outside + e / width;
+      dw = outside + e % width;
+    } else {
+      const int top = outside * T;
+      if (e < top) {
+        dh = e / T; dw = e % T;
+      } else if (e < top + width * 2 * outside) {
+        const int q = e - top;
+        dh = outside + q / (2 * outside);
+        const int m = q % (2 * outside);
+        dw = m < outside ? m : m + width;
+      } else {
+        const int q = e - top - width * 2 * outside;
+        dh = outside + width + q / T; dw = q % T;
+      }
+    }
+    tab[r] = (c << 16) | (dh << 8) | dw;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const size_t plane = (size_t)H * W;
+  for (long long pl = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); pl < count; pl += (long long)gridDim.x * wpb) {
+    const long long p = first + pl;
+    const int ph = (int)(p / nW), pw = (int)(p - (long long)ph * nW);
+    const int y0 = ph * stride - pad, x0 = pw * stride - pad;
+    if (features) {
+      float* dst = features + pl * nfe;
+      for (int r = lane; r < nfe; r += 32) {
+        const int t = tab[r];
+        const int y = reflect(y0 + ((t >> 8) & 255), H), x = reflect(x0 + (t & 255), W);
+        dst[r] = __ldg(img + (size_t)(t >> 16) * plane + (size_t)y * W + x);
+      }
+    }
+    if (targets) {
+      float* dst = targets + pl * nte;
+      for (int r = lane; r < nte; r += 32) {
+        const int t = tab[nfe + r];
+        const int y = reflect(y0 + ((t >> 8) & 255), H), x = reflect(x0 + (t & 255), W);
+        dst[r] = __ldg(img + (size_t)(t >> 16) * plane + (size_t)y * W + x);
+      }
+    }
+  }
+}
+
 // out[c][r][col] = alpha * prev[c][r][col] + (1 - alpha) * block value predicted for that pixel, where the
 // predictions[p][c * w * w + kh * w + kw] come from stride-w patches of the image reflection-padded by 2*o + w
 __global__ void fold_kernel(const float* __restrict__ pred, int C, int H, int W, int width, int outside, int nW,
@@ -101,6 +161,15 @@ extern "C" int hoir_neighborhood_gather(const float* image, int C, int H, int W,
   if (count == 0 || (!features && !targets)) return HOIR_OK;
   if (!image) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_neighborhood_gather");
   const int T = width + 2 * outside;
+  const size_t tab_bytes = (size_t)C * T * T * sizeof(int);
+  if (T <= 255 && C <= 32767 && tab_bytes <= 48 * 1024) {
+    long long g2 = (count + 7) / 8;
+    if (g2 > 148 * 16) g2 = 148 * 16;
+    gather_table_kernel<<<(int)g2, 256, tab_bytes, (cudaStream_t)stream>>>(image, C, H, W, width, outside, stride, pad, nW,
+                                                                         first_patch, count, features, targets);
+    HOIR_CHECK_CUDA(cudaGetLastError());
+    return HOIR_OK;
+  }
   const long long n = count * C * ((features ? T * T - width * width : 0) + (targets ? width * width : 0));
   long long grid = (n + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;
