@@ -63,12 +63,13 @@ class ImageTrainer:
     pixel ranges in random order with coordinates and targets generated in-kernel (no dataset in HBM)."""
 
     def __init__(self, cfg, image: Union[str, Tensor], device: str = "cuda", sampling: str = "shuffle",
-                 process_group=None, seed: int = 0):
+                 process_group=None, seed: int = 0, drop_last: bool = True):
         if sampling not in ("shuffle", "tiles"):
             raise ValueError(f"sampling {sampling} not recognized")
         self.cfg = to_cfg(cfg)
         self.device = torch.device(device)
         self.sampling = sampling
+        self.drop_last = bool(drop_last)        # the reference's train DataLoader drops the ragged last batch
         self.rotations = int(self.cfg.rotations)
         self.batch_size = int(self.cfg.batch_size)
         self.image_u8 = _load_image_u8(image).to(self.device).contiguous()
@@ -132,6 +133,8 @@ class ImageTrainer:
             perm = torch.randperm(n, device=self.device, generator=self.gen)
             for k in range(0, n, bs * self.world):
                 idx = perm[k:k + bs * self.world]
+                if self.drop_last and idx.numel() < bs * self.world and k > 0:
+                    break           # DataLoader(drop_last=True), single_image_dataset.py:312-320
                 mine = idx[self.rank::self.world]
                 if mine.numel() == 0:
                     continue
