@@ -788,17 +788,29 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
       // ---- layer 0 dL/dw.  Incoherent batches (two-pass mode): stream dL/dy rows, basis records and segment
       //      ids to the workspace; gw0_owner_kernel finishes the job.
       if (p.ws_g0 != nullptr) {
-        if (live) {
-          float2* dstg = reinterpret_cast<float2*>(p.ws_g0 + b * HID + hf * HH);
+        // the tile's dL/dy rows go through shared memory (the idle a1 buffer) so that the 20 KB leave the SM as
+        // fully coalesced 16-byte stores instead of 160-byte-strided 8-byte ones
+        const uint32_t ob = (n_tile + 1) & 1, use = (n_tile + 1) >> 1;
+        if (use > 0) mbar_wait(&bars[B_A1FREE0 + ob], (use - 1) & 1);
+        float* sG0 = sA1 + ob * (P::A_BYTES / 4);
+        static_assert(P::GPITCH == HID, "the staged tile is copied as one contiguous block");
 #pragma unroll
-          for (int q = 0; q < HH / 2; ++q) dstg[q] = make_float2(g[2 * q], g[2 * q + 1]);
-          if (hf == 0) {
+        for (int q = 0; q < HH / 2; ++q)
+          *reinterpret_cast<float2*>(sG0 + s * P::GPITCH + hf * HH + 2 * q) = make_float2(g[2 * q], g[2 * q + 1]);
+        if (live && hf == 0) {
 #pragma unroll
-            for (int i = 0; i < IN; ++i) {
-              p.ws_rec[(size_t)i * p.B + b] = rec0[i];
-              p.ws_seg[(size_t)i * p.B + b] = (unsigned short)(__float_as_int(rec0[i].x) / S::STRIDE);
-            }
+          for (int i = 0; i < IN; ++i) {
+            p.ws_rec[(size_t)i * p.B + b] = rec0[i];
+            p.ws_seg[(size_t)i * p.B + b] = (unsigned short)(__float_as_int(rec0[i].x) / S::STRIDE);
           }
+        }
+        bar_all_samples<NSAMPLE_THREADS>();
+        {
+          const long long b0 = tile * TS;
+          const int nrow = (int)((p.B - b0) < TS ? (p.B - b0) : TS);
+          float4* dst = reinterpret_cast<float4*>(p.ws_g0 + b0 * HID);
+          const float4* src = reinterpret_cast<const float4*>(sG0);
+          for (int k = tid; k < nrow * (HID / 4); k += NSAMPLE_THREADS) dst[k] = src[k];
         }
         mbar_arrive(&bars[B_OWNDONE]);
         continue;
