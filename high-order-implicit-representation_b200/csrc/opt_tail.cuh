@@ -92,7 +92,7 @@ __device__ __forceinline__ void peer_exchange_barrier(const OptTail& t) {
     unsigned int spins = 0;
     while (ld_acquire_sys_u32(mine) < t.flag_value) {
       __nanosleep(64);
-      if (++spins > (1u << 26)) __trap();   // a peer never arrived: fail loudly instead of hanging
+      if (++spins > (1u << 30)) __trap();   // a peer never arrived (~1 min): fail loudly instead of hanging
     }
   }
   __syncthreads();

@@ -39,7 +39,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (done) break;
     __nanosleep(ns);
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 27)) __trap();
   }
 }
 // non-blocking poll of a phase
