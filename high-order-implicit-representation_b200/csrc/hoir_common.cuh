@@ -124,6 +124,29 @@ __device__ __forceinline__ void lagrange_deriv(const float* __restrict__ X,
     der[j] = s * D[j];
   }
 }
+// n = 3 on the unit Chebyshev-Lobatto nodes X = {-1, 0, 1}, D = {1/2, -1, 1/2} (both exact in fp32; every piecewise
+// caller of the templates uses the unit table, hoir_make_lagrange_table(n, 1)): the same products in the same order
+// as the generic loops -- bit-identical results -- without the subtractions of zero, the multiplications by one
+// and the table loads (12 -> 7 and 27 -> 13 operations; the basis is evaluated ~240 times per training sample).
+template <>
+__device__ __forceinline__ void lagrange<3>(const float* __restrict__, const float* __restrict__, float xi,
+                                            float* __restrict__ val) {
+  const float a = xi - 1.f, b = xi + 1.f;
+  val[0] = (xi * a) * 0.5f;
+  val[1] = (b * a) * -1.f;
+  val[2] = (b * xi) * 0.5f;
+}
+template <>
+__device__ __forceinline__ void lagrange_deriv<3>(const float* __restrict__, const float* __restrict__, float xi,
+                                                  float* __restrict__ val, float* __restrict__ der) {
+  const float a = xi - 1.f, b = xi + 1.f;
+  val[0] = (xi * a) * 0.5f;
+  val[1] = (b * a) * -1.f;
+  val[2] = (b * xi) * 0.5f;
+  der[0] = (a + xi) * 0.5f;
+  der[1] = (a + b) * -1.f;
+  der[2] = (xi + b) * 0.5f;
+}
 // runtime-n variants (generic per-layer kernels)
 __device__ __forceinline__ void lagrange_rt(int n, const float* X, const float* D, float xi,
                                             float* val, float* der) {
