@@ -103,8 +103,8 @@ __device__ __forceinline__ void locate(float x, const SegConst& sc, int& id, flo
 __device__ __forceinline__ void locate2(float x, int& id, float& xi) {
   const float t = __fadd_rn(x, 1.f);            // ((x + 1) / 2) * 2: both scalings are exact
   id = t >= 1.f ? 1 : 0;                        // trunc + clamp to {0, 1}; NaN -> 0
-  const float q = __fsub_rn(x, id ? 0.f : -1.f);
-  xi = __fsub_rn(__fmul_rn(2.f, q), 1.f);
+  const float q = id ? x : t;                   // x - x_min: x - 0, or x - (-1) = t (the same rounding)
+  xi = __fmaf_rn(2.f, q, -1.f);                 // 2 q is exact, so the fused form rounds once exactly like 2 q - 1
 }
 
 // y[O] += sum_j l[j] * W[(base + j)][0..OP)   (W row-major, OP floats per node, 16B aligned)
