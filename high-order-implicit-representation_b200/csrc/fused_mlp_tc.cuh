@@ -195,13 +195,25 @@ __device__ __forceinline__ float group_sum(float v, float* xsamp, int hf, int wa
 // MaxAbsNormalization of a 40-wide row split over a thread group (W values each); first index wins ties.
 template <int W, int NQ>
 __device__ __forceinline__ void maxabs_group(float* v, int hf, float eps, float* xsamp, int warp, float& inv_d, int& kidx) {
-  float m = -1.f, vk = 0.f;
-  int k = 0;
+  // arg-max of |v| as a balanced tree (depth log2 W instead of a W-long dependent chain); the left operand wins
+  // ties, so the first index wins exactly like the sequential scan
+  float ma[W], mv[W];
+  int mk[W];
 #pragma unroll
-  for (int i = 0; i < W; ++i) {
-    const float a = fabsf(v[i]);
-    if (a > m) { m = a; k = i; vk = v[i]; }
+  for (int i = 0; i < W; ++i) { ma[i] = fabsf(v[i]); mv[i] = v[i]; mk[i] = i; }
+#pragma unroll
+  for (int n = W; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const bool right = ma[2 * i + 1] > ma[2 * i];
+      ma[i] = right ? ma[2 * i + 1] : ma[2 * i];
+      mv[i] = right ? mv[2 * i + 1] : mv[2 * i];
+      mk[i] = right ? mk[2 * i + 1] : mk[2 * i];
+    }
+    if (n & 1) { ma[n / 2] = ma[n - 1]; mv[n / 2] = mv[n - 1]; mk[n / 2] = mk[n - 1]; }
   }
+  const float m = ma[0], vk = mv[0];
+  const int k = mk[0];
   int kk = hf * W + k;
   kk |= vk > 0.f ? 0 : (vk < 0.f ? 0x10000 : 0x20000);
   xsamp[hf * TS * 4] = m;

@@ -193,8 +193,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // positions_from_mesh (A.6) for one pixel; out[2*rotations].
 __device__ __forceinline__ void mesh_position(const hoir_mesh_desc& m, long long pixel,
                                               float* __restrict__ out, int max_rot) {
-  int row = (int)(pixel / m.cols);
-  int col = (int)(pixel - (long long)row * m.cols);
+  int row, col;
+  if (pixel < 0x7fffffffLL) {   // 32-bit division (a quarter of the instructions of the 64-bit one) whenever it fits
+    row = (int)((unsigned)pixel / (unsigned)m.cols);
+    col = (int)((unsigned)pixel - (unsigned)row * (unsigned)m.cols);
+  } else {
+    row = (int)(pixel / m.cols);
+    col = (int)(pixel - (long long)row * m.cols);
+  }
   float xv = (float)row, yv = (float)col;
   if (m.normalize_mode == 1) {
     float ms = (float)max(m.rows, m.cols);
