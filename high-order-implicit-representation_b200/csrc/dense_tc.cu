@@ -624,8 +624,13 @@ int hoir_dense_tc_backward(const void* entry, const hoir_layer_desc* d, long lon
     const size_t smem = 4 * GW_U_BYTES + 4 * 8192 + 512;
     HOIR_CHECK_CUDA(cudaFuncSetAttribute(e.gw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nmb = (p.nch + 3) / 4;
-    long long slices = (2LL * dense_sms() + nmb - 1) / nmb;
-    const long long max_slices = (B + 4 * GW_UNIT - 1) / (4 * GW_UNIT);
+    // one wave of two CTAs per SM -- but every CTA flushes its whole [128 x OUTP] accumulator with global adds, so
+    // a slice should amortise that (and the TMEM / barrier prologue) over a dozen units
+    long long slices = (2LL * dense_sms()) / nmb;
+    // measured: a single 128-column block cut into 296 slices of 7 units costs 128 us, 85 slices of 24 units 83 us;
+    // with two or more blocks, halving the CTA count to lengthen the slices doubled the time instead
+    const int min_units = nmb == 1 ? 24 : 12;
+    const long long max_slices = (B + (long long)min_units * GW_UNIT - 1) / ((long long)min_units * GW_UNIT);
     if (slices > max_slices) slices = max_slices;
     if (slices < 1) slices = 1;
     long long per = (B + slices - 1) / slices;

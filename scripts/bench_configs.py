@@ -79,7 +79,7 @@ def c3f():
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.rand(B, 4, device=dev, generator=g) * 2 - 1
     y = torch.rand(B, 3, device=dev, generator=g) * 2 - 1
-    ms = timeit(lambda: autograd_step(net, opt, x, y), 5)
+    ms = timeit(lambda: autograd_step(net, opt, x, y), 30)
     report("C3 fourier n_in=31 (hidden 31), 4-40-40-3, batch 2^16 (tcgen05 per-layer kernels + autograd)", B, ms, 319600, "dense_tc.cu: tf32x3 on the tensor pipe, 15 launches per step")
 
 
@@ -99,7 +99,7 @@ def c4():
     def step():
         L.check(lib.hoir_neighborhood_gather(L.dptr(img), 3, 2048, 2048, 3, 3, 1, 0, 12345, B, L.dptr(feat), L.dptr(targ), L.stream_ptr(dev)))
         autograd_step(net, opt, feat, targ)
-    ms = timeit(step, 5)
+    ms = timeit(step, 20)
     report("C4 interpolator continuous n=2, 216-50-50-50-27, 2048^2 image, batch 2^16 patches (gather + slab dL/dw + tcgen05 hidden layers)",
            B, ms, 162600, "layer 0 = 2.2 MB gather table (CUDA cores); hidden and output layers on tcgen05")
     ms = timeit(lambda: H.neighborhood_sample_generator(net, img, 3, 3), 3)
