@@ -91,3 +91,23 @@ def test_c5_render_tiles_are_independent_of_the_sharding():
         parts.append(tr.render(rows, cols, 2, first_pixel=first, count=count))
     assert torch.equal(torch.cat(parts), whole)
     assert torch.isfinite(whole).all()
+
+
+@pytest.mark.parametrize("name", ["C2", "C3d"])
+def test_c2_full_step_mesh_path_equals_explicit_batch_path(name):
+    """C2 / C3 at the BASELINE size: 2^20 pixels of a 4096 x 4096 image.  The in-kernel coordinate / uint8-target path
+    with the run-merged layer-0 owner walk must give the same loss and gradients as the explicit (x, y) batch of the
+    same pixels, which takes the two-pass layer-0 path (workspace stream + segment-sorted second pass)."""
+    net = _net(MLP_KW[name])
+    tr = H.FusedTrainer(net, lr=0.0, keep_grads=True)
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (4096, 4096, 3), generator=g, dtype=torch.uint8).cuda()
+    B, first = 1 << 20, 5 * (1 << 20) + 4096 * 3 + 17           # not tile aligned
+    loss_mesh = tr.train_step_mesh(img, 2, first, B).clone()
+    g_mesh = tr.flat_g[:-1].clone()
+    flat, pos, _ = H.image_to_dataset(img, rotations=2)
+    x, y = pos[first:first + B].contiguous(), flat[first:first + B].contiguous()
+    loss_x = tr.train_step(x, y).clone()
+    g_x = tr.flat_g[:-1].clone()
+    assert abs(loss_mesh.item() - loss_x.item()) <= 1e-6 * abs(loss_x.item())
+    assert rel_err(g_mesh, g_x) <= 2e-5                          # fp32 atomics: summation order differs
