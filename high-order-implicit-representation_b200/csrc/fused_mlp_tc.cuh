@@ -229,7 +229,7 @@ __device__ __forceinline__ void maxabs_group(float* v, int hf, float eps, float*
   }
   bar_group<NQ>(warp);
   kidx = kg;
-  inv_d = __fdiv_rn(1.f, __fadd_rn(mg, eps));
+  inv_d = __frcp_rn(__fadd_rn(mg, eps));                // the correctly rounded reciprocal, like 1 / d
 #pragma unroll
   for (int i = 0; i < W; ++i) v[i] *= inv_d;
 }
@@ -256,7 +256,7 @@ __device__ __forceinline__ void maxabs_pair(float* v, int hf, float eps, float* 
   const bool other = (mo > m) || (mo == m && hf == 1);
   m = other ? mo : m;
   kidx = other ? ko : kk;
-  inv_d = __fdiv_rn(1.f, __fadd_rn(m, eps));
+  inv_d = __frcp_rn(__fadd_rn(m, eps));
 #pragma unroll
   for (int i = 0; i < W; ++i) v[i] *= inv_d;
 }

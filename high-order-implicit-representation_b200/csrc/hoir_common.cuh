@@ -203,9 +203,16 @@ __device__ __forceinline__ void mesh_position(const hoir_mesh_desc& m, long long
   }
   float xv = (float)row, yv = (float)col;
   if (m.normalize_mode == 1) {
-    float ms = (float)max(m.rows, m.cols);
-    xv = __fmul_rn(__fsub_rn(__fdiv_rn(xv, ms), 0.5f), 2.f);
-    yv = __fmul_rn(__fsub_rn(__fdiv_rn(yv, ms), 0.5f), 2.f);
+    const int msi = max(m.rows, m.cols);
+    const float ms = (float)msi;
+    if ((msi & (msi - 1)) == 0) {   // power of two (4096 ...): the division is an exact scaling, bit-identical
+      const float inv = __int_as_float(0x7f000000 - __float_as_int(ms));   // 2^-k from 2^k: exponent arithmetic
+      xv = __fmul_rn(__fsub_rn(__fmul_rn(xv, inv), 0.5f), 2.f);
+      yv = __fmul_rn(__fsub_rn(__fmul_rn(yv, inv), 0.5f), 2.f);
+    } else {
+      xv = __fmul_rn(__fsub_rn(__fdiv_rn(xv, ms), 0.5f), 2.f);
+      yv = __fmul_rn(__fsub_rn(__fdiv_rn(yv, ms), 0.5f), 2.f);
+    }
   } else if (m.normalize_mode == 2) {
     xv = __fsub_rn(__fmul_rn(__fdiv_rn(xv, (float)(m.rows - 1)), 2.f), 1.f);
     yv = __fsub_rn(__fmul_rn(__fdiv_rn(yv, (float)(m.cols - 1)), 2.f), 1.f);
@@ -214,8 +221,15 @@ __device__ __forceinline__ void mesh_position(const hoir_mesh_desc& m, long long
   for (int r = 0; r < HOIR_MAX_ROTATIONS; ++r) {
     if (r < max_rot && r < m.rotations) {
       float rx = m.rot_x[r], ry = m.rot_y[r], rs = m.rot_sum[r];
-      out[2 * r] = __fdiv_rn(__fadd_rn(__fmul_rn(rx, xv), __fmul_rn(ry, yv)), rs);
-      out[2 * r + 1] = __fdiv_rn(__fsub_rn(__fmul_rn(rx, yv), __fmul_rn(ry, xv)), rs);
+      const float u = __fadd_rn(__fmul_rn(rx, xv), __fmul_rn(ry, yv));
+      const float v = __fsub_rn(__fmul_rn(rx, yv), __fmul_rn(ry, xv));
+      if (rs == 1.f) {              // rotation 0 (cos 0 + sin 0 = 1): x / 1 is x
+        out[2 * r] = u;
+        out[2 * r + 1] = v;
+      } else {
+        out[2 * r] = __fdiv_rn(u, rs);
+        out[2 * r + 1] = __fdiv_rn(v, rs);
+      }
     }
   }
 }
