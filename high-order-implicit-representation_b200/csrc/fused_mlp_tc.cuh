@@ -633,7 +633,7 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
       //      latency (5 x (15 MMAs + hand-overs) ~ 4 k cycles) would otherwise sit on this path.
 #pragma unroll
       for (int c = 0; c < P::NCH; ++c) {
-        if (c >= PRE || n_tile == 0) stage_chunk(c);
+        if (n_tile == 0) stage_chunk(c);              // later tiles: all chunks were staged during the previous tile
       }
       // ---- a1 tile for the helpers (dL/dw1 units) and the T epilogue.  Its buffer is free once the helpers have
       //      staged its previous occupant and every owner of the previous tile's layer-0 walk is done (the walk
@@ -825,6 +825,10 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
           for (int k = tid; k < nrow * (HID / 4); k += NSAMPLE_THREADS) dst[k] = src[k];
         }
         mbar_arrive(&bars[B_OWNDONE]);
+        if (has_next) {
+#pragma unroll
+          for (int c = PRE; c < P::NCH; ++c) stage_chunk(c);
+        }
         continue;
       }
       // ---- otherwise: owners (input, 4 outputs, sample group) walk the tile, run-merged global atomics
@@ -897,6 +901,10 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
       }
       mbar_arrive(&bars[B_OWNDONE]);                  // (release) this thread is done with the walk tiles; the next
                                                       // tile waits for all 256 before it rewrites a1 / a2
+      if (has_next) {                                 // the remaining forward chunks of the next tile
+#pragma unroll
+        for (int c = PRE; c < P::NCH; ++c) stage_chunk(c);
+      }
     }
     // ---- flush: loss, dL/dw2 (smem), dL/dw1 (TMEM accumulators)
     if (p.gy_ext == nullptr && hf == 0) {
