@@ -287,8 +287,8 @@ def main():
         roofline = {"bound": "fp32_ffma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture
-                    # (profiles/r1f_tc_fused_ncu_summary.txt): the uint8 image block + weights + optimizer state
-                    "traffic": 4047872,
+                    # (profiles/r1g_tc_fused_ncu_summary.txt): the uint8 image block + weights + optimizer state
+                    "traffic": 4049920,
                     "peak_source": "hoir_ffma_peak micro-kernel measured in this run (MEASURED_PEAKS.json has no "
                                    "FP32 entry); best of register-form / constant-form FFMA",
                     "peak_ffma_rrr": peaks["ffma_rrr"], "peak_ffma_const": peaks["ffma_const"],
