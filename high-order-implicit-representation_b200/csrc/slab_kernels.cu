@@ -42,7 +42,7 @@ __device__ __forceinline__ void slab_eval(const PARAMS& p, float xv, int& base, 
 
 constexpr int SLAB_THREADS = 256;
 
-constexpr int GW_BLK = 64;   // samples per staged block
+constexpr int GW_BLK = 32;   // samples per staged block (32: slab + staging fit twice per SM -> 16 warps)
 
 template <int N>
 __global__ void __launch_bounds__(SLAB_THREADS) slab_gw_kernel(const SlabParams p) {
