@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const DensePara
 }
 
 // ---- dL/dw -----------------------------------------------------------------------------------------------
-constexpr int GW_UNIT = 32, GW_WORKERS = 128, GW_THREADS = 160;
+constexpr int GW_UNIT = 32, GW_WORKERS = 256, GW_THREADS = GW_WORKERS + 32, GW_MMAW = GW_WORKERS / 32;   // 8 worker warps + MMA warp
 constexpr uint32_t GW_U_RS = 128 / 32 * 512, GW_U_BYTES = GW_UNIT / 4 * GW_U_RS;   // 2048, 16384
 enum { GB_UFULL0 = 0, GB_UFULL1, GB_UEMPTY0, GB_UEMPTY1, GB_DONE, GB_COUNT };
 
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
   const long long b_hi = b_lo + per_slice < p.B ? b_lo + per_slice : p.B;
   const int units = b_hi > b_lo ? (int)((b_hi - b_lo + GW_UNIT - 1) / GW_UNIT) : 0;
 
-  if (warp == 4) {
+  if (warp == GW_MMAW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(64));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
   fence_after();
   const uint32_t tmem = *tmem_base_s;
 
-  if (warp == 4) {
+  if (warp == GW_MMAW) {
     const uint32_t leader = elect_one();
     const uint32_t idesc = make_idesc(128, p.outp, 1, 0);     // A: Phi unit MN-major, B: G^T K-major
     for (int u = 0; u < units; ++u) {
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
       // dL/dy rows of the unit: issued first (16-byte loads when the rows allow it) so that their latency hides
       // behind the basis evaluation below; element (output o, sample sl) -> G^T smem, sl fastest (conflict-free)
       const bool gvec = (p.out_f & 3) == 0;
-      constexpr int GV = 4;                                  // float4 per thread: 32 samples x (outp <= 64) / 4 / 128 threads
+      constexpr int GV = (GW_UNIT * 16 + GW_WORKERS - 1) / GW_WORKERS;   // float4 per thread: 32 samples x (outp <= 64) / 4
       float4 gpre[GV];
       if (gvec) {
 #pragma unroll
@@ -480,11 +480,13 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
     if (units > 0) {
       mbar_wait(&bars[GB_DONE], 0);
       fence_after();
-      // accumulator lane = K-column of this block: chunk tid / 32, slot tid % 32
-      const int c = mb * 4 + (tid >> 5), within = tid & 31, m = within / ND, q = within - m * ND, i = c * IPC + m;
+      // accumulator lane rt = K-column of this block: chunk rt / 32, slot rt % 32; warps w and w + 4 share the
+      // lane quadrant w & 3 and take alternating groups of 16 output columns
+      const int rt = tid & 127;
+      const int c = mb * 4 + (rt >> 5), within = rt & 31, m = within / ND, q = within - m * ND, i = c * IPC + m;
       const bool valid = c < p.nch && m < IPC && i < p.in_f && q < p.nodes;
-      const uint32_t tm_lane = tmem + ((uint32_t)(warp * 32) << 16);
-      for (int g = 0; g < p.outp; g += 16) {
+      const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+      for (int g = (warp >> 2) * 16; g < p.outp; g += 16 * (GW_WORKERS / 128)) {
         float d[16];
         tmem_ld16(tm_lane + g, d);
         tmem_wait_ld();
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
     }
   }
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+  if (warp == GW_MMAW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
   (void)lane;
 }
 
