@@ -912,7 +912,11 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
   }
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
   const long long tiles = (B + BT - 1) / BT;
-  const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
+  int occ = 1;   // the narrow networks leave room for a second (third) CTA per SM: more warps to hide latency
+  HOIR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e->fwd, BT, e->smem_fwd));
+  if (occ < 1 || getenv("HOIR_GRID_ONE_PER_SM") != nullptr) occ = 1;   // the switch is for A/B measurements
+  const long long cap = (long long)num_sms_fused() * occ;
+  const int grid = (int)(tiles < cap ? tiles : cap);
   e->fwd<<<grid, BT, e->smem_fwd, (cudaStream_t)stream>>>(p);
   HOIR_CHECK_CUDA(cudaGetLastError());
   return HOIR_OK;
@@ -1069,7 +1073,12 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
   const int block = use_q ? e->threads_tc4 : (use_tc ? e->threads_tc : BT), ts = use_tc ? tc::TS : BT;
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (B + ts - 1) / ts;
-  const int grid = (int)(tiles < num_sms_fused() ? tiles : num_sms_fused());
+  int occ = 1;   // persistent grid = every resident CTA slot (the tensor-core kernels fill an SM with one CTA; the
+                 // 10-wide FFMA kernels fit two or three); the cooperative launch needs exactly this bound
+  HOIR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+  if (occ < 1 || getenv("HOIR_GRID_ONE_PER_SM") != nullptr) occ = 1;   // the switch is for A/B measurements
+  const long long cap = (long long)num_sms_fused() * occ;
+  const int grid = (int)(tiles < cap ? tiles : cap);
   if (tail_inside) {
     // the grid barrier needs every CTA resident: cooperative launch (grid <= #SMs, 1 CTA per SM)
     void* args[] = {&p};
