@@ -90,6 +90,13 @@ _EXPORTS = {
                                            C.c_void_p]),
     "hoir_neighborhood_fold": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hoir_radial_uniforms": (C.c_int, [C.c_longlong, C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "hoir_radial_indices": (C.c_int, [C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
+    "hoir_radial_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "hoir_mlp_fused_supported": (C.c_int, [C.POINTER(MlpDesc)]),
     "hoir_mlp_packed_size": (C.c_longlong, [C.POINTER(MlpDesc)]),
     "hoir_mlp_packed_offset": (C.c_longlong, [C.POINTER(MlpDesc), C.c_int]),

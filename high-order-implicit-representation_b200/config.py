@@ -119,3 +119,34 @@ def neighborhood_config(**overrides) -> Config:
     for k, v in overrides.items():
         cfg[k] = v
     return cfg
+
+
+def random_interpolation_config(**overrides) -> Config:
+    """Defaults of /root/reference/config/random_interpolation.yaml + optimizer/adam.yaml (``mlp.input.segments``
+    is the interpolation ``${image_size}``; ``mlp.input.width`` = (3 + 2*rotations) * num_feature_pixels)."""
+    cfg = Config({
+        "folder": "images",
+        "mlp": dict(layer_type="continuous", n=3, n_in=None, n_out=None, n_hidden=None,
+                    periodicity=2.0, rescale_output=False, scale=2.0,
+                    input=dict(segments=64, width=224), output=dict(segments=2, width=3),
+                    hidden=dict(segments=2, layers=2, width=100)),
+        "num_target_pixels": 1, "num_feature_pixels": 32, "split_frac": 0.5, "image_size": 64,
+        "max_epochs": 50, "gpus": 1, "accelerator": "cuda", "batch_size": 256, "train": True, "checkpoint": None,
+        "rotations": 2, "iterations": 10, "all_random": True, "patience": 10, "image": "images/mountains.jpg",
+        "optimizer": dict(name="adam", lr=1e-4, scheduler="plateau", patience=5, factor=0.1, gamma=0.9)})
+    for k, v in overrides.items():
+        cfg[k] = v
+    return cfg
+
+
+def generative_config(**overrides) -> Config:
+    """Defaults of /root/reference/config/generative_config.yaml + optimizer/sparse_lion.yaml."""
+    cfg = Config({
+        "mlp": dict(periodicity=None, rescale_output=False, scale=2.0, width=100, layers=2, segments=2),
+        "embedding_size": 384, "input_size": 2, "output_size": 3, "input_segments": 20, "layer_type": "continuous",
+        "n": 3, "max_epochs": 50, "gpus": 1, "accelerator": "cuda", "lr": 1e-3, "batch_size": 256, "train": True,
+        "checkpoint": None, "rotations": 1,
+        "optimizer": dict(name="sparse_lion", lr=1e-4, scheduler="plateau", patience=10, factor=0.1)})
+    for k, v in overrides.items():
+        cfg[k] = v
+    return cfg

@@ -309,3 +309,56 @@ class Net(nn.Module):
         if map_location is not None:
             net = net.to(map_location)
         return net
+
+
+class GenerativeNetwork(nn.Module):
+    """/root/reference/high_order_implicit_representation/networks.py:132-180: a polynomial (n=2) layer over the text
+    embedding plus a piecewise layer over the pixel position, summed, then a HighOrderMLP.  Every layer runs through
+    the C-ABI layer kernels; the MLP uses the fused whole-network kernel when it has an instantiation."""
+
+    def __init__(self, embedding_size: int, input_size: int, output_size: int, mlp_width: int, mlp_layers: int,
+                 input_segments: int, mlp_segments: int, n: int, normalization: Any = None,
+                 layer_type: str = "continuous"):
+        super().__init__()
+        self.text_layer = high_order_fc_layers(layer_type="polynomial", n=2, in_features=embedding_size,
+                                               out_features=mlp_width)
+        self.position_layer = high_order_fc_layers(layer_type=layer_type, n=n, in_features=input_size,
+                                                   out_features=mlp_width, segments=input_segments)
+        self.mlp = HighOrderMLP(layer_type=layer_type, n=n, in_width=mlp_width, hidden_width=mlp_width,
+                                hidden_layers=mlp_layers, out_width=output_size, in_segments=mlp_segments,
+                                out_segments=mlp_segments, hidden_segments=mlp_segments, normalization=normalization)
+
+    def forward(self, text_embedding: Tensor, position: Tensor) -> Tensor:
+        text_out = self.text_layer(text_embedding)
+        position_out = self.position_layer(position)
+        return self.mlp(text_out + position_out)
+
+
+class GenNet(Net):
+    """networks.py:183-278: the text-to-image model (``batch = (caption embedding, position, colour)``); optimizer and
+    checkpoint handling are Net's."""
+
+    def __init__(self, cfg: Any):
+        nn.Module.__init__(self)
+        cfg = to_cfg(cfg)
+        self.hparams = cfg
+        self.cfg = cfg
+        self.model = GenerativeNetwork(
+            layer_type=cfg.layer_type, embedding_size=cfg.embedding_size, n=cfg.n, input_size=cfg.input_size,
+            output_size=cfg.output_size, mlp_width=cfg.mlp.width, mlp_layers=cfg.mlp.layers,
+            input_segments=cfg.input_segments, mlp_segments=cfg.mlp.segments, normalization=MaxAbsNormalization)
+        initialize_network_polynomial_layers(self.model, max_slope=1.0, max_offset=0.0)
+        self.loss = nn.MSELoss()
+        self.logged = {}
+        self.current_epoch = 0
+        self.global_step = 0
+
+    def forward(self, caption, x):
+        return self.model(caption, x)
+
+    def eval_step(self, batch, name: str):
+        caption, x, color = batch
+        y_hat = self(caption, x.flatten(1))
+        loss = self.loss(y_hat.flatten(), color.flatten())
+        self.log(f"{name}_loss", loss, prog_bar=True)
+        return loss

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HOIR_VERSION 102
+#define HOIR_VERSION 103
 #define HOIR_MAX_LAYERS 8
 #define HOIR_MAX_N 32          /* max basis functions per segment / Fourier terms          */
 #define HOIR_MAX_ROTATIONS 8
@@ -135,6 +135,27 @@ int hoir_neighborhood_gather(const float* image, int C, int H, int W, int width,
  * /root/reference/high_order_implicit_representation/rendering.py:76-95,119 */
 int hoir_neighborhood_fold(const float* predictions, int C, int H, int W, int width, int outside,
                            float alpha, const float* prev_image, float* out_image, void* stream);
+
+/* ---- random interpolation: radial sampler -------------------------------------------------------
+ * For every target pixel k of an S x S image, F interpolation points at random (r, theta):
+ *   dx = trunc(((0.5 r) cos theta) S), dy = trunc(((0.5 r) sin theta) S), reflected at the image borders
+ * (random_symmetric_sample, /root/reference/high_order_implicit_representation/random_sample_dataset.py:211-244).
+ * r / theta [N][F] are caller tensors (r = rand, theta = rand * 2 * pi: the reference's stream) or, when both are
+ * NULL, element e = k*F + f of the Philox4x32-10 stream (seed, offset) -- hoir_radial_uniforms writes that stream
+ * out.  samples [N][2] int32 (x, y) target points, or NULL for the grid order of indices_from_grid (:17-21):
+ * target k is the point (k / S, k % S), pixel x + y*S of a channel plane. */
+int hoir_radial_uniforms(long long n, unsigned long long seed, unsigned long long offset, float* r, float* theta,
+                         void* stream);
+int hoir_radial_indices(int S, int F, long long N, const int* samples, const float* r, const float* theta,
+                        unsigned long long seed, unsigned long long offset, int* xy /* [N][F][2] */, void* stream);
+/* images [M][C][S][S], stripes [P][S][S] (the position planes of positions_from_mesh) ->
+ *   features[m*S*S + k][f] = (image[:, p], stripes[:, p] - stripes[:, t])      [M*S*S][F][C+P]
+ *   targets [m*S*S + k]    = image[:, t]                                      [M*S*S][C]     (may be NULL)
+ * with t the target pixel and p the f-th interpolation point of target k
+ * (random_radial_samples_from_image, random_sample_dataset.py:176-208; r / theta are [M*S*S][F] or NULL) */
+int hoir_radial_sample(const float* images, const float* stripes, int M, int C, int P, int S, int F,
+                       const float* r, const float* theta, unsigned long long seed, unsigned long long offset,
+                       float* features, float* targets, void* stream);
 
 /* ---- fused whole-network path ---------------------------------------------------------------
  * Packed weights: one flat fp32 buffer, layer l at float offset hoir_mlp_packed_offset(l) with

@@ -113,6 +113,32 @@ def c5(tr):
     report("C5 render 8192x8192, C2 model, rotations=2, one GPU (tcgen05 forward kernel, 2 CTAs per SM)", rows * cols, ms, 11280, "12 B/pixel written")
 
 
+def ri():
+    """random_interpolation.yaml: 224-100-100-100-3 continuous n=3 on radial samples of 64 x 64 images."""
+    S, F, rot, M = 64, 32, 2, 16
+    kw = dict(layer_type="continuous", n=3, in_width=F * (3 + 2 * rot), out_width=3, hidden_layers=2, hidden_width=100,
+              in_segments=S, out_segments=2, hidden_segments=2)
+    net = mlp(**kw)
+    opt = H.Adam(net.parameters(), lr=1e-4)
+    imgs = (torch.rand(64, 3, S, S, generator=torch.Generator().manual_seed(0)) * 2 - 1).to(dev)
+    stripes = H.random_sample.stripe_planes(S, rot, dev)
+    ms = timeit(lambda: H.random_radial_samples_from_image(imgs, stripes, S, F), 20)
+    pts = 64 * S * S * F
+    print(json.dumps({"config": "radial sampler, 64 images 64x64, 32 points, rotations=2 (in-kernel Philox)", "points_per_s": pts / ms * 1e3,
+                      "ms": ms, "GB_per_s_written": pts * 28 / ms / 1e6, "note": "28 B written per point; includes the output allocation"}), flush=True)
+    B = M * S * S
+
+    def step():
+        feat, targ = H.random_radial_samples_from_image(imgs[:M], stripes, S, F)
+        autograd_step(net, opt, feat.flatten(1), targ)
+    ms = timeit(step, 10)
+    report("random interpolation: radial sampling + 224-100-100-100-3 continuous n=3 (seg 64 / 2), batch 16 images = 2^16 samples",
+           B, ms, 634200, "per-layer kernels + autograd")
+    model = net
+    ms = timeit(lambda: H.generate_sample_radial(model, features=F, iterations=1, image_size=S, rotations=rot), 10)
+    report("random interpolation inference: one generate_sample_radial application on 64x64", S * S, ms, 256200, "latency-bound (4096 samples)")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c2", "c3d", "c3f", "c4", "c5"]
     C2 = dict(layer_type="continuous", n=3, in_width=4, out_width=3, hidden_layers=1, hidden_width=40,
@@ -124,3 +150,4 @@ if __name__ == "__main__":
     if "c3f" in which: c3f()
     if "c4" in which: c4()
     if "c5" in which: c5(tr)
+    if "ri" in which: ri()
