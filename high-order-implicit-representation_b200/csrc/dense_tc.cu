@@ -33,6 +33,7 @@ using namespace tc;
 struct DenseParams {
   long long B;
   int in_f, out_f, n, nodes, nch, outp, outp8;
+  int ldo, gx_acc;          // row stride of y / gy (an output block of a wider layer: > out_f); gx += instead of =
   float rescale, theta_c, length;
   int odd_is_sin;
   const float* x;
@@ -273,14 +274,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const DensePara
           if (live) {
 #pragma unroll
             for (int o = 0; o < 16; ++o)
-              if (g + o < p.out_f) p.y[b * p.out_f + g + o] = d[o] * p.rescale;
+              if (g + o < p.out_f) p.y[b * p.ldo + g + o] = d[o] * p.rescale;
           }
         }
         fence_before();
         mbar_arrive(&bars[DB_DEMPTY]);
       } else {
         // stage G (scaled dL/dy row, hi | lo); the previous tile's products are complete (its last T chunk was consumed)
-        const float* gr = p.gy + (live ? b : 0) * p.out_f;
+        const float* gr = p.gy + (live ? b : 0) * p.ldo;
         for (int g = 0; g < p.outp8; g += 8) {
           float v[8], lo[8];
 #pragma unroll
@@ -319,7 +320,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(const DensePara
             float acc = 0.f;
 #pragma unroll
             for (int q = 0; q < ND; ++q) acc = fmaf(der[m * ND + q], t[m * ND + q], acc);
-            if (live && i < p.in_f) p.gx[b * p.in_f + i] = acc;
+            if (live && i < p.in_f) {
+              float* gxp = p.gx + b * p.in_f + i;
+              *gxp = p.gx_acc ? *gxp + acc : acc;
+            }
           }
         }
       }
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
       const long long b0 = b_lo + (long long)u * GW_UNIT;
       // dL/dy rows of the unit: issued first (16-byte loads when the rows allow it) so that their latency hides
       // behind the basis evaluation below; element (output o, sample sl) -> G^T smem, sl fastest (conflict-free)
-      const bool gvec = (p.out_f & 3) == 0;
+      const bool gvec = ((p.out_f | p.ldo) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gy) & 15) == 0;
       constexpr int GV = (GW_UNIT * 16 + GW_WORKERS - 1) / GW_WORKERS;   // float4 per thread: 32 samples x (outp <= 64) / 4
       float4 gpre[GV];
       if (gvec) {
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
         for (int r = 0; r < GV; ++r) {
           const int it = tid + r * GW_WORKERS, sl = it % GW_UNIT, o4 = it / GW_UNIT;
           const long long b = b0 + sl;
-          gpre[r] = (b < b_hi && 4 * o4 < p.out_f) ? __ldg(reinterpret_cast<const float4*>(p.gy + b * p.out_f) + o4)
+          gpre[r] = (b < b_hi && 4 * o4 < p.out_f) ? __ldg(reinterpret_cast<const float4*>(p.gy + b * p.ldo) + o4)
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(GW_THREADS, 2) dense_gw_kernel(const DensePara
         for (int it = tid; it < p.outp * GW_UNIT; it += GW_WORKERS) {
           const int sl = it % GW_UNIT, o = it / GW_UNIT;
           const long long b = b0 + sl;
-          const float v = (b < b_hi && o < p.out_f) ? __ldg(p.gy + b * p.out_f + o) * p.rescale : 0.f;
+          const float v = (b < b_hi && o < p.out_f) ? __ldg(p.gy + b * p.ldo + o) * p.rescale : 0.f;
           const uint32_t off = chunk_off((uint32_t)o, (uint32_t)sl);
           *reinterpret_cast<float*>(gr + off) = v;
           *reinterpret_cast<float*>(gl + off) = tf32_lo(v);
@@ -563,6 +567,7 @@ static int dense_fill(const void* entry, const hoir_layer_desc* d, long long B, 
   p->B = B;
   p->in_f = d->in_features;
   p->out_f = d->out_features;
+  p->ldo = d->out_features;
   p->n = d->n;
   p->nodes = hoir_layer_nodes(d);
   p->nch = (d->in_features + e.ipc - 1) / e.ipc;
@@ -589,13 +594,15 @@ static int dense_fill(const void* entry, const hoir_layer_desc* d, long long B, 
   return HOIR_OK;
 }
 
+// ldo: row stride of y (>= out_features; an output block of a wider layer)
 int hoir_dense_tc_forward(const void* entry, const hoir_layer_desc* d, long long B, const float* x, const float* w,
-                          float* y, cudaStream_t stream) {
+                          float* y, int ldo, cudaStream_t stream) {
   const DenseEntry& e = *static_cast<const DenseEntry*>(entry);
   DenseParams p;
   if (int err = dense_fill(entry, d, B, w, &p, stream)) return err;
   p.x = x;
   p.y = y;
+  p.ldo = ldo;
   const size_t smem = DT_STAGES * 16384 + 512;
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(e.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (B + DT_TILE - 1) / DT_TILE;
@@ -605,14 +612,17 @@ int hoir_dense_tc_forward(const void* entry, const hoir_layer_desc* d, long long
   return HOIR_OK;
 }
 
+// ldo: row stride of gy; gx_acc: add this block's dL/dx to gx instead of overwriting it
 int hoir_dense_tc_backward(const void* entry, const hoir_layer_desc* d, long long B, const float* x, const float* w,
-                           const float* gy, float* gx, float* gw, cudaStream_t stream) {
+                           const float* gy, int ldo, float* gx, int gx_acc, float* gw, cudaStream_t stream) {
   const DenseEntry& e = *static_cast<const DenseEntry*>(entry);
   DenseParams p;
   if (int err = dense_fill(entry, d, B, w, &p, stream)) return err;
   p.x = x;
   p.gy = gy;
+  p.ldo = ldo;
   p.gx = gx;
+  p.gx_acc = gx_acc;
   p.gw = gw;
   if (gx != nullptr) {
     const size_t smem = DT_STAGES * 16384 + 512;

@@ -11,15 +11,15 @@
 // dense_tc.cu: tensor-core path for layers whose densified basis expansion is a dense contraction
 const void* hoir_dense_tc_find(const hoir_layer_desc* d, long long B);
 int hoir_dense_tc_forward(const void* entry, const hoir_layer_desc* d, long long B, const float* x, const float* w,
-                          float* y, cudaStream_t stream);
+                          float* y, int ldo, cudaStream_t stream);
 int hoir_dense_tc_backward(const void* entry, const hoir_layer_desc* d, long long B, const float* x, const float* w,
-                           const float* gy, float* gx, float* gw, cudaStream_t stream);
+                           const float* gy, int ldo, float* gx, int gx_acc, float* gw, cudaStream_t stream);
 
 // slab_kernels.cu: shared-memory slab kernels for piecewise layers with many segments
 bool hoir_slab_eligible(const hoir_layer_desc* d, long long B);
 bool hoir_slab_forward_eligible(const hoir_layer_desc* d, long long B);
-int hoir_slab_forward(const hoir_layer_desc* d, long long B, const float* x, const float* wp, float* y, cudaStream_t stream);
-int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, const float* gy, float* gw, cudaStream_t stream);
+int hoir_slab_forward(const hoir_layer_desc* d, long long B, const float* x, const float* wp, float* y, int ldo, cudaStream_t stream);
+int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, const float* gy, int ldo, float* gw, cudaStream_t stream);
 
 namespace {
 
@@ -395,6 +395,24 @@ static int pack_weights(const LayerParams& p, const float* w, float** packed, cu
   return HOIR_OK;
 }
 
+// A layer wider than the 64 outputs the tensor-core / slab kernels hold per CTA is cut into output blocks: the
+// boundary layout [out][in][nodes] makes every block of w (and of dL/dw) a contiguous sub-tensor, and y / dL/dy
+// are addressed with the full row stride.  Returns the number of blocks (0: do not split) and the block width
+// (a multiple of 4, so 16-byte accesses stay aligned when out is).  mode 1: dense blocks, 2: slab blocks.
+static int output_blocks(const hoir_layer_desc* d, long long B, bool forward, int* width, int* mode) {
+  const int out = d->out_features;
+  if (out <= 64 || out > 1024) return 0;
+  const int nb = (out + 63) / 64;
+  const int ob = ((out + nb - 1) / nb + 3) & ~3;
+  if (out - (nb - 1) * ob <= 0) return 0;
+  hoir_layer_desc d2 = *d;
+  d2.out_features = ob;
+  *width = ob;
+  if (hoir_dense_tc_find(&d2, B) != nullptr) { *mode = 1; return nb; }
+  if (forward ? hoir_slab_forward_eligible(&d2, B) : hoir_slab_eligible(&d2, B)) { *mode = 2; return nb; }
+  return 0;
+}
+
 extern "C" int hoir_layer_forward(const hoir_layer_desc* d, long long B, const float* x,
                                   const float* w, float* y, void* stream) {
   LayerParams p;
@@ -402,13 +420,34 @@ extern "C" int hoir_layer_forward(const hoir_layer_desc* d, long long B, const f
   if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_layer_forward");
   if (B == 0) return HOIR_OK;
   if (!x || !w || !y) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_layer_forward");
-  if (const void* dense = hoir_dense_tc_find(d, B)) return hoir_dense_tc_forward(dense, d, B, x, w, y, (cudaStream_t)stream);
+  if (const void* dense = hoir_dense_tc_find(d, B))
+    return hoir_dense_tc_forward(dense, d, B, x, w, y, d->out_features, (cudaStream_t)stream);
+  {
+    int ob = 0, mode = 0;
+    const int nb = output_blocks(d, B, true, &ob, &mode);
+    for (int k = 0; k < nb; ++k) {
+      hoir_layer_desc d2 = *d;
+      const int o0 = k * ob;
+      d2.out_features = min(ob, d->out_features - o0);
+      const float* wk = w + (size_t)o0 * p.in_f * p.nodes;
+      if (mode == 1) {
+        if (int e = hoir_dense_tc_forward(hoir_dense_tc_find(&d2, B), &d2, B, x, wk, y + o0, d->out_features, (cudaStream_t)stream)) return e;
+      } else {
+        LayerParams p2;
+        if (int e = make_params(&d2, &p2)) return e;
+        float* wp2 = nullptr;
+        if (int e = pack_weights(p2, wk, &wp2, (cudaStream_t)stream)) return e;
+        if (int e = hoir_slab_forward(&d2, B, x, wp2, y + o0, d->out_features, (cudaStream_t)stream)) return e;
+      }
+    }
+    if (nb > 0) return HOIR_OK;
+  }
   const size_t per_sample = (size_t)p.in_f * (p.n + 2) * sizeof(float);
   if (per_sample > (size_t)kSmemBudget)
     return hoir_set_error(HOIR_EUNSUPPORTED, "in_features*(n+2) exceeds the shared-memory tile", "hoir_layer_forward");
   float* wp = nullptr;
   if (int e = pack_weights(p, w, &wp, (cudaStream_t)stream)) return e;
-  if (hoir_slab_forward_eligible(d, B)) return hoir_slab_forward(d, B, x, wp, y, (cudaStream_t)stream);
+  if (hoir_slab_forward_eligible(d, B)) return hoir_slab_forward(d, B, x, wp, y, d->out_features, (cudaStream_t)stream);
   int TB = (int)min((size_t)64, (size_t)kSmemBudget / per_sample);
   if ((long long)TB > B) TB = (int)B;
   const size_t smem = per_sample * TB;
@@ -429,7 +468,26 @@ extern "C" int hoir_layer_backward(const hoir_layer_desc* d, long long B, const 
   if (B == 0 || (gx == nullptr && gw == nullptr)) return HOIR_OK;
   if (!x || !w || !gy) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_layer_backward");
   if (const void* dense = hoir_dense_tc_find(d, B))
-    return hoir_dense_tc_backward(dense, d, B, x, w, gy, gx, gw, (cudaStream_t)stream);
+    return hoir_dense_tc_backward(dense, d, B, x, w, gy, d->out_features, gx, 0, gw, (cudaStream_t)stream);
+  bool gw_done = false;
+  {
+    int ob = 0, mode = 0;
+    const int nb = output_blocks(d, B, false, &ob, &mode);
+    for (int k = 0; k < nb; ++k) {
+      hoir_layer_desc d2 = *d;
+      const int o0 = k * ob;
+      d2.out_features = min(ob, d->out_features - o0);
+      const size_t woff = (size_t)o0 * p.in_f * p.nodes;
+      if (mode == 1) {
+        if (int e = hoir_dense_tc_backward(hoir_dense_tc_find(&d2, B), &d2, B, x, w + woff, gy + o0, d->out_features, gx, k > 0,
+                                           gw ? gw + woff : nullptr, (cudaStream_t)stream)) return e;
+      } else if (gw != nullptr) {
+        if (int e = hoir_slab_grad_w(&d2, B, x, gy + o0, d->out_features, gw + woff, (cudaStream_t)stream)) return e;
+      }
+    }
+    if (nb > 0 && (mode == 1 || gx == nullptr)) return HOIR_OK;
+    gw_done = nb > 0;        // slab blocks: dL/dx (if wanted) still goes through the tile kernel below
+  }
   const int OP = (p.out_f + 3) & ~3;
   const size_t per_sample = ((size_t)p.in_f * (2 * p.n + 2) + OP) * sizeof(float);
   if (per_sample + 16 > (size_t)kSmemBudget)
@@ -440,9 +498,10 @@ extern "C" int hoir_layer_backward(const hoir_layer_desc* d, long long B, const 
   // many node windows and a big batch: dL/dw through the input-owner kernel (no per-sample atomics)
   const size_t slab = (size_t)p.nodes * p.out_f * sizeof(float);
   const bool piecewise = p.kind == HOIR_CONTINUOUS || p.kind == HOIR_DISCONTINUOUS;
-  float* gw_tile = gw;
-  if (gw != nullptr && hoir_slab_eligible(d, B)) {
-    if (int e = hoir_slab_grad_w(d, B, x, gy, gw, (cudaStream_t)stream)) return e;
+  float* gw_tile = gw_done ? nullptr : gw;
+  if (gw_done) {
+  } else if (gw != nullptr && hoir_slab_eligible(d, B)) {
+    if (int e = hoir_slab_grad_w(d, B, x, gy, d->out_features, gw, (cudaStream_t)stream)) return e;
     gw_tile = nullptr;
     if (gx == nullptr) return HOIR_OK;
   } else if (gw != nullptr && piecewise && p.segments > 8 && B >= 4096 && slab <= 200 * 1024 / 2) {

@@ -15,6 +15,7 @@
 // Algorithm: oracle/hol_oracle.py.
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include "hoir_common.cuh"
 #include "tc_common.cuh"
 
@@ -23,6 +24,7 @@ namespace {
 struct SlabParams {
   long long B, per_slice;
   int kind, n, segments, stride, in_f, out_f, nodes, op, gi;
+  int ldo;                  // row stride of gy (an output block of a wider layer: > out_f)
   float segf, inv_segf, rescale;
   int pow2;
   const float* x;
@@ -44,7 +46,20 @@ constexpr int SLAB_THREADS = 256;
 
 constexpr int GW_BLK = 32;   // samples per staged block (32: slab + staging fit twice per SM -> 16 warps)
 
-template <int N>
+// HALF: a per-input slab so large that fewer than five inputs fit -- two warps share an input, each owning 32 of its
+// output columns (one float per lane instead of a float2), so that more than gi of the 8 warps have work
+template <bool HALF>
+__device__ __forceinline__ float2 slab_ld(const float* q) {
+  if (HALF) return make_float2(*q, 0.f);
+  return *reinterpret_cast<const float2*>(q);
+}
+template <bool HALF>
+__device__ __forceinline__ void slab_st(float* q, float2 v) {
+  if (HALF) *q = v.x;
+  else *reinterpret_cast<float2*>(q) = v;
+}
+
+template <int N, bool HALF>
 __global__ void __launch_bounds__(SLAB_THREADS) slab_gw_kernel(const SlabParams p) {
   extern __shared__ __align__(16) float slab[];
   const int i0 = blockIdx.x * p.gi;
@@ -60,29 +75,39 @@ __global__ void __launch_bounds__(SLAB_THREADS) slab_gw_kernel(const SlabParams 
   const long long b_lo = (long long)blockIdx.y * p.per_slice;
   const long long b_hi = min(p.B, b_lo + p.per_slice);
   const int nblk = b_hi > b_lo ? (int)((b_hi - b_lo + GW_BLK - 1) / GW_BLK) : 0;
-  const bool act = 2 * lane < p.out_f;
+  const int inp = HALF ? warp >> 1 : warp;                     // the input this warp accumulates for
+  const int col = HALF ? (warp & 1) * 32 + lane : 2 * lane;    // its first output column
+  const bool act = col < p.out_f;
   const int g_elems = GW_BLK * p.out_f;
-  const bool vec = p.op == p.out_f;          // even out: the staged block is a straight 16-byte copy (cp.async)
+  const bool dense_rows = p.ldo == p.out_f;
+  // 16-byte cp.async staging: a straight copy of the block (contiguous rows, even out), or row by row when the rows
+  // are strided and every row start / length is a multiple of 4 floats
+  const bool vec = p.op == p.out_f && (dense_rows || (((p.out_f | p.ldo) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gy) & 15) == 0));
   // dL/dy rows of block k -> sG[k & 1] (asynchronous when vec)
   auto stage_g = [&](int k) {
     const long long b0 = b_lo + (long long)k * GW_BLK;
     float* g = sG + (k & 1) * GW_BLK * p.op;
     const long long avail = (b_hi - b0) * p.out_f;
-    const float* src = p.gy + b0 * p.out_f;
+    const float* src = p.gy + b0 * p.ldo;
     if (vec) {
       for (int e = threadIdx.x * 4; e < g_elems; e += SLAB_THREADS * 4) {
+        const float* se = src + e;
+        if (!dense_rows) {
+          const int sl = e / p.out_f;
+          se = src + (long long)sl * p.ldo + (e - sl * p.out_f);
+        }
         if (e + 3 < avail) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(g + e)), "l"(src + e) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(g + e)), "l"(se) : "memory");
         } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) g[e + c] = e + c < avail ? __ldg(src + e + c) : 0.f;
+          for (int c = 0; c < 4; ++c) g[e + c] = e + c < avail ? __ldg(se + c) : 0.f;
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     } else {
       for (int e = threadIdx.x; e < g_elems; e += SLAB_THREADS) {
         const int sl = e / p.out_f, o = e - sl * p.out_f;
-        g[sl * p.op + o] = e < avail ? __ldg(src + e) : 0.f;
+        g[sl * p.op + o] = e < avail ? __ldg(src + (long long)sl * p.ldo + o) : 0.f;
       }
     }
   };
@@ -93,7 +118,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) slab_gw_kernel(const SlabParams 
 #pragma unroll
     for (int h = 0; h < GW_BLK / 32; ++h) {
       const long long b = b0 + h * 32 + lane;
-      xreg[h] = (warp < gi && b < b_hi) ? __ldg(p.x + b * p.in_f + i0 + warp) : 0.f;
+      xreg[h] = (inp < gi && b < b_hi) ? __ldg(p.x + b * p.in_f + i0 + inp) : 0.f;
     }
   };
   auto finish_rec = [&](int k) {
@@ -113,33 +138,64 @@ __global__ void __launch_bounds__(SLAB_THREADS) slab_gw_kernel(const SlabParams 
     stage_g(0);
     load_x(0);
   }
-  // warp w owns input i0 + w: exclusive slab rows, plain read-modify-write, no atomics
-  float* sl = slab + (size_t)warp * row_f + 2 * lane;
+  // warp w owns input i0 + w (HALF: 32 columns of input i0 + w/2): exclusive slab cells, plain read-modify-write
+  float* sl = slab + (size_t)inp * row_f + col;
   for (int k = 0; k < nblk; ++k) {
-    if (warp < gi) finish_rec(k);
+    if (inp < gi) finish_rec(k);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();                    // block k staged; everyone is done with block k - 1
     if (k + 1 < nblk) {
       stage_g(k + 1);
       load_x(k + 1);
     }
-    if (warp < gi) {
-      const float* g = sG + (k & 1) * GW_BLK * p.op + 2 * lane;
+    if (inp < gi) {
+      const float* g = sG + (k & 1) * GW_BLK * p.op + col;
       const float4* rec = sRec + ((k & 1) * (SLAB_THREADS / 32) + warp) * GW_BLK;
-#pragma unroll 4
-      for (int s = 0; s < GW_BLK; ++s) {
-        const float4 rc = rec[s];
-        const float l[3] = {rc.y, rc.z, rc.w};
-        if (act) {
-          const float2 g2 = *reinterpret_cast<const float2*>(g + s * p.op);
-          float* row = sl + __float_as_int(rc.x) * p.op;
+      constexpr int NJ = N < 3 ? N : 3;
+      // K samples whose node windows do not overlap: all loads, then all FMAs, then all stores -- the K
+      // read-modify-write chains overlap instead of running back to back (the compiler cannot reorder them itself:
+      // it must assume the rows alias)
+      auto rmw = [&](auto kc, const float4* rc, int s0) {
+        constexpr int K = decltype(kc)::value;
+        if (!act) return;
+        float2 a[K][NJ], g2[K];
+        float* row[K];
 #pragma unroll
-          for (int j = 0; j < (N < 3 ? N : 3); ++j) {
-            float2 a = *reinterpret_cast<float2*>(row + j * p.op);
-            a.x = fmaf(l[j], g2.x, a.x);
-            a.y = fmaf(l[j], g2.y, a.y);
-            *reinterpret_cast<float2*>(row + j * p.op) = a;
+        for (int u = 0; u < K; ++u) {
+          g2[u] = slab_ld<HALF>(g + (s0 + u) * p.op);
+          row[u] = sl + __float_as_int(rc[u].x) * p.op;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) a[u][j] = slab_ld<HALF>(row[u] + j * p.op);
+        }
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+          const float l[3] = {rc[u].y, rc[u].z, rc[u].w};
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            a[u][j].x = fmaf(l[j], g2[u].x, a[u][j].x);
+            a[u][j].y = fmaf(l[j], g2[u].y, a[u][j].y);
           }
+        }
+#pragma unroll
+        for (int u = 0; u < K; ++u)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) slab_st<HALF>(row[u] + j * p.op, a[u][j]);
+      };
+      auto apart = [&](const float4& a, const float4& b) {   // warp-uniform: the records are broadcast reads
+        const int d = __float_as_int(a.x) - __float_as_int(b.x);
+        return d >= NJ || d <= -NJ;
+      };
+#pragma unroll 2
+      for (int s = 0; s < GW_BLK; s += 4) {
+        const float4 rc[4] = {rec[s], rec[s + 1], rec[s + 2], rec[s + 3]};
+        const bool p01 = apart(rc[0], rc[1]), p23 = apart(rc[2], rc[3]);
+        if (p01 && p23 && apart(rc[0], rc[2]) && apart(rc[0], rc[3]) && apart(rc[1], rc[2]) && apart(rc[1], rc[3])) {
+          rmw(std::integral_constant<int, 4>{}, rc, s);
+        } else {
+          if (p01) rmw(std::integral_constant<int, 2>{}, rc, s);
+          else { rmw(std::integral_constant<int, 1>{}, rc, s); rmw(std::integral_constant<int, 1>{}, rc + 1, s + 1); }
+          if (p23) rmw(std::integral_constant<int, 2>{}, rc + 2, s + 2);
+          else { rmw(std::integral_constant<int, 1>{}, rc + 2, s + 2); rmw(std::integral_constant<int, 1>{}, rc + 3, s + 3); }
         }
       }
     }
@@ -165,6 +221,7 @@ constexpr int FW_WARPS = 16, FW_TILE = FW_WARPS * 32, FW_THREADS = (FW_WARPS + 1
 struct FwdParams {
   long long B;
   int n, segments, stride, in_f, out_f, nodes, op4, gi, ngroups;
+  int ldo;              // row stride of y
   float segf, inv_segf, rescale;
   int pow2;
   uint32_t stage_bytes;
@@ -267,8 +324,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1) slab_fwd_kernel(const FwdParams
 #pragma unroll
       for (int s = 0; s < 32; ++s) {
         if (b0 + s < p.B) {
-          float* yo = p.y + (b0 + s) * p.out_f + 2 * lane;
-          if (act1 && (p.out_f & 1) == 0) {
+          float* yo = p.y + (b0 + s) * p.ldo + 2 * lane;
+          if (act1 && ((p.out_f | p.ldo) & 1) == 0) {
             *reinterpret_cast<float2*>(yo) = make_float2(acc[s].x * p.rescale, acc[s].y * p.rescale);
           } else {
             yo[0] = acc[s].x * p.rescale;
@@ -346,22 +403,27 @@ bool hoir_slab_eligible(const hoir_layer_desc* d, long long B) {
   return per_input <= kSlabBudget;
 }
 
-int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, const float* gy, float* gw,
+int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, const float* gy, int ldo, float* gw,
                      cudaStream_t stream) {
   SlabParams p;
   slab_fill(d, B, &p, SLAB_THREADS / 32);
   p.x = x;
   p.gy = gy;
+  p.ldo = ldo;
   p.gw = gw;
   const size_t extra = 2 * GW_BLK * p.op * sizeof(float) + 2 * (SLAB_THREADS / 32) * GW_BLK * sizeof(float4) + 64;
+  // measured (224 -> 52 block, 129 nodes, gi = 3): HALF is 10 % SLOWER than leaving 5 warps idle -- every warp still
+  // walks all the samples of a block, so the work per warp does not shrink; kept behind a switch for experiments
+  static const bool half_on = getenv("HOIR_SLAB_HALF") != nullptr;
+  const bool half = half_on && p.gi <= 4 && p.out_f > 32;
   switch (d->n) {
-    case 2: return slab_launch(slab_gw_kernel<2>, p, stream, extra);
-    default: return slab_launch(slab_gw_kernel<3>, p, stream, extra);
+    case 2: return half ? slab_launch(slab_gw_kernel<2, true>, p, stream, extra) : slab_launch(slab_gw_kernel<2, false>, p, stream, extra);
+    default: return half ? slab_launch(slab_gw_kernel<3, true>, p, stream, extra) : slab_launch(slab_gw_kernel<3, false>, p, stream, extra);
   }
 }
 
 // forward through the streamed-slab kernel; wp = packed weights [in][node][out_pad4] (layer_pack_kernel)
-int hoir_slab_forward(const hoir_layer_desc* d, long long B, const float* x, const float* wp, float* y,
+int hoir_slab_forward(const hoir_layer_desc* d, long long B, const float* x, const float* wp, float* y, int ldo,
                       cudaStream_t stream) {
   FwdParams p;
   memset(&p, 0, sizeof(p));
@@ -381,6 +443,7 @@ int hoir_slab_forward(const hoir_layer_desc* d, long long B, const float* x, con
   p.x = x;
   p.wp = wp;
   p.y = y;
+  p.ldo = ldo;
   const size_t per_input = (size_t)p.nodes * p.op4 * sizeof(float);
   int gi = (int)((48 * 1024) / per_input);
   gi = gi < 1 ? 1 : (gi > 4 ? 4 : gi);
@@ -399,7 +462,9 @@ int hoir_slab_forward(const hoir_layer_desc* d, long long B, const float* x, con
 }
 
 bool hoir_slab_forward_eligible(const hoir_layer_desc* d, long long B) {
-  if (!hoir_slab_eligible(d, B)) return false;
+  // every 512-sample tile streams the whole packed layer through shared memory: constant cost up to one tile per
+  // SM (measured 0.56 ms for 224 x 129 x 52 at both 2^12 and 2^16 samples), so small batches stay on the gather kernel
+  if (!hoir_slab_eligible(d, B) || B < 16384) return false;
   const size_t per_input = (size_t)hoir_layer_nodes(d) * ((d->out_features + 3) & ~3) * sizeof(float);
   return per_input <= 64 * 1024 && (per_input % 16) == 0;
 }

@@ -140,14 +140,18 @@ def test_positions_from_mesh_bit_exact(rows, cols, rot):
             assert torch.equal(c, b)
 
 
-@pytest.mark.parametrize("kind,n,in_f,out_f,seg", [("continuous", 2, 24, 50, 50), ("continuous", 3, 4, 40, 100),
-                                                   ("discontinuous", 3, 5, 33, 17), ("continuous", 2, 216, 50, 50),
-                                                   ("discontinuous", 2, 7, 64, 9)])
-def test_large_batch_many_segments_gradient(kind, n, in_f, out_f, seg):
-    """B >= 4096 with many segments routes the forward through the streamed-slab kernel and dL/dw through the
-    shared-memory slab kernel (slab_kernels.cu)."""
+@pytest.mark.parametrize("kind,n,in_f,out_f,seg,B", [
+    ("continuous", 2, 24, 50, 50, 5000), ("continuous", 3, 4, 40, 100, 5000), ("discontinuous", 3, 5, 33, 17, 5000),
+    ("continuous", 2, 216, 50, 50, 5000), ("discontinuous", 2, 7, 64, 9, 5000),
+    # > 64 outputs: output blocks through the slab kernels
+    ("continuous", 3, 56, 100, 64, 5000), ("continuous", 2, 9, 70, 16, 5000), ("discontinuous", 3, 6, 131, 12, 5000),
+    # >= 2^14 samples: the forward also goes through the streamed-slab kernel
+    ("continuous", 3, 4, 40, 100, 17000), ("discontinuous", 2, 7, 64, 9, 16384), ("continuous", 3, 12, 100, 64, 17001),
+    ("continuous", 2, 9, 70, 16, 16999)])
+def test_large_batch_many_segments_gradient(kind, n, in_f, out_f, seg, B):
+    """B >= 4096 with many segments routes dL/dw through the shared-memory slab kernel and, from 2^14 samples, the
+    forward through the streamed-slab kernel (slab_kernels.cu)."""
     ref, lay = make_layers(kind, n, in_f, out_f, seg)
-    B = 5000
     g = torch.Generator().manual_seed(B)
     x = torch.rand(B, in_f, generator=g) * 2.2 - 1.1
     gy = torch.randn(B, out_f, generator=g)
@@ -168,6 +172,8 @@ DENSE_CASES = [
     ("fourier", 16, 3, 64, 1),
     ("continuous", 2, 50, 50, 2), ("continuous", 2, 50, 27, 2), ("continuous", 3, 40, 40, 2), ("continuous", 3, 40, 3, 2),
     ("discontinuous", 3, 40, 40, 2), ("discontinuous", 2, 11, 17, 2),
+    # wider than 64 outputs: cut into output blocks (row-strided y / dL/dy, accumulated dL/dx)
+    ("continuous", 3, 100, 100, 2), ("continuous", 3, 40, 65, 2), ("fourier", 7, 9, 130, 1), ("discontinuous", 2, 30, 101, 2),
 ]
 
 
