@@ -17,7 +17,7 @@ from .random_sample import (RadialRandomImageSampleDataset, RandomImageSampleDat
                             generate_sample, generate_sample_radial, indices_from_grid,
                             random_radial_samples_from_image, random_symmetric_sample)
 from .sparse_optimizers import SparseLion  # noqa: F401
-from .trainer import ImageTrainer, NeighborhoodTrainer  # noqa: F401
+from .trainer import ImageTrainer, NeighborhoodTrainer, RandomInterpolationTrainer  # noqa: F401
 from .utils import positions_from_mesh  # noqa: F401
 
 __version__ = "0.1.0"

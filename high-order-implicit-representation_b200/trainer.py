@@ -301,3 +301,64 @@ class NeighborhoodTrainer:
         ckpt = self.net.checkpoint_dict()
         ckpt["optimizer_states"] = [self.optimizer.state_dict()]
         torch.save(ckpt, path)
+
+
+class RandomInterpolationTrainer:
+    """``examples/random_interpolation.py`` without Lightning: fit ``Net(cfg)`` to predict every pixel of a set of
+    ``image_size x image_size`` images from ``num_feature_pixels`` points drawn at random radius / angle around it
+    (RandomImageSampleDataModule + RadialRandomImageSampleDataset,
+    /root/reference/high_order_implicit_representation/random_sample_dataset.py:122-173, 256-384;
+    config/random_interpolation.yaml), then apply the trained interpolator iteratively (generate_sample_radial,
+    utils.py:20-97).  A step = ``batch_size`` images (the reference's collate concatenates their S*S examples);
+    the interpolation sets are drawn in-kernel, fresh every step, and never stored as a dataset."""
+
+    def __init__(self, cfg, images, device: str = "cuda", seed: int = 0, images_per_step: Optional[int] = None):
+        from .random_sample import RadialRandomImageSampleDataset
+        self.cfg = to_cfg(cfg)
+        self.device = torch.device(device)
+        self.size = int(self.cfg.image_size)
+        self.features = int(self.cfg.num_feature_pixels)
+        self.rotations = int(self.cfg.rotations)
+        self.cfg.mlp.input.width = (3 + 2 * self.rotations) * self.features
+        self.cfg.mlp.input.segments = self.size                  # `segments: ${image_size}`
+        self.dataset = RadialRandomImageSampleDataset(self.size, images, num_feature_pixels=self.features,
+                                                      num_target_pixels=int(self.cfg.num_target_pixels),
+                                                      rotations=self.rotations, device=device)
+        self.images_per_step = int(images_per_step or min(int(self.cfg.batch_size), len(self.dataset)))
+        self.net = Net(self.cfg).to(self.device)
+        conf = self.net.configure_optimizers()
+        self.optimizer = conf[0][0] if isinstance(conf, tuple) else conf
+        self.schedule = _LrSchedule(self.cfg.optimizer, float(self.cfg.optimizer.lr))
+        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.seed, self.draws = seed, 0
+        self.history: List[float] = []
+
+    def train_epoch(self) -> float:
+        order = torch.randperm(len(self.dataset), device=self.device, generator=self.gen).tolist()
+        total = torch.zeros(1, device=self.device)
+        steps = 0
+        for b in range(0, len(order), self.images_per_step):
+            feat, targ = self.dataset.batch(order[b:b + self.images_per_step], seed=self.seed, offset=self.draws)
+            self.draws += 1
+            self.optimizer.zero_grad(set_to_none=True)
+            loss = self.net.training_step((feat, targ), steps)
+            loss.backward()
+            self.optimizer.step()
+            total += loss.detach()
+            steps += 1
+        self.net.global_step += steps
+        return float(total.item()) / max(steps, 1)
+
+    fit = NeighborhoodTrainer.fit
+
+    def generate(self, start_image: Optional[Tensor] = None, iterations: Optional[int] = None,
+                 all_random: Optional[bool] = None) -> List[Tensor]:
+        """ImageSampler / the evaluation branch of the example (utils.py:179-225, examples/random_interpolation.py:
+        96-118): the estimates ``[3, S, S]`` in [-1, 1] after each application of the network."""
+        from .random_sample import generate_sample_radial
+        return generate_sample_radial(self.net, features=self.features, iterations=int(iterations or self.cfg.iterations),
+                                      start_image=start_image, image_size=self.size, device=str(self.device),
+                                      rotations=self.rotations,
+                                      all_random=bool(self.cfg.all_random if all_random is None else all_random))
+
+    save_checkpoint = NeighborhoodTrainer.save_checkpoint
