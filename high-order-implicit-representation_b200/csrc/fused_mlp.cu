@@ -584,15 +584,15 @@ bool mlp_desc_ok(const hoir_mlp_desc* m) {
 //      a warp's adds fall into consecutive addresses of the boundary layout [out][in][nodes].
 // ~0.25 global adds per (sample, input) instead of the 120 of a per-sample scatter, balanced for any
 // distribution of the inputs.
-constexpr int GW0_CHUNK = 16384, GW0_MAXSEG = 1024, GW0_BLOCK = 128, GW0_PITCH_PAD = 1, GW0_THREADS = 512, GW0_WARPS = GW0_THREADS / 32;
+constexpr int GW0_CHUNK = 32768, GW0_SHIFT = 15, GW0_MAXSEG = 1024, GW0_BLOCK = 128, GW0_PITCH_PAD = 1, GW0_THREADS = 512, GW0_WARPS = GW0_THREADS / 32;
 template <int N>
 __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int chunk, int IN, int hid, int seg0, int stride, int nodes0,
                                                        const unsigned short* __restrict__ ws_seg,
                                                        const float4* __restrict__ ws_rec, const float* __restrict__ ws_g0,
                                                        float* __restrict__ gw0) {
   extern __shared__ __align__(16) unsigned char gw0_smem[];
-  unsigned int* s_ent = reinterpret_cast<unsigned int*>(gw0_smem);      // sorted: (segment << 14) | sample offset
-  int* s_cnt = reinterpret_cast<int*>(s_ent + GW0_CHUNK);
+  unsigned int* s_ent = reinterpret_cast<unsigned int*>(gw0_smem);      // sorted: (segment << GW0_SHIFT) | sample offset
+  int* s_cnt = reinterpret_cast<int*>(s_ent + chunk);                  // chunk is a multiple of 256
   int* s_pos = s_cnt + GW0_MAXSEG;
   float* slab = reinterpret_cast<float*>(s_pos + GW0_MAXSEG);           // [nodes0][pitch]
   const int pitch = hid + GW0_PITCH_PAD;
@@ -603,7 +603,8 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
   const unsigned short* seg = ws_seg + (size_t)i * B + b0;
   const float4* rec = ws_rec + (size_t)i * B + b0;
   for (int k = threadIdx.x; k < seg0; k += GW0_THREADS) s_cnt[k] = 0;
-  for (int k = threadIdx.x; k < nodes0 * pitch; k += GW0_THREADS) slab[k] = 0.f;
+  if (hid != 40)                                                         // (the 40-wide path adds straight to global memory)
+    for (int k = threadIdx.x; k < nodes0 * pitch; k += GW0_THREADS) slab[k] = 0.f;
   __syncthreads();
   // histogram with warp-aggregated shared atomics (coherent batches put a whole warp into one bin)
   for (int t0 = warp * 32; t0 < n; t0 += GW0_THREADS) {
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
     int base = 0;
     if (key >= 0 && lane == leader) base = atomicAdd(&s_pos[key], __popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (key >= 0) s_ent[base + __popc(peers & ((1u << lane) - 1u))] = ((unsigned)key << 14) | (unsigned)t;
+    if (key >= 0) s_ent[base + __popc(peers & ((1u << lane) - 1u))] = ((unsigned)key << GW0_SHIFT) | (unsigned)t;
   }
   __syncthreads();
   // reduction over the sorted entries.  hid % 8 == 0 (the 40-wide family): a group of 4 lanes owns a contiguous
@@ -644,57 +645,71 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
   // loads of the dL/dy row and 3 * hid/4 FMAs per lane (5 warp-instructions per entry instead of 30); a segment
   // change flushes the group's registers into the CTA's slab.  Otherwise: warp per entry, lane <-> outputs.
   if (hid == 40) {
-    constexpr int OPL = 10;                                   // outputs per lane
+    constexpr int OPL = 10, DEPTH = 4;                        // outputs per lane; entries in flight per lane
     const int grp = threadIdx.x >> 2, sub = threadIdx.x & 3, ngrp = GW0_THREADS / 4;
     const int per = (n + ngrp - 1) / ngrp;
     const int k0 = grp * per, k1 = min(n, k0 + per);
     if (k0 < k1) {
-      int cur = (int)(s_ent[k0] >> 14);
+      int cur = (int)(s_ent[k0] >> GW0_SHIFT);
       float acc[N][OPL];
 #pragma unroll
       for (int j = 0; j < N; ++j)
 #pragma unroll
         for (int o = 0; o < OPL; ++o) acc[j][o] = 0.f;
+      // a finished segment run goes straight to global memory with fire-and-forget adds (the shared-memory float
+      // atomics this replaced are compare-and-swap loops: 35 % of the kernel's stall samples)
+      float* const gbase = gw0 + ((size_t)(sub * OPL) * IN + i) * nodes0;
       auto flush = [&](int sg) {
-        float* dst = slab + (size_t)(sg * stride) * pitch + sub * OPL;
+        float* dst = gbase + sg * stride;
 #pragma unroll
-        for (int j = 0; j < N; ++j)
+        for (int o = 0; o < OPL; ++o)
 #pragma unroll
-          for (int o = 0; o < OPL; ++o) {
-            if (acc[j][o] != 0.f) atomicAdd(dst + j * pitch + o, acc[j][o]);
+          for (int j = 0; j < N; ++j) {
+            if (acc[j][o] != 0.f) hoir::red_add(dst + (size_t)o * IN * nodes0 + j, acc[j][o]);
             acc[j][o] = 0.f;
           }
       };
-#pragma unroll 2
-      for (int k = k0; k < k1; ++k) {
-        const unsigned e = s_ent[k];
-        const int t = (int)(e & 0x3fffu), sg = (int)(e >> 14);
-        const float4 rc = __ldg(rec + t);
-        const float2* grow = reinterpret_cast<const float2*>(ws_g0 + (size_t)(b0 + t) * 40 + sub * OPL);
-        float g[OPL];
+      // batches of DEPTH entries: all their record / dL/dy-row loads are issued before the first is consumed
+      for (int k = k0; k < k1; k += DEPTH) {
+        float4 rc[DEPTH];
+        float2 g2[DEPTH][OPL / 2];
+        int sgs[DEPTH];
 #pragma unroll
-        for (int o = 0; o < OPL / 2; ++o) {
-          const float2 v = __ldg(grow + o);
-          g[2 * o] = v.x;
-          g[2 * o + 1] = v.y;
+        for (int u = 0; u < DEPTH; ++u) {
+          const bool ok = k + u < k1;
+          const unsigned e = ok ? s_ent[k + u] : 0u;
+          const int t = (int)(e & ((1u << GW0_SHIFT) - 1u));
+          sgs[u] = ok ? (int)(e >> GW0_SHIFT) : -1;
+          rc[u] = __ldg(rec + t);
+          const float2* grow = reinterpret_cast<const float2*>(ws_g0 + (size_t)(b0 + t) * 40 + sub * OPL);
+#pragma unroll
+          for (int o = 0; o < OPL / 2; ++o) g2[u][o] = __ldg(grow + o);
         }
-        if (sg != cur) {
-          flush(cur);
-          cur = sg;
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+          if (sgs[u] < 0) break;
+          if (sgs[u] != cur) {
+            flush(cur);
+            cur = sgs[u];
+          }
+          const float l[3] = {rc[u].y, rc[u].z, rc[u].w};
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int o = 0; o < OPL / 2; ++o) {
+              acc[j][2 * o] = fmaf(l[j], g2[u][o].x, acc[j][2 * o]);
+              acc[j][2 * o + 1] = fmaf(l[j], g2[u][o].y, acc[j][2 * o + 1]);
+            }
         }
-        const float l[3] = {rc.y, rc.z, rc.w};
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-#pragma unroll
-          for (int o = 0; o < OPL; ++o) acc[j][o] = fmaf(l[j], g[o], acc[j][o]);
       }
       flush(cur);
     }
+    return;                                                   // nothing went through the shared-memory slab
   } else {
   const bool hi = lane + 32 < hid, lo = lane < hid;
   for (int k0 = warp * GW0_BLOCK; k0 < n; k0 += GW0_WARPS * GW0_BLOCK) {
     const int k1 = k0 + GW0_BLOCK < n ? k0 + GW0_BLOCK : n;
-    int cur = (int)(s_ent[k0] >> 14);
+    int cur = (int)(s_ent[k0] >> GW0_SHIFT);
     float acc[N][2];
 #pragma unroll
     for (int j = 0; j < N; ++j) acc[j][0] = acc[j][1] = 0.f;
@@ -710,7 +725,7 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
 #pragma unroll 8
     for (int k = k0; k < k1; ++k) {
       const unsigned e = s_ent[k];
-      const int t = (int)(e & 0x3fffu), sg = (int)(e >> 14);
+      const int t = (int)(e & ((1u << GW0_SHIFT) - 1u)), sg = (int)(e >> GW0_SHIFT);
       const float4 rc = __ldg(rec + t);
       const float* grow = ws_g0 + (size_t)(b0 + t) * hid;
       const float g0 = lo ? __ldg(grow + lane) : 0.f;
@@ -736,8 +751,8 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
     if (v != 0.f) hoir::red_add(gw0 + ((size_t)o * IN + i) * nodes0 + q, v);
   }
 }
-inline size_t gw0_smem_bytes(int nodes0, int hid) {
-  return (size_t)GW0_CHUNK * 4 + 2 * GW0_MAXSEG * 4 + (size_t)nodes0 * (hid + GW0_PITCH_PAD) * 4;
+inline size_t gw0_smem_bytes(int nodes0, int hid, long long chunk = GW0_CHUNK) {
+  return (size_t)chunk * 4 + 2 * GW0_MAXSEG * 4 + (hid == 40 ? 0 : (size_t)nodes0 * (hid + GW0_PITCH_PAD) * 4);
 }
 
 struct FusedEntry {
@@ -1089,12 +1104,13 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
   HOIR_CHECK_CUDA(cudaGetLastError());
   if (two_pass) {
     const int stride = hoir::piecewise_stride(m->layers[0].kind, m->layers[0].n);
-    // one wave of 2 CTAs per SM when the batch is large enough; chunks of 2048 .. 16384 samples
-    const long long want = (2LL * num_sms_fused() + in_f - 1) / in_f;
+    // one wave of one CTA per SM (106 registers x 512 threads) when the batch is large enough; chunks of
+    // 2048 .. 32768 samples
+    const long long want = num_sms_fused() / in_f > 0 ? num_sms_fused() / in_f : 1;
     long long chunk = ((B + want - 1) / want + 255) & ~255LL;
     chunk = chunk < 2048 ? 2048 : (chunk > GW0_CHUNK ? GW0_CHUNK : chunk);
     const dim3 grid2((unsigned)((B + chunk - 1) / chunk), (unsigned)in_f);
-    const size_t smem2 = gw0_smem_bytes(p.nodes0, hid);
+    const size_t smem2 = gw0_smem_bytes(p.nodes0, hid, chunk);
     HOIR_CHECK_CUDA(cudaFuncSetAttribute(gw0_slab_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     gw0_slab_kernel<3><<<grid2, GW0_THREADS, smem2, st>>>(B, (int)chunk, in_f, hid, p.seg0, stride, p.nodes0, p.ws_seg, p.ws_rec, p.ws_g0, p.gw[0]);
     HOIR_CHECK_CUDA(cudaGetLastError());
