@@ -607,11 +607,20 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
     for (int k = threadIdx.x; k < nodes0 * pitch; k += GW0_THREADS) slab[k] = 0.f;
   __syncthreads();
   // histogram with warp-aggregated shared atomics (coherent batches put a whole warp into one bin)
-  for (int t0 = warp * 32; t0 < n; t0 += GW0_THREADS) {
-    const int t = t0 + lane;
-    const int key = t < n ? (int)seg[t] : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[key], __popc(peers));
+  // (four key loads in flight per lane: the passes over the keys are latency-, not bandwidth-bound)
+  for (int t0 = warp * 32; t0 < n; t0 += 4 * GW0_THREADS) {
+    int keys[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * GW0_THREADS + lane;
+      keys[u] = t < n ? (int)__ldg(seg + t) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u * GW0_THREADS >= n) break;                    // warp-uniform
+      const unsigned peers = __match_any_sync(0xffffffffu, keys[u]);
+      if (keys[u] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[keys[u]], __popc(peers));
+    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -629,15 +638,24 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
     }
   }
   __syncthreads();
-  for (int t0 = warp * 32; t0 < n; t0 += GW0_THREADS) {
-    const int t = t0 + lane;
-    const int key = t < n ? (int)seg[t] : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (key >= 0 && lane == leader) base = atomicAdd(&s_pos[key], __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (key >= 0) s_ent[base + __popc(peers & ((1u << lane) - 1u))] = ((unsigned)key << GW0_SHIFT) | (unsigned)t;
+  for (int t0 = warp * 32; t0 < n; t0 += 4 * GW0_THREADS) {
+    int keys[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * GW0_THREADS + lane;
+      keys[u] = t < n ? (int)__ldg(seg + t) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u * GW0_THREADS >= n) break;                    // warp-uniform
+      const int t = t0 + u * GW0_THREADS + lane, key = keys[u];
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      const int leader = __ffs(peers) - 1;
+      int base = 0;
+      if (key >= 0 && lane == leader) base = atomicAdd(&s_pos[key], __popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (key >= 0) s_ent[base + __popc(peers & ((1u << lane) - 1u))] = ((unsigned)key << GW0_SHIFT) | (unsigned)t;
+    }
   }
   __syncthreads();
   // reduction over the sorted entries.  hid % 8 == 0 (the 40-wide family): a group of 4 lanes owns a contiguous
