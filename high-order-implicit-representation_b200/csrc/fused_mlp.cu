@@ -596,8 +596,8 @@ __global__ void __launch_bounds__(GW0_THREADS) gw0_slab_kernel(long long B, int 
   int* s_pos = s_cnt + GW0_MAXSEG;
   float* slab = reinterpret_cast<float*>(s_pos + GW0_MAXSEG);           // [nodes0][pitch]
   const int pitch = hid + GW0_PITCH_PAD;
-  const int i = blockIdx.y;
-  const long long b0 = (long long)blockIdx.x * chunk;
+  const int i = blockIdx.x;                                             // input fastest: the IN CTAs of a chunk run together
+  const long long b0 = (long long)blockIdx.y * chunk;
   const int n = (int)((B - b0) < chunk ? (B - b0) : chunk);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short* seg = ws_seg + (size_t)i * B + b0;
@@ -1124,10 +1124,17 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
     const int stride = hoir::piecewise_stride(m->layers[0].kind, m->layers[0].n);
     // one wave of one CTA per SM (106 registers x 512 threads) when the batch is large enough; chunks of
     // 2048 .. 32768 samples
-    const long long want = num_sms_fused() / in_f > 0 ? num_sms_fused() / in_f : 1;
+    // WAVES waves of chunks in sample order (CTA id = chunk * IN + input): the dL/dy rows the resident CTAs gather
+    // from are 1/WAVES of the batch, which has to fit in L2 -- every row is read by the IN CTAs of its chunk, in
+    // sorted (= random) order; with one wave over a 168 MB buffer the kernel read 1.03 GB from DRAM
+    static const int waves_env = getenv("HOIR_GW0_WAVES") ? atoi(getenv("HOIR_GW0_WAVES")) : 0;
+    const long long g0_bytes = B * (long long)hid * 4;
+    const int waves = waves_env > 0 ? waves_env : (int)((g0_bytes + (96LL << 20) - 1) / (96LL << 20));   // measured at 168 MB: 1 wave 1.242 ms/step, 2: 1.221, 3: 1.225, 4: 1.238, 6: 1.263
+    const long long lanes = num_sms_fused() / in_f > 0 ? num_sms_fused() / in_f : 1;
+    const long long want = lanes * (waves < 1 ? 1 : waves);
     long long chunk = ((B + want - 1) / want + 255) & ~255LL;
     chunk = chunk < 2048 ? 2048 : (chunk > GW0_CHUNK ? GW0_CHUNK : chunk);
-    const dim3 grid2((unsigned)((B + chunk - 1) / chunk), (unsigned)in_f);
+    const dim3 grid2((unsigned)in_f, (unsigned)((B + chunk - 1) / chunk));
     const size_t smem2 = gw0_smem_bytes(p.nodes0, hid, chunk);
     HOIR_CHECK_CUDA(cudaFuncSetAttribute(gw0_slab_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     gw0_slab_kernel<3><<<grid2, GW0_THREADS, smem2, st>>>(B, (int)chunk, in_f, hid, p.seg0, stride, p.nodes0, p.ws_seg, p.ws_rec, p.ws_g0, p.gw[0]);
