@@ -147,7 +147,9 @@ def test_positions_from_mesh_bit_exact(rows, cols, rot):
     ("continuous", 3, 56, 100, 64, 5000), ("continuous", 2, 9, 70, 16, 5000), ("discontinuous", 3, 6, 131, 12, 5000),
     # >= 2^14 samples: the forward also goes through the streamed-slab kernel
     ("continuous", 3, 4, 40, 100, 17000), ("discontinuous", 2, 7, 64, 9, 16384), ("continuous", 3, 12, 100, 64, 17001),
-    ("continuous", 2, 9, 70, 16, 16999)])
+    ("continuous", 2, 9, 70, 16, 16999),
+    # slabs so large that only 1-2 inputs fit per CTA (odd segment count, discontinuous)
+    ("continuous", 2, 7, 64, 151, 5000), ("discontinuous", 3, 5, 40, 150, 5000), ("continuous", 3, 3, 50, 200, 4500)])
 def test_large_batch_many_segments_gradient(kind, n, in_f, out_f, seg, B):
     """B >= 4096 with many segments routes dL/dw through the shared-memory slab kernel and, from 2^14 samples, the
     forward through the streamed-slab kernel (slab_kernels.cu)."""
