@@ -12,6 +12,9 @@ B = 1 << 20
 x = torch.rand(B, 4, device=dev) * 2 - 1
 y = torch.rand(B, 3, device=dev) * 2 - 1
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+if len(sys.argv) > 2 and sys.argv[2] == "coherent":      # the same explicit-x path on a coherent batch (256 image rows)
+    lines = H.positions_from_mesh(4096, 4096, device="cuda", rotations=2, normalize=True)
+    x = torch.stack(lines, dim=2).reshape(-1, 4)[:B].contiguous()
 for _ in range(3):
     tr.train_step(x, y)
 torch.cuda.synchronize()

@@ -225,3 +225,42 @@ def test_dense_tensor_core_matches_cuda_core_kernels_at_full_size():
         xh = x[h].clone().requires_grad_(True)
         lay(xh).backward(gy[h])
     assert rel_err(lay.w.grad, gw_tc) <= 2e-5
+
+
+def _fuzz_cases(count=48, seed=20261020):
+    """Random layer shapes around the dispatch boundaries of hoir_layer_forward/backward: batch 512 / 4096 / 2^14
+    (tensor-core, slab dL/dw, slab forward), outputs 64 / 65 (output blocks), segments 2 / 8 / 9 (dense vs gather)."""
+    import random
+    rnd = random.Random(seed)
+    cases = []
+    for _ in range(count):
+        kind = rnd.choice(["continuous", "continuous", "discontinuous", "fourier", "polynomial"])
+        n = rnd.choice([2, 3, 3, 4, 6]) if kind != "fourier" else rnd.choice([1, 3, 5, 8, 17, 31])
+        seg = 1 if kind in ("fourier", "polynomial") else rnd.choice([1, 2, 2, 3, 8, 9, 17, 64, 100])
+        in_f = rnd.choice([1, 2, 3, 4, 7, 16, 33, 50])
+        out_f = rnd.choice([1, 3, 10, 31, 40, 63, 64, 65, 72, 100, 129])
+        B = rnd.choice([2, 33, 511, 512, 513, 1000, 4095, 4096, 4100, 16383, 16384, 16390])
+        nodes = n if kind in ("fourier", "polynomial") else ((n - 1) * seg + 1 if kind == "continuous" else n * seg)
+        if B * in_f * out_f * n > 60_000_000:          # the oracle materialises the gathered weights [B, in, out, n]
+            B = max(2, 60_000_000 // (in_f * out_f * n))
+        cases.append((kind, n, in_f, out_f, seg, B))
+    return cases
+
+
+@pytest.mark.parametrize("kind,n,in_f,out_f,seg,B", _fuzz_cases())
+def test_layer_parity_fuzz(kind, n, in_f, out_f, seg, B):
+    ref, lay = make_layers(kind, n, in_f, out_f, seg)
+    g = torch.Generator().manual_seed(B * 31 + in_f)
+    x = torch.rand(B, in_f, generator=g) * 2.3 - 1.15
+    gy = torch.randn(B, out_f, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy)
+    xc = x.cuda().requires_grad_(True)
+    yc = lay(xc)
+    yc.backward(gy.cuda())
+    tol = TOL[kind]
+    assert rel_err(yc, yr) <= tol
+    gx_ref = xr.grad if xr.grad is not None else torch.zeros_like(x)
+    assert rel_err(xc.grad, gx_ref) <= tol
+    assert rel_err(lay.w.grad, ref.w.grad) <= tol
