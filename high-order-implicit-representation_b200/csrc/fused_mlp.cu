@@ -71,6 +71,7 @@ struct FusedParams {
   float* y;
   int post_scale;
   int seg0, nodes0, pow2_0;
+  int identity;              // every layer is a Polynomial (single window, xi = x)
   int normalize;
   float norm_eps;
   // two-pass layer-0 dL/dw for incoherent batches (generic x, large B): the main kernel streams
@@ -86,6 +87,7 @@ struct FusedParams {
 struct SegConst {
   int segments, stride;
   float segf, inv_segf;
+  int identity;              // Polynomial layer: one window, basis evaluated at x itself (no coordinate map)
 };
 
 __device__ __forceinline__ void locate2(float x, int& id, float& xi);
@@ -93,6 +95,11 @@ template <bool POW2>
 __device__ __forceinline__ void locate(float x, const SegConst& sc, int& id, float& xi) {
   if (POW2 && sc.segments == 2) {   // compile-time after inlining for the hidden / output layers
     locate2(x, id, xi);
+    return;
+  }
+  if (sc.identity) {
+    id = 0;
+    xi = x;
     return;
   }
   id = hoir::segment_index(x, 1.f, 2.f, sc.segf, sc.segments);
@@ -370,9 +377,9 @@ __global__ void __launch_bounds__(BT, 1) fused_mlp_kernel(const FusedParams p) {
   }
   __syncthreads();
 
-  const SegConst sc0 = {p.seg0, S::STRIDE, (float)p.seg0, 1.f / (float)p.seg0};
-  const SegConst sch = {S::SEGH, S::STRIDE, (float)S::SEGH, 1.f / (float)S::SEGH};
-  const SegConst sco = {S::SEGO, S::STRIDE, (float)S::SEGO, 1.f / (float)S::SEGO};
+  const SegConst sc0 = {p.seg0, S::STRIDE, (float)p.seg0, 1.f / (float)p.seg0, p.identity};
+  const SegConst sch = {S::SEGH, S::STRIDE, (float)S::SEGH, 1.f / (float)S::SEGH, p.identity};
+  const SegConst sco = {S::SEGO, S::STRIDE, (float)S::SEGO, 1.f / (float)S::SEGO, p.identity};
   const float* w0 = p.packed + p.off[0];
   const LagrangeTable& lag = p.lag;
   float loss_local = 0.f;
@@ -793,6 +800,15 @@ constexpr FusedEntry make_entry() {
                     fused_mlp_kernel<S, false>, fused_mlp_kernel<S, true>,
                     (size_t)S::S_FWD * 4, (size_t)S::S_TRAIN * 4, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0};
 }
+// Polynomial networks (the default layer_type of config/images_config.yaml): one window per input, i.e. the
+// continuous shape with a single segment everywhere, with the basis evaluated at x itself (FusedParams::identity)
+template <class S>
+constexpr FusedEntry make_entry_poly() {
+  static_assert(S::CONT && S::SEGH == 1 && S::SEGO == 1, "polynomial entry: continuous shape with one segment");
+  FusedEntry e = make_entry<S>();
+  e.kind = HOIR_POLYNOMIAL;
+  return e;
+}
 template <class S>
 constexpr FusedEntry make_entry_tc() {
   return FusedEntry{S::KIND, S::N, S::IN, S::HID, S::OUT, S::NH, S::SEGH, S::SEGO,
@@ -824,6 +840,8 @@ const FusedEntry kEntries[] = {
     make_entry<Shape<HOIR_DISCONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),
     make_entry<Shape<HOIR_CONTINUOUS, 2, 2, 10, 3, 2, 2, 2>>(),
     make_entry<Shape<HOIR_DISCONTINUOUS, 2, 2, 10, 3, 2, 2, 2>>(),
+    make_entry_poly<Shape<HOIR_CONTINUOUS, 3, 4, 10, 3, 2, 1, 1>>(),   // images_config.yaml defaults (rotations 2)
+    make_entry_poly<Shape<HOIR_CONTINUOUS, 3, 2, 10, 3, 2, 1, 1>>(),
 };
 
 const FusedEntry* find_entry(const hoir_mlp_desc* m) {
@@ -838,11 +856,12 @@ const FusedEntry* find_entry(const hoir_mlp_desc* m) {
     if (l > 0 && l < L - 1 && (d.segments != m->layers[1].segments || d.out_features != l0.out_features))
       return nullptr;
   }
-  if (l0.kind != HOIR_CONTINUOUS && l0.kind != HOIR_DISCONTINUOUS) return nullptr;
+  const bool poly = l0.kind == HOIR_POLYNOMIAL;               // `segments` is meaningless for a Polynomial layer
+  if (l0.kind != HOIR_CONTINUOUS && l0.kind != HOIR_DISCONTINUOUS && !poly) return nullptr;
   for (const FusedEntry& e : kEntries)
     if (e.kind == l0.kind && e.n == l0.n && e.in == l0.in_features && e.hid == l0.out_features &&
-        e.out == lo.out_features && e.nh == L - 2 && e.segh == m->layers[1].segments &&
-        e.sego == lo.segments)
+        e.out == lo.out_features && e.nh == L - 2 && e.segh == (poly ? 1 : m->layers[1].segments) &&
+        e.sego == (poly ? 1 : lo.segments))
       return &e;
   return nullptr;
 }
@@ -865,7 +884,8 @@ int fill_params(const hoir_mlp_desc* m, long long B, const float* x, const hoir_
   }
   p->packed = packed;
   for (int l = 0; l < m->num_layers; ++l) p->off[l] = hoir_mlp_packed_offset(m, l);
-  p->seg0 = m->layers[0].segments;
+  p->identity = m->layers[0].kind == HOIR_POLYNOMIAL;
+  p->seg0 = p->identity ? 1 : m->layers[0].segments;
   p->nodes0 = hoir_layer_nodes(&m->layers[0]);
   p->pow2_0 = hoir::is_pow2(p->seg0);
   p->normalize = m->normalize;

@@ -61,6 +61,25 @@ def c1():
     report("C1 same, step captured in a CUDA graph", 256, ms, 4380, "one cooperative launch per replay (optimizer tail in-kernel)")
 
 
+def cdefault():
+    """config/images_config.yaml as shipped: polynomial n=3, 4-10-10-10-3, batch 256, sparse_lion."""
+    kw = dict(layer_type="polynomial", n=3, in_width=4, out_width=3, hidden_layers=2, hidden_width=10,
+              in_segments=100, out_segments=2, hidden_segments=2)
+    net = mlp(**kw)
+    assert net.fused_supported()
+    tr = H.FusedTrainer(net, optimizer="sparse_lion", lr=1e-4)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(256, 4, device=dev, generator=g) * 2 - 1
+    y = torch.rand(256, 3, device=dev, generator=g) * 2 - 1
+    ms = timeit(lambda: tr.train_step(x, y), 200)
+    flop = 3 * 2 * 3 * (4 * 10 + 10 * 10 * 2 + 10 * 3) - 2 * 3 * 4 * 10
+    report("stock images_config.yaml: polynomial n=3 4-10-10-10-3, batch 256 (fused FFMA kernel, one launch per step)", 256, ms, flop, "launch-latency bound")
+    img = torch.randint(0, 256, (744, 1000, 3), dtype=torch.uint8, device=dev)
+    B = 1 << 18
+    ms = timeit(lambda: tr.train_step_mesh(img, 2, 0, B), 20)
+    report("same network, 2^18 pixels of a 1000x744 image per step (mesh mode)", B, ms, flop, "")
+
+
 def fused(name, flop, **kw):
     net = mlp(**kw)
     tr = H.FusedTrainer(net, optimizer="adam", lr=1e-4)
@@ -145,6 +164,7 @@ if __name__ == "__main__":
               in_segments=100, out_segments=2, hidden_segments=2)
     tr = None
     if "c1" in which: c1()
+    if "default" in which: cdefault()
     if "c2" in which or "c5" in which: tr = fused("C2 continuous n=3 4-40-40-3 (tcgen05 kernel)", 32880, **C2)
     if "c3d" in which: fused("C3 discontinuous n=3 4-40-40-3 (tcgen05 kernel, 6 slots per input)", 32880, **dict(C2, layer_type="discontinuous"))
     if "c3f" in which: c3f()

@@ -12,8 +12,8 @@ from helpers import MLP_KW, make_pair, rel_err
 
 pytestmark = pytest.mark.gpu
 
-FUSED = ["C1", "C1d", "C1n2", "C2", "C2r1", "C3d"]
-UNFUSED = ["C3f", "C4s", "poly"]
+FUSED = ["C1", "C1d", "C1n2", "C2", "C2r1", "C3d", "poly"]
+UNFUSED = ["C3f", "C4s"]
 
 
 def batch(name, B, seed=0):
@@ -54,7 +54,7 @@ def test_fused_matches_per_layer_kernels(name):
     assert rel_err(y_fused, y_layers) <= 1e-5
 
 
-@pytest.mark.parametrize("name", ["C1", "C2", "C3d"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3d", "poly"])
 @pytest.mark.parametrize("opt", ["adam", "sparse_lion"])
 def test_trainer_steps_match_oracle_training(name, opt):
     ref, net = make_pair(name)
@@ -83,7 +83,7 @@ def test_trainer_steps_match_oracle_training(name, opt):
     assert rel_err(sd["model.0.w"], ref.state_dict()["model.0.w"]) <= 1e-4
 
 
-@pytest.mark.parametrize("rows,cols,rot,name", [(37, 53, 2, "C2"), (64, 48, 1, "C1"), (40, 40, 2, "C3d")])
+@pytest.mark.parametrize("rows,cols,rot,name", [(37, 53, 2, "C2"), (64, 48, 1, "C1"), (40, 40, 2, "C3d"), (33, 47, 2, "poly")])
 def test_mesh_mode_training_and_render(rows, cols, rot, name):
     ref, net = make_pair(name)
     g = torch.Generator().manual_seed(11)
