@@ -838,6 +838,8 @@ const FusedEntry kEntries[] = {
     make_entry_tc<Shape<HOIR_CONTINUOUS, 3, 2, 40, 3, 1, 2, 2>>(),
     make_entry<Shape<HOIR_CONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),
     make_entry<Shape<HOIR_DISCONTINUOUS, 3, 2, 10, 3, 2, 2, 2>>(),
+    make_entry<Shape<HOIR_CONTINUOUS, 3, 4, 10, 3, 2, 2, 2>>(),      // README.md:24 (10-wide with the default rotations=2)
+    make_entry<Shape<HOIR_DISCONTINUOUS, 3, 4, 10, 3, 2, 2, 2>>(),
     make_entry<Shape<HOIR_CONTINUOUS, 2, 2, 10, 3, 2, 2, 2>>(),
     make_entry<Shape<HOIR_DISCONTINUOUS, 2, 2, 10, 3, 2, 2, 2>>(),
     make_entry_poly<Shape<HOIR_CONTINUOUS, 3, 4, 10, 3, 2, 1, 1>>(),   // images_config.yaml defaults (rotations 2)

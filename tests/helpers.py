@@ -10,6 +10,8 @@ MLP_KW = {
                in_segments=100, out_segments=2, hidden_segments=2),
     "C1d": dict(layer_type="discontinuous", n=3, in_width=2, out_width=3, hidden_layers=2, hidden_width=10,
                 in_segments=100, out_segments=2, hidden_segments=2),
+    "C1r2": dict(layer_type="continuous", n=3, in_width=4, out_width=3, hidden_layers=2, hidden_width=10,
+                 in_segments=100, out_segments=2, hidden_segments=2),          # README.md:24 with the default rotations=2
     "C1n2": dict(layer_type="continuous", n=2, in_width=2, out_width=3, hidden_layers=2, hidden_width=10,
                  in_segments=100, out_segments=2, hidden_segments=2),
     "C2": dict(layer_type="continuous", n=3, in_width=4, out_width=3, hidden_layers=1, hidden_width=40,
