@@ -6,7 +6,7 @@ from ._lib import HoirUnsupported, build  # noqa: F401
 from .config import (Config, apply_overrides, generative_config, images_config, neighborhood_config,  # noqa: F401
                      random_interpolation_config, to_cfg)
 from .datasets import image_neighborhood_dataset, image_to_dataset, neighborhood_gather  # noqa: F401
-from .engine import FusedTrainer, HostBatchStepper  # noqa: F401
+from .engine import FusedTrainer, GraphedStep, HostBatchStepper  # noqa: F401
 from .rendering import generate_sequence, neighborhood_sample_generator, render_image  # noqa: F401
 from .layers import (FourierSeries, HighOrderLayer, MaxAbsNormalization,  # noqa: F401
                      PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial,

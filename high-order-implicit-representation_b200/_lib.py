@@ -122,6 +122,11 @@ _EXPORTS = {
                                  C.c_longlong, C.c_void_p]),
     "hoir_sparse_lion_step": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "hoir_adam_step_dev": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "hoir_sparse_lion_step_dev": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
+    "hoir_write_floats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "hoir_ffma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                  C.c_void_p]),
 }

@@ -173,6 +173,81 @@ extern "C" int hoir_sparse_lion_step(long long n, float* w, const float* g, floa
   return HOIR_OK;
 }
 
+// The same updates with their scalars read from DEVICE memory, so that a step captured in a CUDA graph follows
+// the step count (bias corrections) and the lr schedule without being re-captured: the host refreshes the 8
+// floats (lr, beta1, beta2, eps, weight_decay, bias_correction1, sqrt(bias_correction2), unused) before a replay.
+__global__ void adam_dev_kernel(long long n, float* __restrict__ w, const float* __restrict__ g,
+                                float* __restrict__ m, float* __restrict__ v, const float* __restrict__ hyper) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2_sqrt = hyper[6];
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x) {
+    float gk = g[k];
+    float wk = w[k];
+    if (wd != 0.f) gk = fmaf(wd, wk, gk);
+    float mk = m[k] + (1.f - b1) * (gk - m[k]);
+    float vk = b2 * v[k] + (1.f - b2) * gk * gk;
+    m[k] = mk;
+    v[k] = vk;
+    float denom = sqrtf(vk) / bc2_sqrt + eps;
+    w[k] = wk - (lr / bc1) * (mk / denom);
+  }
+}
+__global__ void sparse_lion_dev_kernel(long long n, float* __restrict__ w, const float* __restrict__ g,
+                                       float* __restrict__ ea, const float* __restrict__ hyper) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], wd = hyper[4];
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x) {
+    float gk = g[k];
+    if (gk != 0.f) {
+      float e = ea[k];
+      float wk = w[k] * (1.f - lr * wd);
+      float u = e * b1 + gk * (1.f - b1);
+      float s = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+      w[k] = wk - lr * s;
+      ea[k] = e * b2 + gk * (1.f - b2);
+    }
+  }
+}
+
+struct Floats8 { float v[8]; };
+__global__ void write_floats_kernel(float* __restrict__ dst, int n, Floats8 f) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = f.v[threadIdx.x];
+}
+// dst[0..n) = values[0..n) (n <= 8), stream-ordered, the values travel as kernel arguments: no host buffer has to
+// stay alive or unchanged until the copy executes
+extern "C" int hoir_write_floats(float* dst, int n, const float* values, void* stream) {
+  if (n < 0 || n > 8) return hoir_set_error(HOIR_EINVAL, "n must be in 0..8", "hoir_write_floats");
+  if (n == 0) return HOIR_OK;
+  if (!dst || !values) return hoir_set_error(HOIR_EINVAL, "null pointer", "hoir_write_floats");
+  Floats8 f;
+  for (int k = 0; k < 8; ++k) f.v[k] = k < n ? values[k] : 0.f;
+  write_floats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dst, n, f);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+extern "C" int hoir_adam_step_dev(long long n, float* w, const float* g, float* exp_avg, float* exp_avg_sq,
+                                  const float* hyper, void* stream) {
+  if (n < 0) return hoir_set_error(HOIR_EINVAL, "bad n", "hoir_adam_step_dev");
+  if (n == 0) return HOIR_OK;
+  if (!w || !g || !exp_avg || !exp_avg_sq || !hyper)
+    return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_adam_step_dev");
+  adam_dev_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, w, g, exp_avg, exp_avg_sq, hyper);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
+extern "C" int hoir_sparse_lion_step_dev(long long n, float* w, const float* g, float* exp_avg, const float* hyper,
+                                         void* stream) {
+  if (n < 0) return hoir_set_error(HOIR_EINVAL, "bad n", "hoir_sparse_lion_step_dev");
+  if (n == 0) return HOIR_OK;
+  if (!w || !g || !exp_avg || !hyper)
+    return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_sparse_lion_step_dev");
+  sparse_lion_dev_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, w, g, exp_avg, hyper);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // FFMA-only micro-kernel: the measured FP32 roofline denominator.  16 independent
 // register-register FFMA chains per thread, 1024 threads per SM-resident CTA pair.

@@ -308,3 +308,78 @@ class HostBatchStepper:
         out = self._collect()
         self.pending = None
         return out
+
+
+class GraphedStep:
+    """``zero_grad + forward + loss + backward + optimizer.step`` of ANY hoir_b200 model (the per-layer kernels
+    under autograd: Fourier networks, the neighborhood / random interpolators, GenerativeNetwork) captured in ONE
+    CUDA graph for a fixed batch shape -- the launch-bound inner loop of the reference's training
+    (/root/reference/high_order_implicit_representation/networks.py:64-73 under ``Trainer.fit``) replayed with a
+    single ``cudaGraphLaunch``.  Networks with a fused whole-network kernel do not need it (``FusedTrainer`` is one
+    launch already).
+
+    Build it BEFORE running eager steps whose autograd graph is still referenced (e.g. a live ``loss`` tensor):
+    such a graph keeps the parameters' AccumulateGrad nodes bound to the default stream and the capture fails with
+    cudaErrorStreamCaptureImplicit.
+
+    ``optimizer`` must be constructed with ``capturable=True`` (scalars in device memory).  ``x`` / ``y`` are the
+    static input buffers: fill them (any stream-ordered producer, e.g. ``hoir_neighborhood_gather`` writing into
+    them) and call ``replay()``, or pass tensors to ``step(x, y)``.  ``loss`` is the static loss tensor."""
+
+    def __init__(self, model, optimizer, x_example: Tensor, y_example: Tensor, loss_fn=None, warmup: int = 3):
+        if not getattr(optimizer, "capturable", False):
+            raise ValueError("GraphedStep needs an optimizer constructed with capturable=True")
+        self.model, self.optimizer = model, optimizer
+        self.loss_fn = loss_fn or (lambda out, y: torch.nn.functional.mse_loss(out.flatten(), y.flatten()))
+        self.x = x_example.detach().clone().contiguous()
+        self.y = y_example.detach().clone().contiguous()
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        # warm-up on a side stream (allocator pools, library workspaces, lazily created optimizer state), then put
+        # weights and optimizer state back: constructing a GraphedStep does not train
+        w_backup = [p.detach().clone() for p in params]
+        st_backup = {p: {k: (v.clone() if isinstance(v, Tensor) else v) for k, v in optimizer.state[p].items()}
+                     for p in params if p in optimizer.state and len(optimizer.state[p])}
+        steps_backup = [g.get("_step", 0) for g in optimizer.param_groups]
+        side = torch.cuda.Stream(device=self.x.device)
+        side.wait_stream(torch.cuda.current_stream(self.x.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager()
+        torch.cuda.current_stream(self.x.device).wait_stream(side)
+        with torch.no_grad():
+            for p, w in zip(params, w_backup):
+                p.copy_(w)
+            for p in params:
+                for k, v in optimizer.state[p].items():
+                    if isinstance(v, Tensor):
+                        v.copy_(st_backup[p][k]) if p in st_backup else v.zero_()
+                    else:
+                        optimizer.state[p][k] = st_backup[p][k] if p in st_backup else 0
+        for g, n in zip(optimizer.param_groups, steps_backup):
+            if "_step" in g:
+                g["_step"] = n
+        optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loss = self.loss_fn(model(self.x), self.y)
+            loss.backward()
+            optimizer.step()
+        self.loss = loss.detach()       # the static loss value; dropping `loss` frees the captured autograd graph
+        del loss
+
+    def _eager(self) -> Tensor:
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.loss_fn(self.model(self.x), self.y)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def replay(self) -> Tensor:
+        self.optimizer.refresh_hyper()          # step count / lr -> device scalars, ordered before the replay
+        self.graph.replay()
+        return self.loss
+
+    def step(self, x: Tensor, y: Tensor) -> Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        return self.replay()

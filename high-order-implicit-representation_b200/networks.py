@@ -173,13 +173,38 @@ def initialize_network_polynomial_layers(network: nn.Module, max_slope: float, m
                 layer.w.copy_(w.to(layer.w.device))
 
 
+def _write_hyper(dev_tensor: Tensor, values) -> None:
+    import ctypes as C
+    arr = (C.c_float * 8)(*([float(v) for v in values] + [0.0] * (8 - len(values))))
+    with torch.cuda.device(dev_tensor.device):
+        _lib.check(_lib.lib().hoir_write_floats(_lib.dptr(dev_tensor), 8, arr, _lib.stream_ptr(dev_tensor.device)))
+
+
 class Adam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0) on
-    ``hoir_adam_step`` -- what /root/reference/.../networks.py:94-97 constructs."""
+    ``hoir_adam_step`` -- what /root/reference/.../networks.py:94-97 constructs.
+
+    ``capturable=True``: the scalars (lr, betas, eps, weight decay, bias corrections) live in device memory
+    (``hoir_adam_step_dev``), so ``step()`` can be captured in a CUDA graph; ``refresh_hyper()`` advances the step
+    count and rewrites them (stream-ordered, outside the graph) before every replay -- the lr schedule and the bias
+    corrections follow without re-capture.  Eager ``step()`` calls it itself."""
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0):
+                 weight_decay: float = 0.0, capturable: bool = False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.capturable = capturable
+
+    def refresh_hyper(self) -> None:
+        for group in self.param_groups:
+            dev = group["params"][0].device
+            if "_hyper" not in group:
+                group["_hyper"] = torch.zeros(8, device=dev)
+                group["_step"] = 0
+            group["_step"] += 1
+            b1, b2 = group["betas"]
+            bc1 = 1.0 - b1 ** group["_step"]
+            bc2 = 1.0 - b2 ** group["_step"]
+            _write_hyper(group["_hyper"], [group["lr"], b1, b2, group["eps"], group["weight_decay"], bc1, bc2 ** 0.5])
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -188,6 +213,8 @@ class Adam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.lib()
+        if self.capturable and not torch.cuda.is_current_stream_capturing():
+            self.refresh_hyper()
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
@@ -198,9 +225,14 @@ class Adam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] += 1
                 g = p.grad.contiguous()
                 with torch.cuda.device(p.device):
+                    if self.capturable:
+                        _lib.check(lib.hoir_adam_step_dev(
+                            p.numel(), _lib.dptr(p.data), _lib.dptr(g), _lib.dptr(st["exp_avg"]),
+                            _lib.dptr(st["exp_avg_sq"]), _lib.dptr(group["_hyper"]), _lib.stream_ptr(p.device)))
+                        continue
+                    st["step"] += 1
                     _lib.check(lib.hoir_adam_step(
                         p.numel(), _lib.dptr(p.data), _lib.dptr(g), _lib.dptr(st["exp_avg"]),
                         _lib.dptr(st["exp_avg_sq"]), float(group["lr"]), float(b1), float(b2),

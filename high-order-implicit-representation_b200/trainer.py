@@ -218,9 +218,10 @@ class NeighborhoodTrainer:
     (generate_sequence, rendering.py:98-126).  Patches are never materialised as a dataset: every step gathers its
     batch of patches from the image resident in HBM (``hoir_neighborhood_gather`` with a first patch / count)."""
 
-    def __init__(self, cfg, images, device: str = "cuda", seed: int = 0):
+    def __init__(self, cfg, images, device: str = "cuda", seed: int = 0, cuda_graph: bool = False):
         self.cfg = to_cfg(cfg)
         self.device = torch.device(device)
+        self.cuda_graph, self._graphed = bool(cuda_graph), None
         self.width, self.outside = int(self.cfg.data.width), int(self.cfg.data.outside)
         total = self.width + 2 * self.outside
         self.cfg.mlp.input.width = (total * total - self.width * self.width) * 3
@@ -236,6 +237,7 @@ class NeighborhoodTrainer:
         self.net = Net(self.cfg).to(self.device)
         conf = self.net.configure_optimizers()
         self.optimizer = conf[0][0] if isinstance(conf, tuple) else conf
+        self.optimizer.capturable = self.cuda_graph          # scalars in device memory: the step can live in a graph
         self.schedule = _LrSchedule(self.cfg.optimizer, float(self.cfg.optimizer.lr))
         self.gen = torch.Generator(device=self.device).manual_seed(seed)
         self.history: List[float] = []
@@ -254,8 +256,17 @@ class NeighborhoodTrainer:
     def train_epoch(self) -> float:
         lib = _lib.lib()
         in_w, out_w = int(self.cfg.mlp.input.width), int(self.cfg.mlp.output.width)
-        feat = torch.empty((self.batch_size, in_w), device=self.device)
-        targ = torch.empty((self.batch_size, out_w), device=self.device)
+        if self.cuda_graph and self._graphed is None:
+            # captured before any eager step of this trainer: a live autograd graph from an eager iteration (its
+            # `loss`) would pin the weights' AccumulateGrad nodes to the default stream and break the capture
+            from .engine import GraphedStep
+            self._graphed = GraphedStep(self.net, self.optimizer, torch.zeros((self.batch_size, in_w), device=self.device),
+                                        torch.zeros((self.batch_size, out_w), device=self.device))
+        if self._graphed is not None:
+            feat, targ = self._graphed.x, self._graphed.y
+        else:
+            feat = torch.empty((self.batch_size, in_w), device=self.device)
+            targ = torch.empty((self.batch_size, out_w), device=self.device)
         total = torch.zeros(1, device=self.device)
         steps = 0
         for k, first, count in self._patch_batches():
@@ -264,11 +275,18 @@ class NeighborhoodTrainer:
                 _lib.check(lib.hoir_neighborhood_gather(_lib.dptr(im), 3, im.shape[1], im.shape[2], self.width,
                                                         self.outside, 1, 0, first, count, _lib.dptr(feat),
                                                         _lib.dptr(targ), _lib.stream_ptr(self.device)))
+            if self.cuda_graph and count == self.batch_size:
+                # full batches: zero_grad + forward + loss + backward + optimizer replayed from ONE CUDA graph whose
+                # static inputs are the gather's output buffers (the ragged last block of an image runs eagerly)
+                total += self._graphed.replay().detach()
+                steps += 1
+                continue
             self.optimizer.zero_grad(set_to_none=True)
             loss = self.net.training_step((feat[:count], targ[:count]), steps)
             loss.backward()
             self.optimizer.step()
             total += loss.detach()
+            del loss
             steps += 1
         self.net.global_step += steps
         return float(total.item()) / max(steps, 1)

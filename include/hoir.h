@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HOIR_VERSION 103
+#define HOIR_VERSION 104
 #define HOIR_MAX_LAYERS 8
 #define HOIR_MAX_N 32          /* max basis functions per segment / Fourier terms          */
 #define HOIR_MAX_ROTATIONS 8
@@ -250,6 +250,16 @@ int hoir_adam_step(long long n, float* w, const float* g, float* exp_avg, float*
                    long long step, void* stream);
 int hoir_sparse_lion_step(long long n, float* w, const float* g, float* exp_avg, float lr,
                           float beta1, float beta2, float weight_decay, void* stream);
+/* The same updates with the scalars in device memory -- hyper[8] = {lr, beta1, beta2, eps, weight_decay,
+ * 1 - beta1^step, sqrt(1 - beta2^step), unused} -- so that a training step captured in a CUDA graph follows the
+ * step count and the lr schedule (networks.py:104-118) without re-capture: the host rewrites hyper before a replay. */
+int hoir_adam_step_dev(long long n, float* w, const float* g, float* exp_avg, float* exp_avg_sq,
+                       const float* hyper, void* stream);
+int hoir_sparse_lion_step_dev(long long n, float* w, const float* g, float* exp_avg, const float* hyper,
+                              void* stream);
+/* dst[0..n) = values[0..n), n <= 8; `values` is HOST memory read before the call returns (the floats travel as
+ * kernel arguments), the write is ordered on `stream` */
+int hoir_write_floats(float* dst, int n, const float* values, void* stream);
 
 /* FFMA-only micro-kernel: runs `iters` rounds of 128 independent FFMAs per thread on every SM and
  * returns the elapsed milliseconds in *ms and the FLOPs executed in *flops (the measured FP32

@@ -100,6 +100,15 @@ def c3f():
     y = torch.rand(B, 3, device=dev, generator=g) * 2 - 1
     ms = timeit(lambda: autograd_step(net, opt, x, y), 30)
     report("C3 fourier n_in=31 (hidden 31), 4-40-40-3, batch 2^16 (tcgen05 per-layer kernels + autograd)", B, ms, 319600, "dense_tc.cu: tf32x3 on the tensor pipe, 15 launches per step")
+    for bs in (B, 256):
+        net2 = mlp(**kw)
+        gs = H.GraphedStep(net2, H.Adam(net2.parameters(), lr=1e-4, capturable=True), x[:bs], y[:bs])
+        ms = timeit(gs.replay, 50)
+        report("C3 fourier, batch %d, the whole step replayed from ONE CUDA graph (GraphedStep)" % bs, bs, ms, 319600, "")
+    net3 = mlp(**kw)
+    opt3 = H.Adam(net3.parameters(), lr=1e-4)
+    ms = timeit(lambda: autograd_step(net3, opt3, x[:256], y[:256]), 50)
+    report("C3 fourier, batch 256 (the reference's batch size), eager launches", 256, ms, 319600, "launch-bound")
 
 
 def c4():
@@ -121,6 +130,14 @@ def c4():
     ms = timeit(step, 20)
     report("C4 interpolator continuous n=2, 216-50-50-50-27, 2048^2 image, batch 2^16 patches (gather + slab dL/dw + tcgen05 hidden layers)",
            B, ms, 162600, "layer 0 = 2.2 MB gather table (CUDA cores); hidden and output layers on tcgen05")
+    net2 = mlp(**kw)
+    gs = H.GraphedStep(net2, H.Adam(net2.parameters(), lr=1e-4, capturable=True), feat, targ)
+
+    def gstep():
+        L.check(lib.hoir_neighborhood_gather(L.dptr(img), 3, 2048, 2048, 3, 3, 1, 0, 12345, B, L.dptr(gs.x), L.dptr(gs.y), L.stream_ptr(dev)))
+        gs.replay()
+    ms = timeit(gstep, 20)
+    report("C4 same, gather + the whole step replayed from ONE CUDA graph (GraphedStep)", B, ms, 162600, "")
     ms = timeit(lambda: H.neighborhood_sample_generator(net, img, 3, 3), 3)
     report("C4 inference: one generate_sequence frame on 2048^2 (gather + forward + fold)", 2048 * 2048, ms, 68600 / 9, "per output pixel")
 

@@ -140,3 +140,67 @@ def test_random_interpolation_trainer_fits_and_generates(tmp_path):
     assert len(frames) == 3 and frames[0].shape == (3, S, S) and all(torch.isfinite(f).all() for f in frames)
     frames = tr.generate(start_image=imgs[0].cuda(), iterations=2, all_random=False)
     assert len(frames) == 2
+
+
+@pytest.mark.parametrize("kind,opt", [("fourier", "adam"), ("c4", "adam"), ("c4", "sparse_lion")])
+def test_graphed_step_equals_eager_training(kind, opt):
+    """GraphedStep: the whole autograd-path training step replayed from one CUDA graph follows the eager trajectory
+    (same kernels, same order): weights after 4 steps agree to round-off (the atomics of dL/dw are unordered), the
+    Adam bias corrections and a mid-run lr change reach the captured kernels through the device scalars, and
+    building the graph does not move the weights."""
+    kw = (dict(layer_type="fourier", n=3, n_in=7, n_hidden=7, in_width=4, out_width=3, hidden_layers=1, hidden_width=20)
+          if kind == "fourier" else
+          dict(layer_type="continuous", n=2, in_width=24, out_width=12, hidden_layers=2, hidden_width=20,
+               in_segments=20, out_segments=2, hidden_segments=2))
+    B = 600
+
+    def make():
+        torch.manual_seed(3)
+        net = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **kw)
+        H.initialize_network_polynomial_layers(net, 1.0, 0.0, generator=torch.Generator().manual_seed(0))
+        return net.cuda()
+    g = torch.Generator().manual_seed(1)
+    xs = [(torch.rand(B, kw["in_width"], generator=g) * 2 - 1).cuda() for _ in range(4)]
+    ys = [(torch.rand(B, kw["out_width"], generator=g) * 2 - 1).cuda() for _ in range(4)]
+    Opt = H.Adam if opt == "adam" else H.SparseLion
+    a, b = make(), make()
+    oa, ob = Opt(a.parameters(), lr=1e-3), Opt(b.parameters(), lr=1e-3, capturable=True)
+    before = [p.detach().clone() for p in b.parameters()]
+    gs = H.GraphedStep(b, ob, xs[0], ys[0])
+    for p, q in zip(b.parameters(), before):
+        assert torch.equal(p, q)
+    for k in range(4):
+        if k == 2:
+            for grp in oa.param_groups + ob.param_groups:
+                grp["lr"] = 3e-4
+        oa.zero_grad(set_to_none=True)
+        la = torch.nn.functional.mse_loss(a(xs[k]).flatten(), ys[k].flatten())
+        la.backward()
+        oa.step()
+        lb = gs.step(xs[k], ys[k])
+        assert abs(la.item() - lb.item()) <= 1e-5 * abs(la.item())
+    for p, q in zip(a.parameters(), b.parameters()):
+        if opt == "adam":
+            assert (p - q).abs().max().item() <= 2e-5
+        else:       # sign updates: entries with round-off-sized momenta may flip
+            assert ((p - q).abs() > 1e-6).float().mean().item() <= 2e-3
+
+
+def test_neighborhood_trainer_with_cuda_graph_matches_eager():
+    """NeighborhoodTrainer(cuda_graph=True): full batches replay one CUDA graph fed by the gather kernel, the ragged
+    last block runs eagerly; same loss history as the eager trainer (to round-off), lr schedule included."""
+    g = torch.Generator().manual_seed(0)
+    img = torch.rand(3, 40, 44, generator=g) * 2 - 1
+    hist = []
+    for graph in (False, True):
+        cfg = H.neighborhood_config(batch_size=256, max_epochs=3)
+        cfg.mlp.n, cfg.mlp.input.segments, cfg.mlp.output.segments = 2, 10, 2
+        cfg.mlp.hidden.width, cfg.mlp.hidden.layers = 20, 2
+        cfg.data.outside = 2
+        cfg.optimizer.lr = 1e-3
+        torch.manual_seed(5)
+        tr = H.NeighborhoodTrainer(cfg, [img], seed=1, cuda_graph=graph)
+        hist.append(tr.fit())
+    assert len(hist[0]) == 3 and hist[0][-1] < hist[0][0]
+    for a, b in zip(*hist):
+        assert abs(a - b) <= 2e-4 * abs(a)
