@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--impl", default="hoir_b200", choices=["hoir_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the global batch stays 2^20 pixels, every rank takes 2^20 / N (default: weak)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -179,6 +181,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.strong:
+        global BATCH
+        BATCH = (1 << 20) // world
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (hoir_b200 has no CPU path); "
                          "use --impl reference for the CPU formulation")
@@ -305,7 +310,7 @@ def main():
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": trainer.launches_per_step * args.steps, "clocks": clocks,
                 "final_loss": final_loss}
