@@ -1133,7 +1133,16 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
   HOIR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
   if (occ < 1 || getenv("HOIR_GRID_ONE_PER_SM") != nullptr) occ = 1;   // the switch is for A/B measurements
   const long long cap = (long long)num_sms_fused() * occ;
-  const int grid = (int)(tiles < cap ? tiles : cap);
+  int grid = (int)(tiles < cap ? tiles : cap);
+  if (tail_inside) {
+    // a small batch must not leave the optimizer tail to one or two CTAs (measured, C1 at batch 256: 70 us with the
+    // tail on the single tile's CTA, 37 + 4 us as two launches): CTAs beyond the tile count skip the tile loop and
+    // join the grid barrier and the walk over the parameters
+    static const bool no_extra = getenv("HOIR_NO_TAIL_CTAS") != nullptr;
+    long long want = (p.tail.woff[p.tail.num_layers] + 1023) / 1024;
+    if (want > cap) want = cap;
+    if (!no_extra && grid < want) grid = (int)want;
+  }
   if (tail_inside) {
     // the grid barrier needs every CTA resident: cooperative launch (grid <= #SMs, 1 CTA per SM)
     void* args[] = {&p};
