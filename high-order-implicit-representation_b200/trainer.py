@@ -63,7 +63,7 @@ class ImageTrainer:
     pixel ranges in random order with coordinates and targets generated in-kernel (no dataset in HBM)."""
 
     def __init__(self, cfg, image: Union[str, Tensor], device: str = "cuda", sampling: str = "shuffle",
-                 process_group=None, seed: int = 0, drop_last: bool = True):
+                 process_group=None, seed: int = 0, drop_last: bool = True, cuda_graph: bool = False):
         if sampling not in ("shuffle", "tiles"):
             raise ValueError(f"sampling {sampling} not recognized")
         self.cfg = to_cfg(cfg)
@@ -87,6 +87,15 @@ class ImageTrainer:
         else:                                   # per-layer kernels under autograd (Fourier, polynomial, ...)
             conf = self.net.configure_optimizers()
             self.optimizer = conf[0][0] if isinstance(conf, tuple) else conf
+        self._graphed = None
+        if cuda_graph and self.fused is None and self.world == 1:
+            # networks without a fused kernel (Fourier, ...): full batches replay ONE CUDA graph of the whole step
+            from .engine import GraphedStep
+            self.optimizer.capturable = True
+            self._graphed = GraphedStep(
+                self.net, self.optimizer,
+                torch.zeros((self.batch_size, int(self.cfg.mlp.input.width)), device=self.device),
+                torch.zeros((self.batch_size, int(self.cfg.mlp.output.width)), device=self.device))
         self._pos = self._targets = None
         self.history: List[float] = []
 
@@ -112,6 +121,8 @@ class ImageTrainer:
         if x is None:
             pos, tg = self._dataset()
             x, y = pos[first:first + count], tg[first:first + count]
+        if self._graphed is not None and x.shape[0] == self.batch_size:
+            return self._graphed.step(x, y).reshape(1)
         self.optimizer.zero_grad(set_to_none=True)
         loss = self.net.training_step((x, y), 0)
         loss.backward()

@@ -56,6 +56,13 @@ def test_image_trainer_autograd_path_for_fourier():
     assert tr.fused is None                                     # per-layer (tensor-core) kernels under autograd
     hist = tr.fit()
     assert len(hist) == 2 and all(h == h for h in hist) and hist[1] < hist[0]
+    # the same run with every full batch replayed from ONE CUDA graph (GraphedStep): same trajectory
+    torch.manual_seed(0)
+    tg = H.ImageTrainer(cfg, _card(48, 64), sampling="shuffle", cuda_graph=True)
+    assert tg._graphed is not None
+    hist_g = tg.fit()
+    for a, b in zip(hist, hist_g):
+        assert abs(a - b) <= 2e-4 * abs(a)
 
 
 def test_plateau_schedule_matches_torch():
