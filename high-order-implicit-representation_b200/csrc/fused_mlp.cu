@@ -71,6 +71,7 @@ struct FusedParams {
   float* y;
   int post_scale;
   int seg0, nodes0, pow2_0;
+  long long alt_off;         // float offset of the [in][half][node][hid/2] copy of the layer-0 weights (tensor-core entries)
   int identity;              // every layer is a Polynomial (single window, xi = x)
   int normalize;
   float norm_eps;
@@ -572,6 +573,23 @@ __global__ void pack_kernel(const float* __restrict__ w, float* __restrict__ pac
   }
 }
 
+// second copy of the layer-0 weights for the tensor-core training kernel: [in][half][node][hid / 2], so that the three
+// node rows a thread (one half of the outputs of a sample) reads are ONE contiguous run -- 2-3 cache lines instead
+// of 3-6 when every lane of a warp gathers from a different segment (incoherent batches)
+__global__ void pack_alt_kernel(const float* __restrict__ w, float* __restrict__ alt, int in_f, int out_f, int nodes) {
+  const int hh = out_f / 2;
+  const long long total = (long long)in_f * nodes * out_f;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total;
+       k += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(k % hh);
+    long long r = k / hh;
+    const int q = (int)(r % nodes);
+    r /= nodes;
+    const int half = (int)(r & 1), i = (int)(r >> 1);
+    alt[k] = w[((size_t)(half * hh + c) * in_f + i) * nodes + q];
+  }
+}
+
 bool mlp_desc_ok(const hoir_mlp_desc* m) {
   if (!m || m->num_layers < 2 || m->num_layers > HOIR_MAX_LAYERS) return false;
   for (int l = 0; l < m->num_layers; ++l) {
@@ -868,6 +886,13 @@ const FusedEntry* find_entry(const hoir_mlp_desc* m) {
   return nullptr;
 }
 
+// floats of the alternative layer-0 copy that follows the per-layer regions (0 without a tensor-core training kernel)
+long long alt_floats(const hoir_mlp_desc* m) {
+  const FusedEntry* e = find_entry(m);
+  if (e == nullptr || e->train_tc == nullptr || (m->layers[0].out_features & 7) != 0) return 0;
+  return (long long)m->layers[0].in_features * hoir_layer_nodes(&m->layers[0]) * m->layers[0].out_features;
+}
+
 int fill_params(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
                 const float* packed, FusedParams* p, const char* where) {
   memset(p, 0, sizeof(*p));
@@ -886,6 +911,7 @@ int fill_params(const hoir_mlp_desc* m, long long B, const float* x, const hoir_
   }
   p->packed = packed;
   for (int l = 0; l < m->num_layers; ++l) p->off[l] = hoir_mlp_packed_offset(m, l);
+  p->alt_off = alt_floats(m) > 0 ? hoir_mlp_packed_offset(m, m->num_layers) : -1;
   p->identity = m->layers[0].kind == HOIR_POLYNOMIAL;
   p->seg0 = p->identity ? 1 : m->layers[0].segments;
   p->nodes0 = hoir_layer_nodes(&m->layers[0]);
@@ -923,7 +949,7 @@ extern "C" long long hoir_mlp_packed_offset(const hoir_mlp_desc* m, int layer) {
 
 extern "C" long long hoir_mlp_packed_size(const hoir_mlp_desc* m) {
   if (!mlp_desc_ok(m)) return -1;
-  return hoir_mlp_packed_offset(m, m->num_layers);
+  return hoir_mlp_packed_offset(m, m->num_layers) + alt_floats(m);
 }
 
 extern "C" int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, float* packed,
@@ -939,6 +965,9 @@ extern "C" int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, floa
     if (grid > 148 * 8) grid = 148 * 8;
     pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w[l], packed + hoir_mlp_packed_offset(m, l),
                                                         d.in_features, d.out_features, nodes, op);
+    if (l == 0 && alt_floats(m) > 0)
+      pack_alt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w[0], packed + hoir_mlp_packed_offset(m, m->num_layers),
+                                                             d.in_features, d.out_features, nodes);
   }
   HOIR_CHECK_CUDA(cudaGetLastError());
   return HOIR_OK;
@@ -1020,6 +1049,8 @@ int fill_tail(const hoir_mlp_desc* m, const hoir_opt_desc* o, OptTail* t, const 
     t->woff[l + 1] = boundary_offset(m, l + 1);
     t->poff[l] = hoir_mlp_packed_offset(m, l);
   }
+  t->alt_off = alt_floats(m) > 0 ? hoir_mlp_packed_offset(m, m->num_layers) : -1;
+  t->alt_hh = m->layers[0].out_features / 2;
   t->w = o->flat_w;
   t->g = o->flat_g;
   t->m = o->exp_avg;

@@ -575,7 +575,11 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
         else locate<false>(x0[i], sc0, id, xi);
         hoir::lagrange<N>(lag.X, lag.D, xi, l);
         const int base0 = id * S::STRIDE;
-        contract_fwd_p<N, HH, HP, true>(w0 + ((size_t)i * p.nodes0 + base0) * HP, l, h_);
+        // pairs: the half-major copy -- this thread's N rows are one contiguous run of N * HH floats
+        if constexpr (NQ == 2 && HH % 4 == 0)
+          contract_fwd_p<N, HH, (HH % 4 == 0 ? HH : HP), true>(p.packed + p.alt_off + ((size_t)(i * 2 + hf) * p.nodes0 + base0) * HH, l, h_);
+        else
+          contract_fwd_p<N, HH, HP, true>(w0 + ((size_t)i * p.nodes0 + base0) * HP, l, h_);
         rec_[i] = make_float4(__int_as_float(base0), l[0], l[1], l[2]);
       }
       inv_d_ = 1.f;

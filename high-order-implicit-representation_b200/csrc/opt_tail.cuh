@@ -18,6 +18,8 @@ struct OptTail {
   int row0[HOIR_MAX_LAYERS + 1];          // prefix sums of out*in links
   long long woff[HOIR_MAX_LAYERS + 1];    // boundary-layout float offsets; woff[L] = number of parameters
   long long poff[HOIR_MAX_LAYERS];        // packed float offsets
+  long long alt_off;                      // >= 0: second copy of the layer-0 weights, [in][half][node][alt_hh]
+  int alt_hh;
   float* w;
   float* g;                               // [n + 1]: gradients, then the loss accumulator
   float* m;
@@ -142,6 +144,10 @@ __device__ __forceinline__ void opt_tail_rows(const OptTail& t, int gwarp, int n
     }
     if (!t.keep_grad && t.world <= 1) t.g[k] = 0.f;
     t.packed[t.poff[l] + ((long long)i * nodes + q) * op + o] = wk;
+    if (l == 0 && t.alt_off >= 0) {
+      const int half = o >= t.alt_hh;
+      t.packed[t.alt_off + ((long long)(i * 2 + half) * nodes + q) * t.alt_hh + (o - half * t.alt_hh)] = wk;
+    }
   }
   if (gwarp == 0 && lane == 0) {
     if (t.world > 1) {

@@ -160,7 +160,10 @@ int hoir_radial_sample(const float* images, const float* stripes, int M, int C, 
 /* ---- fused whole-network path ---------------------------------------------------------------
  * Packed weights: one flat fp32 buffer, layer l at float offset hoir_mlp_packed_offset(l) with
  * layout [in][node][out_padded] (out_padded = out rounded up to 4).  hoir_mlp_pack fills it from
- * the boundary-layout tensors; it must be refreshed whenever a w changes. */
+ * the boundary-layout tensors; it must be refreshed whenever a w changes.  Networks trained by the tensor-core
+ * kernel carry a second copy of the layer-0 weights behind the last layer, [in][half][node][out/2] (a thread's node
+ * rows are then one contiguous run): hoir_mlp_packed_size includes it, hoir_mlp_pack and the optimizer tail
+ * write both. */
 int hoir_mlp_fused_supported(const hoir_mlp_desc* m);           /* 1 / 0 */
 long long hoir_mlp_packed_size(const hoir_mlp_desc* m);         /* floats, or -1 */
 long long hoir_mlp_packed_offset(const hoir_mlp_desc* m, int layer);
