@@ -290,3 +290,39 @@ def test_quad_thread_variant_of_the_tensor_core_kernel():
                         "-k", "trainer_steps_match_oracle_training or mesh_mode_training_and_render or two_pass"],
                        env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["C2", "C3d", "C1"])
+@pytest.mark.parametrize("mode", ["coherent", "two_pass"])
+def test_packed_copies_follow_the_weights(name, mode):
+    """The kernel-side packed buffer ([in][node][out_pad4] per layer, + for tensor-core networks the half-major second
+    copy of layer 0, [in][half][node][out/2]) is written by hoir_mlp_pack and re-written by the optimizer tail (inside
+    the kernel, or as its own launch after the second pass): after training steps every copy equals the live weights."""
+    ref, net = make_pair(name)
+    tr = H.FusedTrainer(net, optimizer="adam", lr=1e-2)
+    B = 40000 if mode == "two_pass" else 700          # explicit batches >= 32768 take the two-pass path on TC networks
+    for step in range(2):
+        x, y = batch(name, B, seed=step)
+        tr.train_step(x.cuda(), y.cuda())
+    lib, desc = H._lib.lib(), tr.desc
+    layers = net.high_order_layers()
+    end = 0
+    for l, lay in enumerate(layers):
+        w = lay.w.detach()
+        out_f, in_f, nodes = w.shape
+        op = (out_f + 3) // 4 * 4
+        off = lib.hoir_mlp_packed_offset(desc, l)
+        got = tr.packed[off:off + in_f * nodes * op].view(in_f, nodes, op)
+        assert torch.equal(got[:, :, :out_f], w.permute(1, 2, 0)), f"layer {l}"
+        end = off + in_f * nodes * op
+    assert end == lib.hoir_mlp_packed_offset(desc, len(layers))
+    extra = lib.hoir_mlp_packed_size(desc) - end
+    w0 = layers[0].w.detach()
+    if name in ("C2", "C3d"):                          # tensor-core entries carry the second copy
+        out_f, in_f, nodes = w0.shape
+        assert extra == in_f * nodes * out_f
+        alt = tr.packed[end:].view(in_f, 2, nodes, out_f // 2)
+        want = w0.view(2, out_f // 2, in_f, nodes).permute(2, 0, 3, 1)
+        assert torch.equal(alt, want)
+    else:
+        assert extra == 0
