@@ -86,17 +86,18 @@ def _parse(raw: str):
 
 
 def images_config(**overrides) -> Config:
-    """Defaults of /root/reference/config/images_config.yaml + optimizer/sparse_lion.yaml (keys that
-    reach the hot path)."""
+    """The values of /root/reference/config/images_config.yaml + config/optimizer/sparse_lion.yaml, verbatim
+    (polynomial n=3, 2 -> 10 -> 10 -> 10 -> 3, one segment everywhere, rotations=1); the tuned README networks are
+    explicit overrides in examples/implicit_images.py, as on the reference's command lines (README.md:24,38)."""
     cfg = Config(
-        images=["images/newt.jpg"],
+        images=["images/newt.jpg", "images/jupiter.jpg"],
         mlp=dict(layer_type="polynomial", n=3, n_in=None, n_out=None, n_hidden=None,
-                 periodicity=2.0, rescale_output=False, scale=2.0,
-                 input=dict(segments=100, width=4), output=dict(segments=2, width=3),
-                 hidden=dict(segments=2, layers=2, width=10)),
-        max_epochs=50, gpus=1, accelerator="cuda", lr=1e-3, batch_size=256, rotations=2,
-        train=True, checkpoint=None,
-        optimizer=dict(name="sparse_lion", lr=1e-4, scheduler="plateau", patience=10, factor=0.1))
+                 periodicity=None, rescale_output=False, scale=2.0,
+                 input=dict(segments=1, width=2), output=dict(segments=1, width=3),
+                 hidden=dict(segments=1, layers=2, width=10)),
+        max_epochs=50, gpus=1, accelerator="cuda", lr=1e-3, batch_size=256,
+        train=True, checkpoint=None, rotations=1,
+        optimizer=dict(name="sparse_lion", lr=1e-4, patience=5, factor=0.1, gamma=0.9, scheduler="plateau"))
     for k, v in overrides.items():
         cfg[k] = v
     return cfg
@@ -125,7 +126,7 @@ def random_interpolation_config(**overrides) -> Config:
     """Defaults of /root/reference/config/random_interpolation.yaml + optimizer/adam.yaml (``mlp.input.segments``
     is the interpolation ``${image_size}``; ``mlp.input.width`` = (3 + 2*rotations) * num_feature_pixels)."""
     cfg = Config({
-        "folder": "images",
+        "folder": "images", "num_workers": 10, "save_plots": False,
         "mlp": dict(layer_type="continuous", n=3, n_in=None, n_out=None, n_hidden=None,
                     periodicity=2.0, rescale_output=False, scale=2.0,
                     input=dict(segments=64, width=224), output=dict(segments=2, width=3),
@@ -142,11 +143,12 @@ def random_interpolation_config(**overrides) -> Config:
 def generative_config(**overrides) -> Config:
     """Defaults of /root/reference/config/generative_config.yaml + optimizer/sparse_lion.yaml."""
     cfg = Config({
+        "files": ["test_data/test.parquet"],
         "mlp": dict(periodicity=None, rescale_output=False, scale=2.0, width=100, layers=2, segments=2),
         "embedding_size": 384, "input_size": 2, "output_size": 3, "input_segments": 20, "layer_type": "continuous",
         "n": 3, "max_epochs": 50, "gpus": 1, "accelerator": "cuda", "lr": 1e-3, "batch_size": 256, "train": True,
         "checkpoint": None, "rotations": 1,
-        "optimizer": dict(name="sparse_lion", lr=1e-4, scheduler="plateau", patience=10, factor=0.1)})
+        "optimizer": dict(name="sparse_lion", lr=1e-4, patience=5, factor=0.1, gamma=0.9, scheduler="plateau")})
     for k, v in overrides.items():
         cfg[k] = v
     return cfg

@@ -531,16 +531,7 @@ const DenseEntry kDense[] = {
     dense_entry<PieceP<3, 2, false>>(HOIR_DISCONTINUOUS, 3, 2),
 };
 
-int dense_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int dense_sms() { return hoir_num_sms(); }
 
 }  // namespace
 

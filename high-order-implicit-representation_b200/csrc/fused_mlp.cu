@@ -922,16 +922,7 @@ int fill_params(const hoir_mlp_desc* m, long long B, const float* x, const hoir_
   return HOIR_OK;
 }
 
-int num_sms_fused() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int num_sms_fused() { return hoir_num_sms(); }
 
 }  // namespace
 

@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
 #include "hoir_common.cuh"
 
@@ -42,10 +43,27 @@ int hoir_get_workspace(int slot, size_t bytes, void** out) {
     const size_t grow = bytes + bytes / 4;
     HOIR_CHECK_CUDA(cudaMalloc(&w.ptr, grow));
     HOIR_CHECK_CUDA(cudaMemset(w.ptr, 0, grow));   // slot 2 holds the grid-barrier counters
+    // the memset runs on the legacy default stream; callers launch on non-blocking streams (PyTorch side streams,
+    // graph capture warm-ups): make it visible to all of them before the first kernel can read the counters
+    HOIR_CHECK_CUDA(cudaDeviceSynchronize());
     w.bytes = grow;
   }
   *out = w.ptr;
   return HOIR_OK;
+}
+
+int hoir_num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int sms = cache[dev].load(std::memory_order_relaxed);
+  if (sms == 0) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    cache[dev].store(sms, std::memory_order_relaxed);
+  }
+  return sms;
 }
 
 void hoir_free_workspaces() {

@@ -19,6 +19,8 @@ int hoir_set_error(int code, const char* msg, const char* where);
 // slot 2: grid-barrier counters of the in-kernel optimizer tail; memory is zeroed when (re)allocated)
 int hoir_get_workspace(int slot, size_t bytes, void** out);
 void hoir_free_workspaces();
+// multiprocessor count of the CURRENT device (cached per device index: one process may drive several GPUs)
+int hoir_num_sms();
 
 // Lagrange nodes X_j (fp32, exactly the host table of the package) and
 // D_j = 1 / prod_{m != j} (X_j - X_m) (computed in double on the host).

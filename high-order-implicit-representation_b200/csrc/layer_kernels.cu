@@ -356,16 +356,7 @@ int make_params(const hoir_layer_desc* d, LayerParams* p) {
   return HOIR_OK;
 }
 
-int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int num_sms() { return hoir_num_sms(); }
 
 constexpr int kSmemBudget = 96 * 1024;
 

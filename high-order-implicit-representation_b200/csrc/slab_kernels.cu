@@ -337,16 +337,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) slab_fwd_kernel(const FwdParams
   }
 }
 
-int slab_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int slab_sms() { return hoir_num_sms(); }
 
 constexpr size_t kSlabBudget = 88 * 1024;    // + staging: two CTAs per SM
 

@@ -92,7 +92,7 @@ class FusedTrainer:
         self._w_table = _lib.ptr_table(self.w_views)
         self._g_table = _lib.ptr_table(self.g_views)
         self._loss_ptr = _lib.C.c_void_p(self.flat_g.data_ptr() + 4 * self.n_params)
-        self._w_version = -1
+        self._w_version = None
         self._opt = _lib.OptDesc()
         self._opt.kind = _lib.OPT_KIND[optimizer]
         self._opt.flat_w = self.flat_w.data_ptr()
@@ -107,16 +107,23 @@ class FusedTrainer:
         self.kernel_events = None
 
     # ------------------------------------------------------------------------------------------
+    def _versions(self) -> tuple:
+        # ``l.w.data = view`` gives every Parameter its OWN version counter: ``load_state_dict`` / ``p.copy_`` bump
+        # the Parameter's, in-place writes through ``flat_w`` bump flat_w's -- watch all of them
+        return (self.flat_w._version,) + tuple(l.w._version for l in self.layers)
+
     def pack(self) -> None:
         """Refresh the kernel-side packed weights from ``flat_w``.  The fused tail keeps them in sync
         during training; this is only needed after the weights were written from outside
-        (``load_state_dict``, manual edits), which ``_ensure_packed`` detects by the version counter."""
+        (``load_state_dict``, in-place edits of ``w`` / ``flat_w``), which ``_ensure_packed`` detects by the
+        version counters of ``flat_w`` and of every ``w`` Parameter.  Writes through ``w.data`` or raw pointers
+        are invisible to the counters: call ``pack()`` after them."""
         _lib.check(self.lib.hoir_mlp_pack(self.desc, self._w_table, _lib.dptr(self.packed),
                                           _lib.stream_ptr(self.device)))
-        self._w_version = self.flat_w._version
+        self._w_version = self._versions()
 
     def _ensure_packed(self) -> None:
-        if self.flat_w._version != self._w_version:
+        if self._versions() != self._w_version:
             self.pack()
 
     def _loss_scale(self, B: int, global_batch: Optional[int]) -> float:
@@ -170,8 +177,9 @@ class FusedTrainer:
     def train_step(self, x: Tensor, y: Tensor, global_batch: Optional[int] = None) -> Tensor:
         """One optimisation step on explicit samples x[B, in], y[B, out] (the reference's batch).
         Returns a 1-element device tensor holding the loss; valid until the next step."""
-        x2 = x.reshape(x.shape[0], -1)
-        y2 = y.reshape(y.shape[0], -1)
+        x2 = x if x.dim() == 2 else x.flatten(1)          # (an empty share of a global batch is legal: B == 0)
+        y2 = y if y.dim() == 2 else y.flatten(1)
+        x2, y2 = x2.contiguous(), y2.contiguous()
         if x2.shape[1] != self.in_features or y2.shape[1] != self.out_features:
             raise ValueError(f"expected x[B,{self.in_features}] / y[B,{self.out_features}], got "
                              f"{tuple(x.shape)} / {tuple(y.shape)}")
@@ -225,7 +233,7 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x: Tensor) -> Tensor:
-        x2 = x.reshape(x.shape[0], -1).contiguous()
+        x2 = (x if x.dim() == 2 else x.flatten(1)).contiguous()
         y = torch.empty((x2.shape[0], self.out_features), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             self._ensure_packed()

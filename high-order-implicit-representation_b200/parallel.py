@@ -31,6 +31,38 @@ def render_shard(n_pixels: int, rank: int, world: int, align: int = 256) -> Tupl
     return first, max(0, min(per, n_pixels - first))
 
 
+def tile_schedule(order, n_samples: int, batch: int, rank: int, world: int):
+    """Steps of one epoch over contiguous blocks of ``batch`` samples visited in ``order`` (a permutation of the
+    block indices, identical on every rank): a list of ``(first, count, global_batch)`` with the SAME length on every
+    rank.  Ranks take consecutive entries of ``order``; when ``len(order) % world != 0`` the last group has fewer
+    blocks than ranks and the surplus ranks get an EMPTY share ``(0, 0, global_batch)`` -- they still step, because
+    the gradient exchange is collective (include/hoir.h: every rank calls every step)."""
+    steps = []
+    for k in range(0, len(order), world):
+        blocks = order[k:k + world]
+        sizes = [min(batch, n_samples - b * batch) for b in blocks]
+        if rank < len(blocks):
+            steps.append((blocks[rank] * batch, sizes[rank], sum(sizes)))
+        else:
+            steps.append((0, 0, sum(sizes)))
+    return steps
+
+
+def shuffle_schedule(n_samples: int, batch: int, rank: int, world: int, drop_last: bool = True):
+    """Steps of one epoch over a shuffled index vector ``perm`` of ``n_samples`` entries: a list of
+    ``(lo, hi, global_batch)``; this rank's share of a step is ``perm[lo:hi][rank::world]`` (possibly empty on the
+    ragged last batch -- still a step).  ``drop_last`` drops a ragged last global batch like the reference's
+    DataLoader (/root/reference/high_order_implicit_representation/single_image_dataset.py:312-320), except when it
+    is the only one."""
+    steps = []
+    for k in range(0, n_samples, batch * world):
+        hi = min(n_samples, k + batch * world)
+        if drop_last and hi - k < batch * world and k > 0:
+            break
+        steps.append((k, hi, hi - k))
+    return steps
+
+
 def global_loss_scale(local_batch: int, world: int, out_features: int, global_batch: Optional[int] = None) -> float:
     """MSE(mean) over the GLOBAL batch (Quirk Q12): each rank scales its sum of squared errors and
     its gradients by 1/(B_global*out) so that the all-reduced sum equals the single-GPU result."""

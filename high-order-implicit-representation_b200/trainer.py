@@ -114,6 +114,10 @@ class ImageTrainer:
                 g["lr"] = lr
 
     def _step(self, x: Optional[Tensor], y: Optional[Tensor], first: int, count: int, global_batch: int) -> Tensor:
+        """One optimisation step on this rank's share of a global batch.  EVERY rank calls this for EVERY global
+        batch, also with an empty share (count / x.shape[0] == 0): the gradient exchange (in-kernel peer rendezvous or
+        NCCL all-reduce) is collective, a rank that skipped it would leave the others waiting
+        (include/hoir.h: hoir_mlp_train_step_fused_peer)."""
         if self.fused is not None:
             if x is None:
                 return self.fused.train_step_mesh(self.image_u8, self.rotations, first, count, global_batch=global_batch)
@@ -124,14 +128,22 @@ class ImageTrainer:
         if self._graphed is not None and x.shape[0] == self.batch_size:
             return self._graphed.step(x, y).reshape(1)
         self.optimizer.zero_grad(set_to_none=True)
-        loss = self.net.training_step((x, y), 0)
-        loss.backward()
+        local = int(x.shape[0])
+        if local > 0:
+            # MSE(mean) over the GLOBAL batch (Quirk Q12): scale this rank's mean by its share
+            loss = self.net.training_step((x, y), 0) * (local / float(global_batch))
+            loss.backward()
+            loss = loss.detach().reshape(1)
+        else:
+            loss = torch.zeros(1, device=self.device)
         if self.world > 1:
             for p in self.net.parameters():
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
                 parallel.allreduce_sum_(p.grad, None)
-                p.grad /= self.world
+            parallel.allreduce_sum_(loss, None)
         self.optimizer.step()
-        return loss.detach().reshape(1)
+        return loss
 
     def train_epoch(self) -> float:
         """One pass over the image; every rank takes its share of each global batch.  Returns train_loss."""
@@ -142,25 +154,16 @@ class ImageTrainer:
         if self.sampling == "shuffle":
             pos, tg = self._dataset()
             perm = torch.randperm(n, device=self.device, generator=self.gen)
-            for k in range(0, n, bs * self.world):
-                idx = perm[k:k + bs * self.world]
-                if self.drop_last and idx.numel() < bs * self.world and k > 0:
-                    break           # DataLoader(drop_last=True), single_image_dataset.py:312-320
-                mine = idx[self.rank::self.world]
-                if mine.numel() == 0:
-                    continue
-                total += self._step(pos[mine], tg[mine], 0, 0, global_batch=int(idx.numel()))
+            for lo, hi, gb in parallel.shuffle_schedule(n, bs, self.rank, self.world, self.drop_last):
+                mine = perm[lo:hi][self.rank::self.world]   # may be empty on the ragged last batch: still a step
+                total += self._step(pos[mine], tg[mine], 0, 0, global_batch=gb)
                 steps += 1
         else:
             n_blocks = (n + bs - 1) // bs
             order = torch.randperm(n_blocks, device=self.device, generator=self.gen).tolist()
-            for k in range(0, n_blocks, self.world):
-                blocks = order[k:k + self.world]
-                sizes = [min(bs, n - b * bs) for b in blocks]
-                if self.rank < len(blocks):
-                    b = blocks[self.rank]
-                    total += self._step(None, None, b * bs, sizes[self.rank], global_batch=sum(sizes))
-                    steps += 1
+            for first, count, gb in parallel.tile_schedule(order, n, bs, self.rank, self.world):
+                total += self._step(None, None, first, count, global_batch=gb)
+                steps += 1
         self.net.global_step += steps
         return float(total.item()) / max(steps, 1)
 
@@ -208,6 +211,8 @@ class ImageTrainer:
         """Resume: weights, optimizer moments and step, lr schedule, epoch counters."""
         ckpt = torch.load(path, map_location="cpu", weights_only=False)
         self.net.load_state_dict(ckpt["state_dict"])      # in-place into the flat parameter vector
+        if self.fused is not None:
+            self.fused.pack()                             # the kernel-side copy follows explicitly
         self.net.current_epoch = ckpt.get("epoch", 0)
         self.net.global_step = ckpt.get("global_step", 0)
         if ckpt.get("optimizer_states"):

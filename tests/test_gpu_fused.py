@@ -139,6 +139,35 @@ def test_single_launch_step_equals_unfused_tail(name):
     assert abs(tr_a.train_step(x.cuda(), y.cuda()).item() - tr_b.train_step(x.cuda(), y.cuda()).item()) <= 1e-5
 
 
+def test_load_state_dict_after_a_step_reaches_the_kernels():
+    """after any step / render has packed the weights once, ``load_state_dict`` with CLEARLY
+    different weights must reach the fused kernels (forward, render and the next step's loss)."""
+    _, net = make_pair("C2", seed=0)
+    ref2, _ = make_pair("C2", seed=7)
+    assert max((a - b).abs().max().item() for a, b in zip(ref2.state_dict().values(),
+                                                          net.cpu().state_dict().values())) > 1e-2
+    net = net.cuda()
+    tr = H.FusedTrainer(net, optimizer="adam", lr=1e-3)
+    x, y = batch("C2", 2048, seed=3)
+    tr.train_step(x.cuda(), y.cuda())
+    tr.render(8, 8, 2)                                        # packed, and the tail has kept it in sync since
+    net.load_state_dict(ref2.state_dict())
+    assert rel_err(tr.forward(x.cuda()), ref2(x)) <= 1e-5
+    pos = torch.stack([t.cpu() for t in H.positions_from_mesh(8, 8, device="cuda", rotations=2, normalize=True)],
+                      dim=2).reshape(-1, 4)
+    assert rel_err(tr.render(8, 8, 2, post_scale=False), ref2(pos)) <= 1e-5
+    tr.lr = 0.0
+    loss = tr.train_step(x.cuda(), y.cuda()).item()
+    loss_ref = O.mse_training_step(ref2, x, y).item()
+    assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+    # in-place edit through flat_w is seen as well
+    with torch.no_grad():
+        tr.flat_w.mul_(0.5)
+        for p in ref2.parameters():
+            p.mul_(0.5)
+    assert rel_err(tr.forward(x.cuda()), ref2(x)) <= 1e-5
+
+
 def test_fused_empty_and_edge_batches():
     ref, net = make_pair("C2")
     assert net(torch.empty(0, 4, device="cuda")).shape == (0, 3)
