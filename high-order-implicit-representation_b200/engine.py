@@ -23,12 +23,13 @@ from .networks import HighOrderMLP
 
 
 class FusedTrainer:
-    """``keep_grads=True`` leaves ``flat_g`` / ``g_views`` holding the step's gradient (parity tests,
+    """``Net.eval_step`` + ``backward`` + ``optimizer.step`` of a ``HighOrderMLP`` on the fused kernels.
+    ``keep_grads=True`` leaves ``flat_g`` / ``g_views`` holding the step's gradient (parity tests,
     inspection) at the price of one extra memset per step; by default the fused tail zeroes it."""
 
     def __init__(self, mlp: HighOrderMLP, optimizer: str = "adam", lr: float = 1e-4,
                  betas: Optional[tuple] = None, eps: float = 1e-8, weight_decay: float = 0.0,
-                 process_group=None, keep_grads: bool = False):
+                 process_group=None, keep_grads: bool = False, data_parallel: bool = True):
         self.lib = _lib.lib()
         self.mlp = mlp
         self.layers = mlp.high_order_layers()
@@ -50,7 +51,8 @@ class FusedTrainer:
         self.step_count = 0
         self.keep_grads = bool(keep_grads)
         self.group = process_group
-        self.rank, self.world = parallel.world_info(process_group)
+        # data_parallel=False: a single-GPU trainer inside a multi-rank job (no gradient exchange)
+        self.rank, self.world = parallel.world_info(process_group) if data_parallel else (0, 1)
         self.out_features = self.layers[-1].out_features
         self.in_features = self.layers[0].in_features
         sizes = [l.w.numel() for l in self.layers]

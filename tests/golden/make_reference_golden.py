@@ -54,7 +54,8 @@ def install_stubs():
     _stub("omegaconf", DictConfig=dict, OmegaConf=object)
     _stub("hydra")
     _stub("lion_pytorch", Lion=object)
-    sys.path.insert(0, ROOT)      # high_order_layers_torch -> alias package of this repository
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "compat"))   # high_order_layers_torch -> alias package of this repository
     sys.path.insert(0, REF)
 
 

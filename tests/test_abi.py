@@ -102,7 +102,17 @@ def test_no_cpu_fallback():
 
 def test_dependency_alias_package_exports_what_the_reference_imports():
     """The reference reaches the hot path through `high_order_layers_torch.*` imports; the alias
-    package at the repository root must satisfy every one of them, star imports included (Quirk Q7)."""
+    package under compat/ must satisfy every one of them, star imports included (Quirk Q7).  It is NOT importable
+    from the repository root alone (a real install of the dependency must never be shadowed by accident)."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert not os.path.exists(os.path.join(root, "high_order_layers_torch"))
+    spec = importlib.util.find_spec("high_order_layers_torch")
+    if spec is not None and not (spec.origin or "").startswith(os.path.join(root, "compat")):
+        pytest.skip("a real high_order_layers_torch is installed: the alias is not exercised here")
+    sys.path.insert(0, os.path.join(root, "compat"))
     ns = {}
     exec("from high_order_layers_torch.layers import *\n"
          "from high_order_layers_torch.networks import *\n"
