@@ -112,6 +112,15 @@ _EXPORTS = {
     "hoir_mlp_train_step_fused": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p,
                                             C.POINTER(MeshDesc), C.c_int, C.c_void_p, C.c_float,
                                             C.POINTER(OptDesc), C.c_void_p]),
+    "hoir_mlp_order_supported": (C.c_int, [C.POINTER(MlpDesc)]),
+    "hoir_mlp_batch_sort": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p, C.POINTER(MeshDesc), C.c_void_p,
+                                      C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
+    "hoir_mlp_train_step_order": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p, C.POINTER(MeshDesc),
+                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_void_p), C.c_void_p, C.c_float, C.c_void_p]),
+    "hoir_mlp_train_step_fused_order": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p, C.POINTER(MeshDesc),
+                                                  C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.POINTER(OptDesc),
+                                                  C.POINTER(PeerDesc), C.c_void_p]),
     "hoir_peer_stride": (C.c_longlong, [C.POINTER(MlpDesc)]),
     "hoir_peer_block_floats": (C.c_longlong, [C.POINTER(MlpDesc)]),
     "hoir_mlp_train_step_fused_peer": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p,

@@ -59,6 +59,7 @@ struct Shape {
 struct FusedParams {
   long long B;
   const float* x;            // [B][IN] or nullptr (mesh)
+  const int* perm;           // nullptr, or [B] source index of every sample slot (tensor-core training kernel only)
   hoir_mesh_desc mesh;
   int target_kind;
   const void* target;
@@ -798,6 +799,244 @@ inline size_t gw0_smem_bytes(int nodes0, int hid, long long chunk = GW0_CHUNK) {
   return (size_t)chunk * 4 + 2 * GW0_MAXSEG * 4 + (hid == 40 ? 0 : (size_t)nodes0 * (hid + GW0_PITCH_PAD) * 4);
 }
 
+// ------------------------------------------------------------------------------------------
+// Batch sort by layer-0 cell (explicit batches in arbitrary order: the reference's DataLoader(shuffle=True),
+// /root/reference/high_order_implicit_representation/single_image_dataset.py:312-320).
+// MSE(mean) and the summed gradients do not depend on the order of the samples, so the training kernel may visit them
+// in any order; visited by (segment of x0, segment of x1[, low bits of the segments of x2, x3]) the layer-0 weight
+// reads of a warp fall into one or two node windows again and the in-kernel run-merged owner walk of the layer-0
+// dL/dw works as for contiguous pixel tiles -- no dL/dy workspace (185 MB written + re-read per 2^20 samples), no
+// second pass.  Counting sort: (1) key + rank within its bin by one returning atomic per sample, the last CTA
+// scans the histogram; (2) scatter.  Keys only need to be coherent, not exact.
+// ------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256, SORT_MAX_BINS = 1 << 18;
+struct SortPlan {
+  int in_f, seg0, shift, cells_1d, minor_bits, bins, bins_pad;   // bins_pad: multiple of 4 * SORT_THREADS (one chunk)
+  float segf;
+};
+__device__ __forceinline__ int sort_key(const SortPlan& sp, const float* xv) {
+  const int s0 = hoir::segment_index(xv[0], 1.f, 2.f, sp.segf, sp.seg0) >> sp.shift;
+  const int s1 = sp.in_f > 1 ? hoir::segment_index(xv[1], 1.f, 2.f, sp.segf, sp.seg0) >> sp.shift : 0;
+  int key = s0 * sp.cells_1d + s1;
+  if (sp.minor_bits) {   // rotated coordinates (x2, x3 are functions of x0, x1): 2-3 neighbouring segments per cell
+    const int s2 = hoir::segment_index(xv[2], 1.f, 2.f, sp.segf, sp.seg0) & 3;
+    const int s3 = hoir::segment_index(xv[3], 1.f, 2.f, sp.segf, sp.seg0) & 3;
+    key = (key << 4) | (s2 << 2) | s3;
+  }
+  return key;
+}
+// x != nullptr: sample b = row b of x[B][in_f]; else sample b = pixel idx[b] (or first_pixel + b) of the mesh
+__device__ __forceinline__ void sort_load(const SortPlan& sp, const float* __restrict__ x, const hoir_mesh_desc& mesh,
+                                          const int* __restrict__ idx, long long b, float* xv) {
+  if (x != nullptr) {
+    if (sp.in_f == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + b);
+      xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = i < sp.in_f ? __ldg(x + b * sp.in_f + i) : 0.f;
+    }
+  } else {
+    xv[0] = xv[1] = xv[2] = xv[3] = 0.f;
+    hoir::mesh_position(mesh, idx != nullptr ? (long long)__ldg(idx + b) : mesh.first_pixel + b, xv, 2);
+  }
+}
+// One cooperative launch, five phases separated by grid barriers (the whole pre-pass is latency-bound: as three
+// launches + a memset + a single-CTA scan it took 94 us at any batch size):
+//   P0 zero the histogram   P1 key + rank within its bin (one returning atomic per sample)
+//   P2 per-chunk sums (1024 bins per chunk)   P3 exclusive scan (chunk base = sum of the preceding chunk sums)
+//   P4 out[offset[key] + rank] = source index of the sample (its row, or its pixel)
+struct SortArgs {
+  SortPlan sp;
+  long long B;
+  const float* x;
+  hoir_mesh_desc mesh;
+  const int* idx;
+  long long first;
+  unsigned int* sync;        // [2] phase counter / depart counter (zero on entry, re-armed by the last CTA to leave)
+  unsigned int* partial;     // [bins_pad / 1024]
+  unsigned int* hist;        // [bins_pad]
+  uint2* keyrank;            // [B]
+  int* out;                  // [B]
+};
+__device__ __forceinline__ void grid_sync_phase(unsigned int* counter, unsigned int phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = phase * gridDim.x;
+    unsigned int spins = 0;
+    while (hoir::ld_acquire_u32(counter) < target) {
+      __nanosleep(32);
+      if (++spins > (1u << 26)) __trap();   // a CTA never arrived: fail loudly instead of hanging
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ unsigned int block_sum_256(unsigned int v, unsigned int* sh) {   // all threads get the sum
+  v = __reduce_add_sync(0xffffffffu, v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned int t = 0;
+#pragma unroll
+  for (int w = 0; w < SORT_THREADS / 32; ++w) t += sh[w];
+  return t;
+}
+__global__ void __launch_bounds__(SORT_THREADS) batch_sort_kernel(const SortArgs a) {
+  __shared__ unsigned int sh[SORT_THREADS / 32 + 1];
+  const long long gtid = blockIdx.x * (long long)SORT_THREADS + threadIdx.x, gthreads = (long long)gridDim.x * SORT_THREADS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint4* hist4 = reinterpret_cast<uint4*>(a.hist);
+  for (long long k = gtid; k < a.sp.bins_pad / 4; k += gthreads) hist4[k] = make_uint4(0u, 0u, 0u, 0u);
+  grid_sync_phase(a.sync, 1);
+  for (long long b = gtid; b < a.B; b += gthreads) {
+    float xv[4];
+    sort_load(a.sp, a.x, a.mesh, a.idx, b, xv);
+    const int key = sort_key(a.sp, xv);
+    a.keyrank[b] = make_uint2((unsigned)key, atomicAdd(&a.hist[key], 1u));
+  }
+  grid_sync_phase(a.sync, 2);
+  const int nchunks = a.sp.bins_pad / (4 * SORT_THREADS);
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const uint4 v = __ldcg(hist4 + (size_t)c * SORT_THREADS + tid);
+    const unsigned int t = block_sum_256(v.x + v.y + v.z + v.w, sh);
+    if (tid == 0) a.partial[c] = t;
+  }
+  grid_sync_phase(a.sync, 3);
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    unsigned int pre = 0;
+    for (int j = tid; j < c; j += SORT_THREADS) pre += __ldcg(a.partial + j);
+    const unsigned int base = block_sum_256(pre, sh);
+    uint4 v = __ldcg(hist4 + (size_t)c * SORT_THREADS + tid);
+    const unsigned int mine = v.x + v.y + v.z + v.w;
+    unsigned int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    __syncthreads();
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    unsigned int wbase = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; ++w) wbase += w < warp ? sh[w] : 0u;
+    const unsigned int e0 = base + wbase + incl - mine, e1 = e0 + v.x, e2 = e1 + v.y, e3 = e2 + v.z;
+    hist4[(size_t)c * SORT_THREADS + tid] = make_uint4(e0, e1, e2, e3);
+  }
+  grid_sync_phase(a.sync, 4);
+  for (long long b = gtid; b < a.B; b += gthreads) {
+    const uint2 kr = a.keyrank[b];
+    a.out[__ldcg(a.hist + kr.x) + kr.y] = a.idx != nullptr ? __ldg(a.idx + b) : (int)(a.first + b);
+  }
+  if (tid == 0 && atomicAdd(&a.sync[1], 1u) == gridDim.x - 1) {   // the last CTA to leave re-arms the counters
+    a.sync[0] = 0u;
+    a.sync[1] = 0u;
+    __threadfence();
+  }
+}
+// coherence probe: fraction of (sample, input) pairs whose layer-0 segment differs from the previous sample's in the
+// sorted order (image pixels: ~0.03; independent random inputs: ~0.5)
+__global__ void __launch_bounds__(SORT_THREADS) sort_breaks_kernel(const SortPlan sp, long long B, const float* __restrict__ x,
+                                                                   const hoir_mesh_desc mesh, const int* __restrict__ order,
+                                                                   unsigned long long* __restrict__ breaks) {
+  unsigned int local = 0;
+  for (long long k = blockIdx.x * (long long)SORT_THREADS + threadIdx.x + 1; k < B; k += (long long)gridDim.x * SORT_THREADS) {
+    float a[4], c[4];
+    if (x != nullptr) {
+      sort_load(sp, x, mesh, nullptr, order[k - 1], a);
+      sort_load(sp, x, mesh, nullptr, order[k], c);
+    } else {
+      sort_load(sp, nullptr, mesh, order, k - 1, a);
+      sort_load(sp, nullptr, mesh, order, k, c);
+    }
+    for (int i = 0; i < sp.in_f && i < 4; ++i)
+      local += hoir::segment_index(a[i], 1.f, 2.f, sp.segf, sp.seg0) != hoir::segment_index(c[i], 1.f, 2.f, sp.segf, sp.seg0);
+  }
+  local = (unsigned int)hoir::warp_sum((float)local);   // < 2^24 per warp: exact in fp32
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(breaks, (unsigned long long)local);
+}
+
+bool make_sort_plan(const hoir_layer_desc& l0, SortPlan* sp) {
+  if ((l0.kind != HOIR_CONTINUOUS && l0.kind != HOIR_DISCONTINUOUS) || l0.length != 2.f || l0.periodicity > 0.f) return false;
+  if (l0.in_features < 1 || l0.in_features > 4) return false;
+  sp->in_f = l0.in_features;
+  sp->seg0 = l0.segments;
+  sp->segf = (float)l0.segments;
+  sp->minor_bits = l0.in_features == 4 ? 4 : 0;
+  sp->shift = 0;
+  auto bins_of = [&](int sh) {
+    const long long c = ((l0.segments - 1) >> sh) + 1;
+    return (l0.in_features > 1 ? c * c : c) << sp->minor_bits;
+  };
+  while (bins_of(sp->shift) > SORT_MAX_BINS) ++sp->shift;
+  sp->cells_1d = l0.in_features > 1 ? ((l0.segments - 1) >> sp->shift) + 1 : 1;
+  sp->bins = (int)bins_of(sp->shift);
+  const int q = 4 * SORT_THREADS;
+  sp->bins_pad = (sp->bins + q - 1) / q * q;
+  return true;
+}
+
+// perm_out[0 .. B): the samples' source indices in cell order.  x: rows of x; else pixels idx[b] / first_pixel + b.
+int batch_sort_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh, const int* idx,
+                      int* perm_out, float* breaks_host, cudaStream_t st, const char* where) {
+  SortPlan sp;
+  if (!mlp_desc_ok(m) || !make_sort_plan(m->layers[0], &sp))
+    return hoir_set_error(HOIR_EUNSUPPORTED, "batch sort: layer 0 must be piecewise with 1..4 inputs, length 2", where);
+  if (B < 0 || B > 0x7fffffffLL) return hoir_set_error(HOIR_EINVAL, "bad batch size", where);
+  if ((x == nullptr) == (mesh == nullptr)) return hoir_set_error(HOIR_EINVAL, "exactly one of x / mesh must be given", where);
+  if (mesh != nullptr && (mesh->rotations * 2 != sp.in_f || mesh->rows < 1 || mesh->cols < 1 ||
+                          (long long)mesh->rows * mesh->cols > 0x7fffffffLL))
+    return hoir_set_error(HOIR_EINVAL, "mesh descriptor does not match layer 0", where);
+  if (B == 0) {
+    if (breaks_host) *breaks_host = 0.f;
+    return HOIR_OK;
+  }
+  if (!perm_out) return hoir_set_error(HOIR_EINVAL, "null output pointer", where);
+  const size_t n_head = 64 + 1024, n_hist = (size_t)sp.bins_pad * 4, n_kr = (size_t)B * 8;
+  void* ws = nullptr;
+  if (int err = hoir_get_workspace(3, n_head + n_hist + n_kr, &ws)) return err;   // (zeroed when allocated)
+  SortArgs a;
+  memset(&a, 0, sizeof(a));
+  a.sp = sp;
+  a.B = B;
+  a.x = x;
+  if (mesh) a.mesh = *mesh;
+  a.idx = idx;
+  a.first = mesh ? mesh->first_pixel : 0;
+  a.sync = static_cast<unsigned int*>(ws);
+  unsigned long long* brk = reinterpret_cast<unsigned long long*>(static_cast<char*>(ws) + 16);
+  a.partial = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 64);
+  a.hist = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + n_head);
+  a.keyrank = reinterpret_cast<uint2*>(static_cast<char*>(ws) + n_head + n_hist);
+  a.out = perm_out;
+  const hoir_mesh_desc& md = a.mesh;
+  int occ = 1;
+  HOIR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, batch_sort_kernel, SORT_THREADS, 0));
+  if (occ < 1) occ = 1;
+  if (occ > 4) occ = 4;
+  const long long cap = (long long)hoir_num_sms() * occ;
+  long long g = (B + 2 * SORT_THREADS - 1) / (2 * SORT_THREADS);
+  if (g < hoir_num_sms()) g = hoir_num_sms();
+  const int grid = (int)(g < cap ? g : cap);
+  {
+    void* args[] = {&a};
+    HOIR_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)batch_sort_kernel, dim3(grid), dim3(SORT_THREADS), args, 0, st));
+  }
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  if (breaks_host != nullptr) {
+    HOIR_CHECK_CUDA(cudaMemsetAsync(brk, 0, sizeof(unsigned long long), st));
+    sort_breaks_kernel<<<grid, SORT_THREADS, 0, st>>>(sp, B, x, md, perm_out, brk);
+    unsigned long long h = 0;
+    HOIR_CHECK_CUDA(cudaMemcpyAsync(&h, brk, sizeof(h), cudaMemcpyDeviceToHost, st));
+    HOIR_CHECK_CUDA(cudaStreamSynchronize(st));
+    *breaks_host = (float)((double)h / ((double)B * sp.in_f));
+  }
+  return HOIR_OK;
+}
+
 struct FusedEntry {
   int kind, n, in, hid, out, nh, segh, sego;
   void (*fwd)(const FusedParams);
@@ -1093,11 +1332,20 @@ int launch_tail(const OptTail& t, cudaStream_t stream) {
 int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
                  int target_kind, const void* target, const float* gy_ext, const float* packed,
                  float* const* gw, float* loss_sum, float loss_scale, const OptTail* tail, void* stream,
-                 const char* where) {
+                 const char* where, const int* perm = nullptr) {
   const FusedEntry* e = find_entry(m);
   if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", where);
   FusedParams p;
-  if (int err = fill_params(m, B, x, mesh, packed, &p, where)) return err;
+  hoir_mesh_desc mesh_all;
+  if (perm != nullptr && mesh != nullptr) {   // perm holds absolute pixels: the range check of fill_params does not apply
+    mesh_all = *mesh;
+    mesh_all.first_pixel = 0;
+    if (B > (long long)mesh->rows * mesh->cols) return hoir_set_error(HOIR_EINVAL, "more samples than pixels", where);
+    if (int err = fill_params(m, 0, x, &mesh_all, packed, &p, where)) return err;
+    p.B = B;
+    if (!packed && B > 0) return hoir_set_error(HOIR_EINVAL, "null packed weights", where);
+  } else if (int err = fill_params(m, B, x, mesh, packed, &p, where)) return err;
+  p.perm = perm;
   if (B == 0) {   // nothing to add; with peers the exchange must still happen (the other ranks wait for it)
     if (tail != nullptr && tail->world > 1) return launch_tail(*tail, (cudaStream_t)stream);
     return HOIR_OK;
@@ -1124,8 +1372,10 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
   static const bool no_2p = getenv("HOIR_NO_TWOPASS") != nullptr;
   static const bool no_fuse = getenv("HOIR_NO_FUSED_TAIL") != nullptr;   // A/B switch: tail as its own launch
   const bool use_tc = e->train_tc != nullptr && !no_tc;
+  if (perm != nullptr && !use_tc)
+    return hoir_set_error(HOIR_EUNSUPPORTED, "sample permutations need the tensor-core training kernel", where);
   const int in_f = m->layers[0].in_features, hid = m->layers[0].out_features;
-  const bool two_pass = use_tc && x != nullptr && B >= 32768 && !no_2p && p.seg0 <= GW0_MAXSEG && hid <= 64 &&
+  const bool two_pass = use_tc && x != nullptr && perm == nullptr && B >= 32768 && !no_2p && p.seg0 <= GW0_MAXSEG && hid <= 64 &&
                         m->layers[0].n == 3 && gw0_smem_bytes(p.nodes0, hid) <= 200 * 1024;
   if (two_pass) {
     const size_t b_al = ((size_t)B + 63) & ~(size_t)63;
@@ -1222,6 +1472,43 @@ extern "C" int hoir_mlp_train_step_fused(const hoir_mlp_desc* m, long long B, co
   for (int l = 0; l < m->num_layers; ++l) gw[l] = opt->flat_g + t.woff[l];
   return train_launch(m, B, x, mesh, target_kind, target, nullptr, opt->packed, gw,
                       opt->flat_g + t.woff[m->num_layers], loss_scale, &t, stream, "hoir_mlp_train_step_fused");
+}
+
+extern "C" int hoir_mlp_order_supported(const hoir_mlp_desc* m) {
+  const FusedEntry* e = find_entry(m);
+  SortPlan sp;
+  return e != nullptr && e->train_tc != nullptr && getenv("HOIR_NO_TC") == nullptr && make_sort_plan(m->layers[0], &sp);
+}
+
+extern "C" int hoir_mlp_batch_sort(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
+                                   const int* pixels, int* order, float* breaks, void* stream) {
+  if (x != nullptr && pixels != nullptr)
+    return hoir_set_error(HOIR_EINVAL, "pixel indices need a mesh, not x", "hoir_mlp_batch_sort");
+  return batch_sort_launch(m, B, x, mesh, pixels, order, breaks, (cudaStream_t)stream, "hoir_mlp_batch_sort");
+}
+
+extern "C" int hoir_mlp_train_step_order(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
+                                         const int* order, int target_kind, const void* target, const float* gy_ext,
+                                         const float* packed, float* const* gw, float* loss_sum, float loss_scale,
+                                         void* stream) {
+  if (!order && B > 0) return hoir_set_error(HOIR_EINVAL, "null order", "hoir_mlp_train_step_order");
+  return train_launch(m, B, x, mesh, target_kind, target, gy_ext, packed, gw, loss_sum, loss_scale, nullptr,
+                      stream, "hoir_mlp_train_step_order", order);
+}
+
+extern "C" int hoir_mlp_train_step_fused_order(const hoir_mlp_desc* m, long long B, const float* x,
+                                               const hoir_mesh_desc* mesh, const int* order, int target_kind,
+                                               const void* target, float loss_scale, const hoir_opt_desc* opt,
+                                               const hoir_peer_desc* peers, void* stream) {
+  const char* where = "hoir_mlp_train_step_fused_order";
+  if (!order && B > 0) return hoir_set_error(HOIR_EINVAL, "null order", where);
+  OptTail t;
+  if (int err = fill_tail(m, opt, &t, where, peers)) return err;
+  float* gw[HOIR_MAX_LAYERS] = {};
+  float* gbase = peers ? t.g : opt->flat_g;
+  for (int l = 0; l < m->num_layers; ++l) gw[l] = gbase + t.woff[l];
+  return train_launch(m, B, x, mesh, target_kind, target, nullptr, opt->packed, gw, gbase + t.woff[m->num_layers],
+                      loss_scale, &t, stream, where, order);
 }
 
 extern "C" long long hoir_peer_stride(const hoir_mlp_desc* m) { return mlp_desc_ok(m) ? peer_stride(m) : -1; }

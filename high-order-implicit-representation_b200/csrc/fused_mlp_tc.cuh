@@ -537,8 +537,19 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
     uint32_t q_chunk = 0, q_unit = 0, n_tile = 0;
     // layer 0 (FFMA, weights through L1) of one tile: this thread's 20 outputs, MaxAbs over the pair
     // (also fetches the tile's targets / external dL/dy: their DRAM latency hides behind the previous tile)
+    // p.perm != nullptr: sample slot b reads SOURCE index perm[b] -- a row of x / target / gy_ext (explicit batches sorted
+    // by layer-0 cell, hoir_mlp_batch_sort) or an absolute pixel of the mesh (shuffled pixel indices).  The index of the
+    // tile after the one being loaded is prefetched one layer0 call ahead, so only one dependent load is exposed.
+    int permN = 0;
+    if (p.perm != nullptr && (long long)blockIdx.x * TS + s < p.B) permN = __ldg(p.perm + (long long)blockIdx.x * TS + s);
     auto layer0 = [&](long long tile_, float* h_, float4* rec_, float& inv_d_, int& kidx_, float* tg_) {
       const long long b_ = tile_ * TS + s;
+      const long long src_ = p.perm != nullptr ? (long long)permN : b_;
+      const long long pix_ = p.perm != nullptr ? (long long)permN : p.mesh.first_pixel + b_;
+      if (p.perm != nullptr) {
+        const long long bn_ = (tile_ + gridDim.x) * TS + s;
+        if (bn_ < p.B) permN = __ldg(p.perm + bn_);
+      }
       float x0[IN];
 #pragma unroll
       for (int i = 0; i < IN; ++i) x0[i] = 0.f;
@@ -547,22 +558,30 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
       if (b_ < p.B) {
         if (p.gy_ext != nullptr) {
 #pragma unroll
-          for (int o = 0; o < OUT; ++o) tg_[o] = __ldg(p.gy_ext + b_ * OUT + o);
+          for (int o = 0; o < OUT; ++o) tg_[o] = __ldg(p.gy_ext + src_ * OUT + o);
         } else if (p.target_kind == HOIR_TARGET_U8_IMAGE) {
           const unsigned char* img = static_cast<const unsigned char*>(p.target);
 #pragma unroll
-          for (int o = 0; o < OUT; ++o) tg_[o] = (float)__ldg(img + (p.mesh.first_pixel + b_) * OUT + o);
+          for (int o = 0; o < OUT; ++o) tg_[o] = (float)__ldg(img + pix_ * OUT + o);
         } else {
 #pragma unroll
-          for (int o = 0; o < OUT; ++o) tg_[o] = __ldg(static_cast<const float*>(p.target) + b_ * OUT + o);
+          for (int o = 0; o < OUT; ++o) tg_[o] = __ldg(static_cast<const float*>(p.target) + src_ * OUT + o);
         }
       }
       if (b_ < p.B) {
         if (p.x != nullptr) {
+          if constexpr (IN == 4) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x) + src_);
+            x0[0] = xv.x; x0[1] = xv.y; x0[2] = xv.z; x0[3] = xv.w;
+          } else if constexpr (IN == 2) {
+            const float2 xv = __ldg(reinterpret_cast<const float2*>(p.x) + src_);
+            x0[0] = xv.x; x0[1] = xv.y;
+          } else {
 #pragma unroll
-          for (int i = 0; i < IN; ++i) x0[i] = __ldg(p.x + b_ * IN + i);
+            for (int i = 0; i < IN; ++i) x0[i] = __ldg(p.x + src_ * IN + i);
+          }
         } else {
-          hoir::mesh_position(p.mesh, p.mesh.first_pixel + b_, x0, IN / 2);
+          hoir::mesh_position(p.mesh, pix_, x0, IN / 2);
         }
       }
 #pragma unroll

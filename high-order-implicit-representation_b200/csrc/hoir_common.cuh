@@ -16,7 +16,8 @@
 
 int hoir_set_error(int code, const char* msg, const char* where);
 // library-owned per-device scratch (slot 0: two-pass layer-0 gradient, slot 1: packed layer weights,
-// slot 2: grid-barrier counters of the in-kernel optimizer tail; memory is zeroed when (re)allocated)
+// slot 2: grid-barrier counters of the in-kernel optimizer tail, slot 3: histogram / keys of the batch sort;
+// memory is zeroed when (re)allocated)
 int hoir_get_workspace(int slot, size_t bytes, void** out);
 void hoir_free_workspaces();
 // multiprocessor count of the CURRENT device (cached per device index: one process may drive several GPUs)

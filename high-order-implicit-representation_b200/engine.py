@@ -13,6 +13,7 @@ and the gradient zeroing run inside the whole-network kernel behind a grid barri
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -105,6 +106,13 @@ class FusedTrainer:
         self._opt.loss_out = self.loss_out.data_ptr()
         #: kernels launched by the last train step
         self.launches_per_step = 1 if (self.world == 1 or self.peer is not None) else 2
+        #: explicit batches x[B, in] in arbitrary order (DataLoader(shuffle=True)): "sorted" = visit the samples in
+        #: layer-0 cell order (hoir_mlp_batch_sort; coordinates of image pixels), "two_pass" = the workspace path
+        #: (independent random inputs), "auto" = decided ONCE from the coherence probe on the first large batch
+        self.batch_order = os.environ.get("HOIR_BATCH_ORDER", "auto")
+        self.sort_min_batch = 8192
+        self._order_buf = None
+        self._sort_ok = bool(self.lib.hoir_mlp_order_supported(self.desc))
         #: set to a list to collect (start, end) CUDA events around the fused training kernel
         self.kernel_events = None
 
@@ -139,7 +147,31 @@ class FusedTrainer:
         o.keep_grad = 1 if self.keep_grads else 0
         return o
 
-    def _step(self, B: int, x_ptr, mesh, target_kind: int, target_ptr, global_batch: Optional[int]) -> Tensor:
+    def _order(self, B: int) -> Tensor:
+        if self._order_buf is None or self._order_buf.numel() < B:
+            self._order_buf = torch.empty(max(B, 1), device=self.device, dtype=torch.int32)
+        return self._order_buf
+
+    def _sorted(self, B: int, x2: Optional[Tensor], mesh, pixels: Optional[Tensor]):
+        """order[B] (device int32) for this batch, or None when the batch should not be sorted."""
+        if not self._sort_ok or B < self.sort_min_batch or self.batch_order == "two_pass":
+            return None
+        order = self._order(B)
+        # below 32768 samples the alternative is the unsorted in-kernel walk (no two-pass mode): always sort
+        probe = _lib.C.c_float(0.0) if (self.batch_order == "auto" and B >= 32768) else None
+        _lib.check(self.lib.hoir_mlp_batch_sort(
+            self.desc, B, _lib.dptr(x2) if x2 is not None else None, mesh,
+            _lib.dptr(pixels, torch.int32) if pixels is not None else None, _lib.dptr(order, torch.int32),
+            _lib.C.byref(probe) if probe is not None else None, _lib.stream_ptr(self.device)))
+        if probe is not None:       # one synchronising probe per trainer: pixel coordinates ~0.03, random inputs ~0.5
+            self.batch_coherence = float(probe.value)
+            self.batch_order = "sorted" if probe.value < 0.25 else "two_pass"
+            if self.batch_order == "two_pass":
+                return None
+        return order
+
+    def _step(self, B: int, x_ptr, mesh, target_kind: int, target_ptr, global_batch: Optional[int],
+              order: Optional[Tensor] = None) -> Tensor:
         """zero_grad + forward + MSE + backward + [all-reduce] + optimizer + weight re-pack.
         Single GPU: ONE launch (the optimizer tail runs inside the whole-network kernel behind a grid
         barrier), or kernel + second pass + tail for large incoherent batches.  Multi-GPU: kernel, one NCCL
@@ -154,7 +186,18 @@ class FusedTrainer:
         if self.kernel_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        if self.world == 1:
+        o_ptr = _lib.dptr(order, torch.int32) if order is not None else None
+        self.last_launches = (1 if (self.world == 1 or self.peer is not None) else 2) + (1 if order is not None else 0)
+        if order is not None and (self.world == 1 or self.peer is not None):
+            if self.peer is not None:
+                self.flat_g = self._peer_bufs[self.step_count & 1]
+            _lib.check(lib.hoir_mlp_train_step_fused_order(
+                self.desc, B, x_ptr, mesh, o_ptr, target_kind, target_ptr, scale, _lib.C.byref(self._opt_desc()),
+                _lib.C.byref(self._peer_desc) if self.peer is not None else None, st))
+        elif order is not None:
+            _lib.check(lib.hoir_mlp_train_step_order(self.desc, B, x_ptr, mesh, o_ptr, target_kind, target_ptr, None,
+                                                     _lib.dptr(self.packed), self._g_table, self._loss_ptr, scale, st))
+        elif self.world == 1:
             _lib.check(lib.hoir_mlp_train_step_fused(self.desc, B, x_ptr, mesh, target_kind, target_ptr,
                                                      scale, _lib.C.byref(self._opt_desc()), st))
         elif self.peer is not None:
@@ -186,7 +229,30 @@ class FusedTrainer:
             raise ValueError(f"expected x[B,{self.in_features}] / y[B,{self.out_features}], got "
                              f"{tuple(x.shape)} / {tuple(y.shape)}")
         with torch.cuda.device(self.device):
-            return self._step(x2.shape[0], _lib.dptr(x2), None, _lib.TARGET_F32, _lib.dptr(y2), global_batch)
+            B = x2.shape[0]
+            order = self._sorted(B, x2, None, None)
+            return self._step(B, _lib.dptr(x2), None, _lib.TARGET_F32, _lib.dptr(y2), global_batch, order)
+
+    def train_step_pixels(self, image_u8: Tensor, rotations: int, pixels: Tensor,
+                          global_batch: Optional[int] = None) -> Tensor:
+        """One optimisation step on the pixels ``pixels[B]`` (int32 row-major indices, any order, e.g. a slice of a
+        random permutation = the reference's DataLoader(shuffle=True) over image_to_dataset rows) of a uint8 image
+        resident in HBM.  No dataset is materialised: the indices are sorted by layer-0 cell and the kernel produces
+        coordinates (positions_from_mesh) and targets (u*2/255-1) from the pixel index -- 4 bytes per sample instead
+        of the 28 of an explicit (x, y) batch."""
+        if image_u8.dtype != torch.uint8 or image_u8.dim() != 3 or image_u8.shape[2] != 3:
+            raise ValueError("expected a uint8 image [rows, cols, 3]")
+        if pixels.dtype != torch.int32 or pixels.dim() != 1:
+            raise TypeError("pixels must be a 1-D int32 tensor")
+        if not self._sort_ok:
+            raise _lib.HoirUnsupported("pixel-index batches need the tensor-core training kernel")
+        B = int(pixels.shape[0])
+        mesh = _lib.make_mesh_desc(image_u8.shape[0], image_u8.shape[1], rotations, True, 0)
+        with torch.cuda.device(self.device):
+            order = self._order(B)
+            _lib.check(self.lib.hoir_mlp_batch_sort(self.desc, B, None, mesh, _lib.dptr(pixels.contiguous(), torch.int32),
+                                                    _lib.dptr(order, torch.int32), None, _lib.stream_ptr(self.device)))
+            return self._step(B, None, mesh, _lib.TARGET_U8_IMAGE, _lib.dptr(image_u8, torch.uint8), global_batch, order)
 
     def train_step_mesh(self, image_u8: Tensor, rotations: int, first_pixel: int, B: int,
                         global_batch: Optional[int] = None) -> Tensor:

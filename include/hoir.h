@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HOIR_VERSION 104
+#define HOIR_VERSION 105
 #define HOIR_MAX_LAYERS 8
 #define HOIR_MAX_N 32          /* max basis functions per segment / Fourier terms          */
 #define HOIR_MAX_ROTATIONS 8
@@ -245,6 +245,34 @@ int hoir_mlp_train_step_fused_peer(const hoir_mlp_desc* m, long long B, const fl
                                    const hoir_mesh_desc* mesh, int target_kind, const void* target,
                                    float loss_scale, const hoir_opt_desc* opt,
                                    const hoir_peer_desc* peers, void* stream);
+
+/* ---- batches in arbitrary sample order (the reference's DataLoader(shuffle=True),
+ * /root/reference/high_order_implicit_representation/single_image_dataset.py:312-320) -------------------------------
+ * MSE(mean) and the summed gradients do not depend on the order in which a batch's samples are visited.
+ * hoir_mlp_batch_sort writes into order[B] the samples' SOURCE indices sorted by layer-0 cell (segment of x0, segment
+ * of x1, low bits of the segments of x2 / x3; a counting sort, 3 small launches):
+ *   x != NULL              : sample b = row b of x[B][in];        order holds row indices 0 .. B-1
+ *   mesh != NULL           : sample b = pixel pixels[b] of the mesh (pixels == NULL: first_pixel + b);
+ *                            order holds absolute pixel indices
+ * The *_order training entries then visit sample slot k as source order[k] (row of x / target / gy_ext, or pixel of the
+ * mesh / uint8 image): a warp's layer-0 weight reads fall into one or two node windows again and the layer-0 dL/dw is
+ * accumulated by the in-kernel run-merged walk, as for contiguous pixel tiles -- no workspace, no second pass.
+ * breaks != NULL (HOST pointer): the call synchronises the stream and returns the fraction of (sample, input) pairs
+ * whose layer-0 segment differs from the previous sample's in sorted order (pixel coordinates: ~0.03; independent
+ * random inputs: ~0.5 -- such batches are better served by hoir_mlp_train_step_fused's two-pass mode).
+ * Layer 0 must be piecewise with <= 4 inputs; networks trained by the tensor-core kernel only (HOIR_EUNSUPPORTED
+ * otherwise).  order is a DEVICE pointer owned by the caller. */
+int hoir_mlp_order_supported(const hoir_mlp_desc* m);          /* 1 / 0: the *_order entries accept this network */
+int hoir_mlp_batch_sort(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
+                        const int* pixels, int* order, float* breaks, void* stream);
+/* hoir_mlp_train_step / hoir_mlp_train_step_fused(_peer) with an explicit visiting order (peers may be NULL) */
+int hoir_mlp_train_step_order(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
+                              const int* order, int target_kind, const void* target, const float* gy_ext,
+                              const float* packed, float* const* gw, float* loss_sum, float loss_scale, void* stream);
+int hoir_mlp_train_step_fused_order(const hoir_mlp_desc* m, long long B, const float* x,
+                                    const hoir_mesh_desc* mesh, const int* order, int target_kind,
+                                    const void* target, float loss_scale, const hoir_opt_desc* opt,
+                                    const hoir_peer_desc* peers, void* stream);
 
 /* ---- optimizers on flat fp32 vectors --------------------------------------------------------
  * torch.optim.Adam (networks.py:94-97) and SparseLion (networks.py:99-102). */
