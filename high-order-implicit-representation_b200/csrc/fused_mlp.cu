@@ -859,21 +859,6 @@ struct SortArgs {
   uint2* keyrank;            // [B]
   int* out;                  // [B]
 };
-__device__ __forceinline__ void grid_sync_phase(unsigned int* counter, unsigned int phase) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    const unsigned int target = phase * gridDim.x;
-    unsigned int spins = 0;
-    while (hoir::ld_acquire_u32(counter) < target) {
-      __nanosleep(32);
-      if (++spins > (1u << 26)) __trap();   // a CTA never arrived: fail loudly instead of hanging
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
 __device__ __forceinline__ unsigned int block_sum_256(unsigned int v, unsigned int* sh) {   // all threads get the sum
   v = __reduce_add_sync(0xffffffffu, v);
   __syncthreads();
@@ -890,21 +875,21 @@ __global__ void __launch_bounds__(SORT_THREADS) batch_sort_kernel(const SortArgs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint4* hist4 = reinterpret_cast<uint4*>(a.hist);
   for (long long k = gtid; k < a.sp.bins_pad / 4; k += gthreads) hist4[k] = make_uint4(0u, 0u, 0u, 0u);
-  grid_sync_phase(a.sync, 1);
+  hoir::grid_sync_phase(a.sync, 1);
   for (long long b = gtid; b < a.B; b += gthreads) {
     float xv[4];
     sort_load(a.sp, a.x, a.mesh, a.idx, b, xv);
     const int key = sort_key(a.sp, xv);
     a.keyrank[b] = make_uint2((unsigned)key, atomicAdd(&a.hist[key], 1u));
   }
-  grid_sync_phase(a.sync, 2);
+  hoir::grid_sync_phase(a.sync, 2);
   const int nchunks = a.sp.bins_pad / (4 * SORT_THREADS);
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const uint4 v = __ldcg(hist4 + (size_t)c * SORT_THREADS + tid);
     const unsigned int t = block_sum_256(v.x + v.y + v.z + v.w, sh);
     if (tid == 0) a.partial[c] = t;
   }
-  grid_sync_phase(a.sync, 3);
+  hoir::grid_sync_phase(a.sync, 3);
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     unsigned int pre = 0;
     for (int j = tid; j < c; j += SORT_THREADS) pre += __ldcg(a.partial + j);
@@ -926,7 +911,7 @@ __global__ void __launch_bounds__(SORT_THREADS) batch_sort_kernel(const SortArgs
     const unsigned int e0 = base + wbase + incl - mine, e1 = e0 + v.x, e2 = e1 + v.y, e3 = e2 + v.z;
     hist4[(size_t)c * SORT_THREADS + tid] = make_uint4(e0, e1, e2, e3);
   }
-  grid_sync_phase(a.sync, 4);
+  hoir::grid_sync_phase(a.sync, 4);
   for (long long b = gtid; b < a.B; b += gthreads) {
     const uint2 kr = a.keyrank[b];
     a.out[__ldcg(a.hist + kr.x) + kr.y] = a.idx != nullptr ? __ldg(a.idx + b) : (int)(a.first + b);
@@ -1165,10 +1150,13 @@ int num_sms_fused() { return hoir_num_sms(); }
 
 }  // namespace
 
-extern "C" int hoir_mlp_fused_supported(const hoir_mlp_desc* m) { return find_entry(m) != nullptr; }
+extern "C" int hoir_mlp_fused_supported(const hoir_mlp_desc* m) {
+  return find_entry(m) != nullptr || (mlp_desc_ok(m) && hoir_fourier_supported(m));
+}
 
 extern "C" long long hoir_mlp_packed_offset(const hoir_mlp_desc* m, int layer) {
   if (!mlp_desc_ok(m) || layer < 0 || layer > m->num_layers) return -1;
+  if (hoir_fourier_supported(m)) return hoir_fourier_packed_offset(m, layer);
   long long off = 0;
   for (int l = 0; l < layer; ++l) {
     const hoir_layer_desc& d = m->layers[l];
@@ -1186,6 +1174,11 @@ extern "C" int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, floa
                              void* stream) {
   if (!mlp_desc_ok(m)) return hoir_set_error(HOIR_EINVAL, "bad network descriptor", "hoir_mlp_pack");
   if (!w || !packed) return hoir_set_error(HOIR_EINVAL, "null pointer", "hoir_mlp_pack");
+  if (hoir_fourier_supported(m)) {
+    for (int l = 0; l < m->num_layers; ++l)
+      if (!w[l]) return hoir_set_error(HOIR_EINVAL, "null weight pointer", "hoir_mlp_pack");
+    return hoir_fourier_pack(m, w, packed, (cudaStream_t)stream);
+  }
   for (int l = 0; l < m->num_layers; ++l) {
     const hoir_layer_desc& d = m->layers[l];
     if (!w[l]) return hoir_set_error(HOIR_EINVAL, "null weight pointer", "hoir_mlp_pack");
@@ -1206,6 +1199,8 @@ extern "C" int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, floa
 extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float* x,
                                 const hoir_mesh_desc* mesh, const float* packed, float* y,
                                 int post_scale, void* stream) {
+  if (mlp_desc_ok(m) && hoir_fourier_supported(m))
+    return hoir_fourier_forward(m, B, x, mesh, packed, y, post_scale, (cudaStream_t)stream);
   const FusedEntry* e = find_entry(m);
   if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", "hoir_mlp_forward");
   FusedParams p;
@@ -1281,6 +1276,7 @@ int fill_tail(const hoir_mlp_desc* m, const hoir_opt_desc* o, OptTail* t, const 
   }
   t->alt_off = alt_floats(m) > 0 ? hoir_mlp_packed_offset(m, m->num_layers) : -1;
   t->alt_hh = m->layers[0].out_features / 2;
+  if (hoir_fourier_supported(m)) hoir_fourier_fill_tail(m, t);
   t->w = o->flat_w;
   t->g = o->flat_g;
   t->m = o->exp_avg;
@@ -1333,6 +1329,12 @@ int train_launch(const hoir_mlp_desc* m, long long B, const float* x, const hoir
                  int target_kind, const void* target, const float* gy_ext, const float* packed,
                  float* const* gw, float* loss_sum, float loss_scale, const OptTail* tail, void* stream,
                  const char* where, const int* perm = nullptr) {
+  if (mlp_desc_ok(m) && hoir_fourier_supported(m)) {       // Fourier networks: fused_fourier.cu
+    if (perm != nullptr) return hoir_set_error(HOIR_EUNSUPPORTED, "sample permutations: piecewise networks only", where);
+    if (B == 0 && !(tail != nullptr && tail->world > 1)) return HOIR_OK;
+    return hoir_fourier_train(m, B, x, mesh, target_kind, target, gy_ext, packed, gw, loss_sum, loss_scale, tail,
+                              (cudaStream_t)stream, where);
+  }
   const FusedEntry* e = find_entry(m);
   if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", where);
   FusedParams p;

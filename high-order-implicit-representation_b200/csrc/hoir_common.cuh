@@ -16,7 +16,7 @@
 
 int hoir_set_error(int code, const char* msg, const char* where);
 // library-owned per-device scratch (slot 0: two-pass layer-0 gradient, slot 1: packed layer weights,
-// slot 2: grid-barrier counters of the in-kernel optimizer tail, slot 3: histogram / keys of the batch sort;
+// slot 2: grid-barrier counters of the in-kernel optimizer tail, slot 3: histogram / keys of the batch sort, slot 4: private gradient slabs of the fused Fourier kernel;
 // memory is zeroed when (re)allocated)
 int hoir_get_workspace(int slot, size_t bytes, void** out);
 void hoir_free_workspaces();

@@ -20,6 +20,10 @@ struct OptTail {
   long long poff[HOIR_MAX_LAYERS];        // packed float offsets
   long long alt_off;                      // >= 0: second copy of the layer-0 weights, [in][half][node][alt_hh]
   int alt_hh;
+  // layers whose kernel-side copy is a pre-swizzled hi | lo chunk image [chunk][hi | lo][outp x 32] (tcgen05 B operand of
+  // the fused Fourier kernel) instead of the plain [in][node][out_pad] table: bit l of img_mask
+  int img_mask;
+  int img_nd[HOIR_MAX_LAYERS], img_ipc[HOIR_MAX_LAYERS], img_outp[HOIR_MAX_LAYERS];
   float* w;
   float* g;                               // [n + 1]: gradients, then the loss accumulator
   float* m;
@@ -68,6 +72,31 @@ __device__ __forceinline__ void grid_barrier_depart(unsigned int* sync) {
       sync[1] = 0u;
       __threadfence();
     }
+  }
+}
+
+// Barrier number `phase` (1, 2, ...) of a kernel that synchronises its (fully resident) grid several times on ONE counter
+// that only counts up; the last CTA to leave the kernel re-arms it with grid_sync_rearm.
+__device__ __forceinline__ void grid_sync_phase(unsigned int* counter, unsigned int phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = phase * gridDim.x;
+    unsigned int spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+      __nanosleep(32);
+      if (++spins > (1u << 26)) __trap();   // a CTA never arrived: fail loudly instead of hanging
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void grid_sync_rearm(unsigned int* counter, unsigned int* depart) {
+  if (threadIdx.x == 0 && atomicAdd(depart, 1u) == gridDim.x - 1) {
+    *counter = 0u;
+    *depart = 0u;
+    __threadfence();
   }
 }
 
@@ -143,7 +172,16 @@ __device__ __forceinline__ void opt_tail_rows(const OptTail& t, int gwarp, int n
       t.m[k] = ea * t.b2 + gk * one_m_b2;
     }
     if (!t.keep_grad && t.world <= 1) t.g[k] = 0.f;
-    t.packed[t.poff[l] + ((long long)i * nodes + q) * op + o] = wk;
+    if ((t.img_mask >> l) & 1) {
+      const int c = i / t.img_ipc[l], col = (i - c * t.img_ipc[l]) * t.img_nd[l] + q, outp = t.img_outp[l];
+      float* chunk = t.packed + t.poff[l] + (long long)c * 2 * outp * 32;
+      const unsigned int off = (((unsigned)o >> 2) * 512u + ((unsigned)o & 3u) * 128u +
+                                (((unsigned)col << 2) ^ (((unsigned)o & 3u) << 5))) >> 2;
+      chunk[off] = wk;
+      chunk[outp * 32 + off] = wk - __uint_as_float(__float_as_uint(wk) & 0xffffe000u);   // tf32 residual
+    } else {
+      t.packed[t.poff[l] + ((long long)i * nodes + q) * op + o] = wk;
+    }
     if (l == 0 && t.alt_off >= 0) {
       const int half = o >= t.alt_hh;
       t.packed[t.alt_off + ((long long)(i * 2 + half) * nodes + q) * t.alt_hh + (o - half * t.alt_hh)] = wk;
@@ -173,3 +211,14 @@ __device__ __forceinline__ void opt_tail_in_kernel(const OptTail& t) {
 }
 
 }  // namespace hoir
+
+// fused Fourier-network family (fused_fourier.cu), dispatched from the C ABI entry points of fused_mlp.cu
+bool hoir_fourier_supported(const hoir_mlp_desc* m);
+long long hoir_fourier_packed_offset(const hoir_mlp_desc* m, int layer);     // layer == 3: total floats
+int hoir_fourier_pack(const hoir_mlp_desc* m, const float* const* w, float* packed, cudaStream_t st);
+void hoir_fourier_fill_tail(const hoir_mlp_desc* m, OptTail* t);
+int hoir_fourier_forward(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh,
+                         const float* packed, float* y, int post_scale, cudaStream_t st);
+int hoir_fourier_train(const hoir_mlp_desc* m, long long B, const float* x, const hoir_mesh_desc* mesh, int target_kind,
+                       const void* target, const float* gy_ext, const float* packed, float* const* gw, float* loss_sum,
+                       float loss_scale, const OptTail* tail, cudaStream_t st, const char* where);

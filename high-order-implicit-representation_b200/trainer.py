@@ -152,11 +152,20 @@ class ImageTrainer:
         total = torch.zeros(1, device=self.device)
         steps = 0
         if self.sampling == "shuffle":
-            pos, tg = self._dataset()
             perm = torch.randperm(n, device=self.device, generator=self.gen)
+            # networks on the tensor-core training kernel take the shuffled pixel INDICES (4 B per sample; coordinates
+            # and targets are produced in-kernel, no dataset in HBM); the others gather rows of image_to_dataset
+            by_index = self.fused is not None and self.fused._sort_ok and n < 2 ** 31
+            if by_index:
+                perm = perm.to(torch.int32)
+            else:
+                pos, tg = self._dataset()
             for lo, hi, gb in parallel.shuffle_schedule(n, bs, self.rank, self.world, self.drop_last):
                 mine = perm[lo:hi][self.rank::self.world]   # may be empty on the ragged last batch: still a step
-                total += self._step(pos[mine], tg[mine], 0, 0, global_batch=gb)
+                if by_index:
+                    total += self.fused.train_step_pixels(self.image_u8, self.rotations, mine.contiguous(), global_batch=gb)
+                else:
+                    total += self._step(pos[mine], tg[mine], 0, 0, global_batch=gb)
                 steps += 1
         else:
             n_blocks = (n + bs - 1) // bs

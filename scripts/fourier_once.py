@@ -1,0 +1,17 @@
+"""One fused Fourier training step at a given batch size (for ncu captures).  usage: python scripts/fourier_once.py [B]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import hoir_b200 as H
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
+KW = dict(layer_type="fourier", n=3, n_in=31, n_hidden=31, n_out=3, in_width=4, out_width=3, hidden_layers=1, hidden_width=40)
+net = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **KW).cuda()
+tr = H.FusedTrainer(net, optimizer="adam", lr=1e-4)
+g = torch.Generator(device="cuda").manual_seed(0)
+x = torch.rand(B, 4, device="cuda", generator=g) * 2 - 1
+y = torch.rand(B, 3, device="cuda", generator=g) * 2 - 1
+for _ in range(3):
+    tr.train_step(x, y)
+torch.cuda.synchronize()
+print("loss", tr.train_step(x, y).item())

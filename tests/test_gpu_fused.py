@@ -12,8 +12,8 @@ from helpers import MLP_KW, make_pair, rel_err
 
 pytestmark = pytest.mark.gpu
 
-FUSED = ["C1", "C1d", "C1r2", "C1n2", "C2", "C2r1", "C3d", "poly"]
-UNFUSED = ["C3f", "C4s"]
+FUSED = ["C1", "C1d", "C1r2", "C1n2", "C2", "C2r1", "C3d", "poly", "C3f"]
+UNFUSED = ["C4s"]
 
 
 def batch(name, B, seed=0):
