@@ -40,11 +40,21 @@
 namespace {
 using namespace tc;
 
+// in-kernel cycle accounting of CTA 0 (printed when HOIR_FOURIER_DBG has bit 5 set): compiled in with -DHOIR_FOURIER_TIMERS=1
+#ifndef HOIR_FOURIER_TIMERS
+#define HOIR_FOURIER_TIMERS 0
+#endif
+#if HOIR_FOURIER_TIMERS
+#define FCLK() clock64()
+#else
+#define FCLK() 0LL
+#endif
+
 constexpr int FT = 256;                       // samples per tile == sample threads
 constexpr int F_THREADS = 320, F_STAGES = 4;  // 8 sample warps + MMA warp (8) + loader warp (9)
 constexpr uint32_t F_STAGE_BYTES = 16384;
 constexpr int F_APITCH = 41, F_MAXH = 48;     // activation row pitch (floats); hidden width padded to 16
-constexpr int F_A_COL = 0, F_D_COL = 256, F_T_COL = 384;
+constexpr int F_A_COL = 0, F_D_COL = 256, F_T_COL = 256;   // (the T accumulators of dL/dx reuse the D columns: 2 x 2 x 64)
 constexpr int F_UNIT = 32;                    // samples per dL/dw unit
 constexpr int F_FLUSH = 64;                   // units per accumulator flush: the tensor core's fp32 accumulation truncates,
                                               // so a chain is kept to 2048 samples (measured: 1.7e-4 relative after 22 k)
@@ -52,12 +62,14 @@ constexpr int F_FLUSH = 64;                   // units per accumulator flush: th
 constexpr uint32_t F_U_RS = 256 / 32 * 512, F_U_BYTES = F_UNIT / 4 * F_U_RS;   // 4096 per 4-row group, 32768 per image
 constexpr uint32_t F_G_BYTES = 16384;         // G^T unit: [hi | lo] of the hidden gradient (<= 48 rows) + [hi | lo] of dL/dy (16 rows)
 enum { FB_AFULL0 = 0, FB_AFULL1, FB_AEMPTY0, FB_AEMPTY1, FB_DFULL, FB_DEMPTY, FB_GFULL, FB_TFULL0, FB_TFULL1,
-       FB_TEMPTY0, FB_TEMPTY1, FB_WFULL0, FB_WEMPTY0 = FB_WFULL0 + F_STAGES, FB_UFULL0 = FB_WEMPTY0 + F_STAGES, FB_UFULL1,
-       FB_UEMPTY0, FB_UEMPTY1, FB_GTFULL0, FB_GTFULL1, FB_GTEMPTY0, FB_GTEMPTY1, FB_GWDONE, FB_ACCFREE, FB_COUNT };
+       FB_TEMPTY0, FB_TEMPTY1, FB_WFULL0, FB_WEMPTY0 = FB_WFULL0 + F_STAGES, FB_UFULL0 = FB_WEMPTY0 + F_STAGES,
+       FB_UEMPTY0 = FB_UFULL0 + 3, FB_GTFULL0 = FB_UEMPTY0 + 3, FB_GTFULL1, FB_GTEMPTY0, FB_GTEMPTY1, FB_GWDONE, FB_ACCFREE, FB_COUNT };
 // shared memory plan (bytes): phase 1 [W ring | a1 tile | a2 tile], phase 2 [2 Phi^T stages | 2 G^T units] over it
 constexpr uint32_t FS_W = 0, FS_A1 = F_STAGES * F_STAGE_BYTES, FS_A2 = FS_A1 + FT * F_APITCH * 4;
-constexpr uint32_t FS_U = 0, FS_G = 4 * F_U_BYTES;
-constexpr uint32_t FS_W2 = FS_G + 2 * F_G_BYTES, FS_BAR = FS_W2 + 4096, FS_TOTAL = FS_BAR + 512;
+constexpr int F_USTAGES = 3;                  // Phi^T stages in flight (the workers run up to two stages ahead of the tensor pipe)
+constexpr uint32_t FS_U = 0, FS_G = F_USTAGES * 2 * F_U_BYTES;
+constexpr uint32_t FS_W2 = FS_G + 2 * F_G_BYTES, FS_BAR = FS_W2 + 2048, FS_TOTAL = FS_BAR + 512;
+static_assert(FS_TOTAL <= 227 * 1024, "shared-memory plan");
 static_assert(FS_A2 + FT * F_APITCH * 4 <= FS_W2, "phase-1 tiles end before the output-layer weights");
 
 struct FourierParams {
@@ -122,6 +134,16 @@ __device__ __forceinline__ void fourier_eval(const FourierParams& p, int n, floa
   }
 }
 
+// shared-memory descriptor (SWIZZLE_128B_BASE32B) with an explicit stride between 32-column atoms
+__device__ __forceinline__ uint64_t make_desc_lbo(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
 __device__ __forceinline__ uint32_t chunk_off(uint32_t r, uint32_t c) {   // one-atom-wide operand, rows of 128 B
   return (r >> 2) * 512u + (r & 3u) * 128u + ((c << 2) ^ ((r & 3u) << 5));
 }
@@ -167,8 +189,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
     mbar_init(&bars[FB_TFULL0], 1); mbar_init(&bars[FB_TFULL1], 1);
     mbar_init(&bars[FB_TEMPTY0], FT); mbar_init(&bars[FB_TEMPTY1], FT);
     for (int s = 0; s < F_STAGES; ++s) { mbar_init(&bars[FB_WFULL0 + s], 1); mbar_init(&bars[FB_WEMPTY0 + s], 1); }
-    mbar_init(&bars[FB_UFULL0], FT); mbar_init(&bars[FB_UFULL1], FT);
-    mbar_init(&bars[FB_UEMPTY0], 1); mbar_init(&bars[FB_UEMPTY1], 1); mbar_init(&bars[FB_GWDONE], 1);
+    for (int k = 0; k < F_USTAGES; ++k) { mbar_init(&bars[FB_UFULL0 + k], FT); mbar_init(&bars[FB_UEMPTY0 + k], 1); }
+    mbar_init(&bars[FB_GWDONE], 1);
     mbar_init(&bars[FB_GTFULL0], FT); mbar_init(&bars[FB_GTFULL1], FT);
     mbar_init(&bars[FB_GTEMPTY0], 1); mbar_init(&bars[FB_GTEMPTY1], 1);
     mbar_init(&bars[FB_ACCFREE], FT);
@@ -205,7 +227,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
     // =========================== MMA warp ==============================================================
     const uint32_t leader = elect_one();
     const uint32_t id_fwd = make_idesc(128, p.outp, 0, 0);      // A: TMEM, B: W chunk K-major (rows = outputs)
-    constexpr uint32_t ID_GX = make_idesc(128, 32, 0, 1);       // A: TMEM (G), B: W chunk MN-major (N = basis columns)
+    constexpr uint32_t ID_GX = make_idesc(128, 64, 0, 1);       // A: TMEM (G), B: two W chunks MN-major (N = 64 basis columns)
     uint32_t qw = 0, qa = 0, qd = 0, qt = 0, n_tile = 0;
     auto fwd_layer = [&](int nch) {
       if (qd > 0) mbar_wait(&bars[FB_DEMPTY], (qd - 1) & 1);    // the previous accumulation has been read out
@@ -240,23 +262,28 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
       if (TRAIN) {
         mbar_wait(&bars[FB_GFULL], n_tile & 1);
         const int ksteps = p.outp8 >> 3;
-        for (int c = 0; c < nch1; ++c, ++qw, ++qt) {
+        // two inputs (64 basis columns) per product: the W chunk images of inputs 2 cp, 2 cp + 1 sit in consecutive ring
+        // stages (in0 and hid are even), addressed as ONE MN-major B operand whose column atoms are a stage apart
+        for (int cp = 0; cp < nch1 / 2; ++cp, qw += 2, ++qt) {
           const uint32_t st = qw % F_STAGES, wph = (qw / F_STAGES) & 1, buf = qt & 1, ph = (qt >> 1) & 1;
           mbar_wait(&bars[FB_TEMPTY0 + buf], ph ^ 1);
           mbar_wait(&bars[FB_WFULL0 + st], wph);
+          mbar_wait(&bars[FB_WFULL0 + st + 1], wph);
           fence_after();
           if (leader) {
             const uint32_t wbase = smem_u32(sW + st * F_STAGE_BYTES);
-            const uint64_t dW[2] = {make_desc(wbase, 512), make_desc(wbase + (uint32_t)p.outp * 128u, 512)};
+            const uint64_t dW[2] = {make_desc_lbo(wbase, F_STAGE_BYTES, 512),
+                                    make_desc_lbo(wbase + (uint32_t)p.outp * 128u, F_STAGE_BYTES, 512)};
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
               for (int pass = 0; pass < 3; ++pass)
                 for (int j = 0; j < ksteps; ++j)
-                  mma_ts(tmem + F_T_COL + (blk * 2 + buf) * 32, tmem + F_A_COL + blk * 128 + (pass == 1 ? p.outp8 : 0) + j * 8,
+                  mma_ts(tmem + F_T_COL + (blk * 2 + buf) * 64, tmem + F_A_COL + blk * 128 + (pass == 1 ? p.outp8 : 0) + j * 8,
                          dW[pass == 2] + (uint64_t)((j * 2 * 512) >> 4), ID_GX, (pass | j) != 0);
             umma_commit(&bars[FB_TFULL0 + buf]);
             umma_commit(&bars[FB_WEMPTY0 + st]);
+            umma_commit(&bars[FB_WEMPTY0 + st + 1]);
           }
           __syncwarp();
         }
@@ -270,12 +297,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
     float* a2 = sA2 + s * F_APITCH;
     uint32_t qa = 0, qd = 0, qt = 0, n_tile = 0;
     float loss_local = 0.f;
-    long long tm_eval = 0, tm_wait = 0, tm_st = 0, tm_d = 0, tm_out = 0, tm_all = clock64();
+    long long tm_eval = 0, tm_wait = 0, tm_st = 0, tm_d = 0, tm_out = 0, tm_ob = 0, tm_gxe = 0, tm_gxw = 0, tm_gxr = 0, tm_all = FCLK();
     // one basis chunk (input value xv, n terms) -> TMEM A staging
     auto stage = [&](float xv, int n) {
       const uint32_t buf = qa & 1, ph = (qa >> 1) & 1;
       float v[32], lo[32];
-      const long long c0 = clock64();
+      const long long c0 = FCLK();
       if (p.dbg & 8) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = xv;
@@ -283,25 +310,25 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
       fourier_eval<32, NT, ODD_SIN, false>(p, n, xv, v, nullptr);
 #pragma unroll
       for (int k = 0; k < 32; ++k) lo[k] = tf32_lo(v[k]);
-      const long long c1 = clock64();
+      const long long c1 = FCLK();
       mbar_wait(&bars[FB_AEMPTY0 + buf], ph ^ 1);
       fence_after();
-      const long long c2 = clock64();
+      const long long c2 = FCLK();
       const uint32_t col = tm_lane + F_A_COL + blk * 128 + buf * 64;
       tmem_st32(col, v);
       tmem_st32(col + 32, lo);
       tmem_wait_st();
       fence_before();
       mbar_arrive(&bars[FB_AFULL0 + buf]);
-      const long long c3 = clock64();
+      const long long c3 = FCLK();
       tm_eval += c1 - c0; tm_wait += c2 - c1; tm_st += c3 - c2;
       ++qa;
     };
     // accumulator of the finished layer -> h[0 .. F_MAXH)
     auto read_d = [&](float* h) {
-      const long long c0 = clock64();
+      const long long c0 = FCLK();
       mbar_wait(&bars[FB_DFULL], qd & 1);
-      tm_d += clock64() - c0;
+      tm_d += FCLK() - c0;
       fence_after();
 #pragma unroll
       for (int g = 0; g < F_MAXH; g += 16) {
@@ -362,7 +389,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
       read_d(h);
       if (p.normalize) maxabs_regs<F_MAXH>(h, p.hid, p.norm_eps, inv_d1, kidx1);
       // ---- output layer (CUDA cores): y[o] = sum_i sum_j phi_j(a2_i) W2[i][j][o]
-      const long long co0 = clock64();
+      const long long co0 = FCLK();
       float yo[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < F_MAXH; ++i)
@@ -370,7 +397,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
           a2[i] = h[i];
           if (TRAIN) wsa2[(size_t)i * FT] = live ? h[i] : 0.f;
         }
-#pragma unroll 1
+#pragma unroll 4
       for (int i = 0; i < p.hid; ++i) {
         float val[4];
         fourier_eval<4, 0, ODD_SIN, false>(p, p.n2, a2[i], val, nullptr);
@@ -385,7 +412,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
             yo[3] = fmaf(val[j], w4.w, yo[3]);
           }
       }
-      tm_out += clock64() - co0;
+      tm_out += FCLK() - co0;
       if (!TRAIN) {
         if (live) {
 #pragma unroll
@@ -395,6 +422,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
         continue;
       }
       // ---- loss and dL/dy
+      const long long cb0 = FCLK();
       float gy[4] = {0.f, 0.f, 0.f, 0.f};
       if (live) {
 #pragma unroll
@@ -421,7 +449,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
       for (int o = 0; o < 4; ++o) wsgy[(size_t)o * FT] = gy[o];
       // ---- output layer backward: dL/da2_i = sum_j phi'_j(a2_i) sum_o W2[i][j][o] gy[o];  MaxAbs backward -> g1
       float dot = 0.f;
-#pragma unroll 1
+#pragma unroll 4
       for (int i = 0; i < p.hid; ++i) {
         const float xa = a2[i];
         float val[4], der[4];
@@ -464,26 +492,41 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
         mbar_arrive(&bars[FB_GFULL]);
       }
       // ---- dL/da1 through the tensor cores: T chunk of input c contracted with the basis derivatives
+      tm_ob += FCLK() - cb0;
       dot = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < nch1; ++c, ++qt) {
+      for (int cp = 0; cp < nch1 / 2; ++cp, ++qt) {
         const uint32_t buf = qt & 1, ph = (qt >> 1) & 1;
-        const float xa = a1[c];
-        float val[32], der[32];
-        fourier_eval<32, NT, ODD_SIN, true>(p, p.n1, xa, val, der);
+        const float xa0 = a1[2 * cp], xa1 = a1[2 * cp + 1];
+        float val[32], der0[32], der1[32];
+        const long long cg0 = FCLK();
+        fourier_eval<32, NT, ODD_SIN, true>(p, p.n1, xa0, val, der0);
+        fourier_eval<32, NT, ODD_SIN, true>(p, p.n1, xa1, val, der1);
+        const long long cg1 = FCLK();
         mbar_wait(&bars[FB_TFULL0 + buf], ph);
         fence_after();
+        const long long cg2 = FCLK();
+        tm_gxe += cg1 - cg0; tm_gxw += cg2 - cg1;
         float t[32];
-        tmem_ld16(tm_lane + F_T_COL + (blk * 2 + buf) * 32, t);
-        tmem_ld16(tm_lane + F_T_COL + (blk * 2 + buf) * 32 + 16, t + 16);
+        const uint32_t tcol = tm_lane + F_T_COL + (blk * 2 + buf) * 64;
+        tmem_ld16(tcol, t);
+        tmem_ld16(tcol + 16, t + 16);
+        tmem_wait_ld();
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc0 = fmaf(der0[q], t[q], acc0);
+        tmem_ld16(tcol + 32, t);
+        tmem_ld16(tcol + 48, t + 16);
         tmem_wait_ld();
         fence_before();
         mbar_arrive(&bars[FB_TEMPTY0 + buf]);
-        float acc = 0.f;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) acc = fmaf(der[q], t[q], acc);
-        dot = fmaf(acc, xa, dot);
-        a2[c] = acc;
+        for (int q = 0; q < 32; ++q) acc1 = fmaf(der1[q], t[q], acc1);
+        dot = fmaf(acc0, xa0, dot);
+        dot = fmaf(acc1, xa1, dot);
+        a2[2 * cp] = acc0;
+        a2[2 * cp + 1] = acc1;
+        tm_gxr += FCLK() - cg2;
       }
       {
         const int k0 = kidx0 & 0xffff;
@@ -495,8 +538,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
         }
       }
     }
-    if ((p.dbg & 32) && blockIdx.x == 0 && tid == 0)
-      printf("tiles %u all %lld eval %lld wait %lld st %lld dwait %lld out %lld\n", n_tile, clock64() - tm_all, tm_eval, tm_wait, tm_st, tm_d, tm_out);
+    if (HOIR_FOURIER_TIMERS && (p.dbg & 32) && blockIdx.x == 0 && tid == 0)
+      printf("tiles %u all %lld eval %lld wait %lld st %lld dwait %lld out %lld outbwd %lld gx: eval %lld wait %lld rest %lld\n", n_tile, FCLK() - tm_all, tm_eval, tm_wait, tm_st, tm_d, tm_out, tm_ob, tm_gxe, tm_gxw, tm_gxr);
     if (TRAIN && p.gy_ext == nullptr) {
       const float sum = hoir::warp_sum(loss_local) * p.loss_scale;
       if (lane == 0 && sum != 0.f) hoir::red_add(p.loss_sum, sum);
@@ -509,9 +552,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
     return;
   }
   // =============================== phase 2: dL/dw of the three layers ===================================
+  const long long tp0 = FCLK();
   fence_before();
   hoir::grid_sync_phase(p.sync + 2, 1);
   fence_after();
+  const long long tp1 = FCLK();
   if ((int)blockIdx.x < p.p2_ctas) {
     const long long units_all = tiles * (FT / F_UNIT);
     const long long per = (units_all + p.p2_ctas - 1) / p.p2_ctas;
@@ -540,7 +585,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
           }
           mbar_wait(&bars[FB_GTFULL0 + gbuf], gph);
           for (int st = 0; st < ns; ++st, ++qu) {
-            const uint32_t ubuf = qu & 1, uph = (qu >> 1) & 1;
+            const uint32_t ubuf = qu % F_USTAGES, uph = (qu / F_USTAGES) & 1;
             mbar_wait(&bars[FB_UFULL0 + ubuf], uph);
             fence_after();
             if (leader) {
@@ -572,44 +617,52 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
           if ((u + 1) % F_FLUSH == 0 || u == units - 1) ++qf;
         }
       } else if (warp < 8) {
+        long long t_ld = 0, t_gw = 0, t_gs = 0, t_ev = 0, t_uw = 0, t_us = 0, t_l2 = 0, t_fl = 0, t_o2 = 0;
+        const long long t_pass0 = FCLK();
+        constexpr int GV = (F_MAXH * F_UNIT) / FT, YV = (16 * F_UNIT) / FT, XV1 = (F_MAXH / 4 + 1) / 2, XV2 = (8 * 8 * F_UNIT) / FT;
+        struct UnitRegs { float g[GV], y[YV], x1[XV1], x2[XV2]; };
+        UnitRegs cur, nxt;
+        auto issue_loads = [&](long long gu_, UnitRegs& q) {
+          const long long tile_ = gu_ / (FT / F_UNIT);
+          const int sub_ = (int)(gu_ - tile_ * (FT / F_UNIT)) * F_UNIT;
+          const float* ga = p.ws + (pass == 0 ? p.ws_g1 : p.ws_g0) + (size_t)tile_ * p.hid * FT + sub_;
+#pragma unroll
+          for (int r = 0; r < GV; ++r) {
+            const int it = tid + r * FT, sl = it % F_UNIT, o = it / F_UNIT;
+            q.g[r] = o < p.hid ? __ldcg(ga + (size_t)o * FT + sl) : 0.f;
+          }
+          const int in_f = pass == 0 ? p.hid : p.in0;
+          const float* xa = p.ws + (pass == 0 ? p.ws_a1 : p.ws_a0) + (size_t)tile_ * in_f * FT + sub_;
+#pragma unroll
+          for (int r = 0; r < XV1; ++r) {
+            const int i = (2 * r) * 4 + tid / F_UNIT;            // stage r: first block 2 r, column atom tid / 32
+            q.x1[r] = (r < ns_a && i < in_f) ? __ldcg(xa + (size_t)i * FT + (tid % F_UNIT)) : 0.f;
+          }
+          const float* gya = p.ws + p.ws_gy + (size_t)tile_ * 4 * FT + sub_;
+#pragma unroll
+          for (int r = 0; r < YV; ++r) {
+            const int it = tid + r * FT, sl = it % F_UNIT, o = it / F_UNIT;
+            q.y[r] = (pass == 0 && o < p.out) ? __ldcg(gya + (size_t)o * FT + sl) : 0.f;
+          }
+          const float* x2 = p.ws + p.ws_a2 + (size_t)tile_ * p.hid * FT + sub_;
+#pragma unroll
+          for (int r = 0; r < XV2; ++r) {
+            const int it = tid + r * FT, sl = it % F_UNIT, i = it / F_UNIT;     // (first block pair of the output layer)
+            q.x2[r] = (pass == 0 && i < p.hid) ? __ldcg(x2 + (size_t)i * FT + sl) : 0.f;
+          }
+        };
+        if (units > 0) issue_loads(u_lo, cur);
         for (int u = 0; u < units; ++u, ++qg) {
+          const long long k0 = FCLK();
           const uint32_t gbuf = qg & 1, gph = (qg >> 1) & 1;
           const long long gu = u_lo + u, tile = gu / (FT / F_UNIT);
           const int sub = (int)(gu - tile * (FT / F_UNIT)) * F_UNIT;
-          // ---- every global load of the unit is issued up front (one exposed L2 latency per unit instead of ~20)
-          constexpr int GV = (F_MAXH * F_UNIT) / FT, YV = (16 * F_UNIT) / FT, XV1 = (F_MAXH / 4 + 1) / 2, XV2 = (8 * 8 * F_UNIT) / FT;
-          float gpre[GV], ypre[YV], xpre1[XV1], xpre2[XV2];
-          {
-            const float* ga = p.ws + (pass == 0 ? p.ws_g1 : p.ws_g0) + (size_t)tile * p.hid * FT + sub;
-#pragma unroll
-            for (int r = 0; r < GV; ++r) {
-              const int it = tid + r * FT, sl = it % F_UNIT, o = it / F_UNIT;
-              gpre[r] = o < p.hid ? __ldcg(ga + (size_t)o * FT + sl) : 0.f;
-            }
-            const int in_f = pass == 0 ? p.hid : p.in0;
-            const float* xa = p.ws + (pass == 0 ? p.ws_a1 : p.ws_a0) + (size_t)tile * in_f * FT + sub;
-#pragma unroll
-            for (int r = 0; r < XV1; ++r) {
-              const int i = (2 * r) * 4 + tid / F_UNIT;            // stage r: first block 2 r, column atom tid / 32
-              xpre1[r] = (r < ns_a && i < in_f) ? __ldcg(xa + (size_t)i * FT + (tid % F_UNIT)) : 0.f;
-            }
-            if (pass == 0) {
-              const float* gya = p.ws + p.ws_gy + (size_t)tile * 4 * FT + sub;
-#pragma unroll
-              for (int r = 0; r < YV; ++r) {
-                const int it = tid + r * FT, sl = it % F_UNIT, o = it / F_UNIT;
-                ypre[r] = o < p.out ? __ldcg(gya + (size_t)o * FT + sl) : 0.f;
-              }
-              const float* x2 = p.ws + p.ws_a2 + (size_t)tile * p.hid * FT + sub;
-#pragma unroll
-              for (int r = 0; r < XV2; ++r) {
-                const int it = tid + r * FT, sl = it % F_UNIT, i = it / F_UNIT;     // (first block pair of the output layer)
-                xpre2[r] = i < p.hid ? __ldcg(x2 + (size_t)i * FT + sl) : 0.f;
-              }
-            }
-          }
+          // ---- the global loads of unit u + 1 are issued now, those of unit u arrived during unit u - 1
+          issue_loads(u + 1 < units ? gu + 1 : gu, nxt);
           // ---- G^T of the unit: element (output o, sample sl), sl fastest
+          const long long k1 = FCLK();
           mbar_wait(&bars[FB_GTEMPTY0 + gbuf], gph ^ 1);
+          const long long k2 = FCLK();
           {
             uint8_t* gb = sG + gbuf * F_G_BYTES;
 #pragma unroll
@@ -617,8 +670,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
               const int it = tid + r * FT, sl = it % F_UNIT, o = it / F_UNIT;
               if (o < p.outp) {
                 const uint32_t off = chunk_off((uint32_t)o, (uint32_t)sl);
-                *reinterpret_cast<float*>(gb + off) = gpre[r];
-                *reinterpret_cast<float*>(gb + gh_bytes + off) = tf32_lo(gpre[r]);
+                *reinterpret_cast<float*>(gb + off) = cur.g[r];
+                *reinterpret_cast<float*>(gb + gh_bytes + off) = tf32_lo(cur.g[r]);
               }
             }
             if (pass == 0) {
@@ -626,16 +679,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
               for (int r = 0; r < YV; ++r) {
                 const int it = tid + r * FT, sl = it % F_UNIT, o = it / F_UNIT;
                 const uint32_t off = 2 * gh_bytes + chunk_off((uint32_t)o, (uint32_t)sl);
-                *reinterpret_cast<float*>(gb + off) = ypre[r];
-                *reinterpret_cast<float*>(gb + 16 * 128 + off) = tf32_lo(ypre[r]);
+                *reinterpret_cast<float*>(gb + off) = cur.y[r];
+                *reinterpret_cast<float*>(gb + 16 * 128 + off) = tf32_lo(cur.y[r]);
               }
             }
           }
           fence_async_smem();
           mbar_arrive(&bars[FB_GTFULL0 + gbuf]);
+          const long long k3 = FCLK();
+          t_ld += k1 - k0; t_gw += k2 - k1; t_gs += k3 - k2;
           // ---- Phi^T stages
           for (int st = 0; st < ns; ++st, ++qu) {
-            const uint32_t ubuf = qu & 1, uph = (qu >> 1) & 1;
+            const uint32_t ubuf = qu % F_USTAGES, uph = (qu / F_USTAGES) & 1;
             const int layer = stage_layer(st), mb0 = stage_mb(st);
             uint8_t* ur = sU + ubuf * 2 * F_U_BYTES;
             uint8_t* ul = ur + F_U_BYTES;
@@ -647,9 +702,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                 const int sl = tid % F_UNIT, ca = tid / F_UNIT;
                 const int i = mb0 * 4 + ca;
                 const bool on = i < in_f;
+                const long long e0 = FCLK();
                 float xv = 0.f;
 #pragma unroll
-                for (int r = 0; r < XV1; ++r) xv = r == st ? xpre1[r] : xv;
+                for (int r = 0; r < XV1; ++r) xv = r == st ? cur.x1[r] : xv;
                 float val[32];
                 if (on && !(p.dbg & 1)) {
                   fourier_eval<32, NT, ODD_SIN, false>(p, nterm, xv, val, nullptr);
@@ -670,7 +726,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                   }
                 const uint32_t rowoff = (uint32_t)(sl >> 2) * F_U_RS + (uint32_t)(sl & 3) * 128u + (uint32_t)ca * 512u;
                 const uint32_t sw = ((uint32_t)(sl & 3) << 5) ^ (swp ? 16u : 0u);
+                const long long e1 = FCLK();
                 mbar_wait(&bars[FB_UEMPTY0 + ubuf], uph ^ 1);
+                const long long e2 = FCLK();
+                t_ev += e1 - e0; t_uw += e2 - e1;
+                const long long e3 = FCLK();
                 if (!(p.dbg & 4)) {
 #pragma unroll
                 for (int q4 = 0; q4 < 8; ++q4) {
@@ -680,11 +740,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                                                                      tf32_lo(val[4 * q4 + 2]), tf32_lo(val[4 * q4 + 3]));
                 }
                 }
+                t_l2 += FCLK() - e3;
               }
             } else {
               // 4 slots per input, 8 inputs per column atom: items (atom ca, input m of the atom, sample sl)
               const float* xa = p.ws + p.ws_a2 + (size_t)tile * p.hid * FT + sub;
+              const long long l0 = FCLK();
               mbar_wait(&bars[FB_UEMPTY0 + ubuf], uph ^ 1);
+              const long long l1 = FCLK();
+              t_uw += l1 - l0;
 #pragma unroll
               for (int r = 0; r < XV2; ++r) {
                 const int it = tid + r * FT;
@@ -692,7 +756,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                 const int c = mb0 * 4 + ca, i = c * 8 + m;
                 float val[4];
                 if (c < nch2 && i < p.hid) {
-                  const float xv = mb0 == 0 ? xpre2[r] : __ldcg(xa + (size_t)i * FT + sl);
+                  const float xv = mb0 == 0 ? cur.x2[r] : __ldcg(xa + (size_t)i * FT + sl);
                   fourier_eval<4, 0, ODD_SIN, false>(p, p.n2, xv, val, nullptr);
                 } else {
                   val[0] = val[1] = val[2] = val[3] = 0.f;
@@ -702,10 +766,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                 *reinterpret_cast<float4*>(ur + off) = make_float4(val[0], val[1], val[2], val[3]);
                 *reinterpret_cast<float4*>(ul + off) = make_float4(tf32_lo(val[0]), tf32_lo(val[1]), tf32_lo(val[2]), tf32_lo(val[3]));
               }
+              t_o2 += FCLK() - l1;
             }
+            const long long s0 = FCLK();
             fence_async_smem();
             mbar_arrive(&bars[FB_UFULL0 + ubuf]);
+            t_us += FCLK() - s0;
           }
+          const long long f0 = FCLK();
           // ---- accumulators -> the CTA's private gradient slab (every F_FLUSH units and at the end of the pass)
           if ((u + 1) % F_FLUSH == 0 || u == units - 1) {
             mbar_wait(&bars[FB_GWDONE], qf & 1);
@@ -728,10 +796,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                   float d[16];
                   tmem_ld16(tm_lane + acc_col(layer, mb0 + h) + g, d);
                   tmem_wait_ld();
-                  if (valid) {
-#pragma unroll
+                  if (valid) {              // fire-and-forget adds into the PRIVATE slab: no load round trips; one add
+#pragma unroll                      // per address and flush, so the order of the sum is the order of the flushes
                     for (int o = 0; o < 16; ++o)
-                      if (g + o < out_f) gl[((size_t)(g + o) * in_f + i) * nterm + q] += d[o];
+                      if (g + o < out_f && d[o] != 0.f) hoir::red_add(gl + ((size_t)(g + o) * in_f + i) * nterm + q, d[o]);
                   }
                 }
               }
@@ -739,7 +807,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
             fence_before();
             mbar_arrive(&bars[FB_ACCFREE]);
           }
+          t_fl += FCLK() - f0;
+          cur = nxt;
         }
+        if (HOIR_FOURIER_TIMERS && (p.dbg & 32) && blockIdx.x == 0 && tid == 0)
+          printf("pass %d units %d total %lld: loads %lld gwait %lld gstage %lld eval %lld uwait %lld stores %lld outlayer-stage %lld fence+arrive %lld flush %lld\n", pass, units, FCLK() - t_pass0, t_ld, t_gw, t_gs, t_ev, t_uw, t_l2, t_o2, t_us, t_fl);
       }
       // between the passes: every accumulator of pass 0 has been read (the workers' last flush), and the MMA warp
       // must not start pass 1 before that
@@ -753,28 +825,44 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
   __syncthreads();
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   // =============================== phase 2b: slabs -> gradient vector, fixed order ========================
+  const long long tp2 = FCLK();
   hoir::grid_sync_phase(p.sync + 2, 2);
+  const long long tp3 = FCLK();
   {
-    const long long gthreads = (long long)gridDim.x * F_THREADS;
-    for (long long k = blockIdx.x * (long long)F_THREADS + tid; k < p.n_params; k += gthreads) {
-      float sum = 0.f;
-      for (int c0 = 0; c0 < p.p2_ctas; c0 += 8) {               // 8 independent loads in flight, fixed summation order
-        float v[8];
+    // a thread sums 4 consecutive parameters over the slabs (16-byte loads, 8 in flight, fixed order)
+    const long long gthreads = (long long)gridDim.x * F_THREADS, n4 = p.n_params >> 2;      // n_params % 4 == 0 (host)
+    for (long long k4 = blockIdx.x * (long long)F_THREADS + tid; k4 < n4; k4 += gthreads) {
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c0 = 0; c0 < p.p2_ctas; c0 += 8) {
+        float4 v[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = c0 + c < p.p2_ctas ? __ldcg(p.slabs + (size_t)(c0 + c) * p.n_params + k) : 0.f;
+        for (int c = 0; c < 8; ++c)
+          v[c] = c0 + c < p.p2_ctas ? __ldcg(reinterpret_cast<const float4*>(p.slabs + (size_t)(c0 + c) * p.n_params) + k4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          sum += v[c];
-          if (c0 + c < p.p2_ctas) p.slabs[(size_t)(c0 + c) * p.n_params + k] = 0.f;
+          sum.x += v[c].x; sum.y += v[c].y; sum.z += v[c].z; sum.w += v[c].w;
+          if (c0 + c < p.p2_ctas)
+            reinterpret_cast<float4*>(p.slabs + (size_t)(c0 + c) * p.n_params)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      const int l = k >= p.woff[2] ? 2 : (k >= p.woff[1] ? 1 : 0);
-      float* gp = p.gw[l] + (k - p.woff[l]);
-      *gp = __ldcg(gp) + sum;
+      const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long long k = 4 * k4 + e;
+        if (k < p.woff[3]) {
+          const int l = k >= p.woff[2] ? 2 : (k >= p.woff[1] ? 1 : 0);
+          float* gp = p.gw[l] + (k - p.woff[l]);
+          *gp = __ldcg(gp) + sv[e];
+        }
+      }
     }
   }
   hoir::grid_sync_rearm(p.sync + 2, p.sync + 3);
+  const long long tp4 = FCLK();
   hoir::opt_tail_in_kernel(p.tail);
+  if (HOIR_FOURIER_TIMERS && (p.dbg & 32) && blockIdx.x == 0 && tid == 0)
+    printf("barrier1 %lld phase2 %lld barrier2 %lld reduce %lld tail %lld\n", tp1 - tp0, tp2 - tp1, tp3 - tp2, tp4 - tp3, FCLK() - tp4);
 }
 
 // ---- weight images / packed output layer ------------------------------------------------------------------
@@ -819,6 +907,7 @@ bool geometry(const hoir_mlp_desc* m, Geo* g) {
   const hoir_layer_desc &l0 = m->layers[0], &l1 = m->layers[1], &l2 = m->layers[2];
   if (l0.in_features < 1 || l0.in_features > 2 * HOIR_MAX_ROTATIONS) return false;
   if (l0.out_features != l1.out_features || l0.out_features < 8 || l0.out_features > 40) return false;   // a row per thread: 40 registers
+  if ((l0.in_features | l0.out_features) & 1) return false;       // dL/dx takes the hidden inputs two at a time (W ring stage pairs)
   if (l0.n < 1 || l0.n > 32 || l1.n < 1 || l1.n > 32 || l2.n < 1 || l2.n > 4) return false;
   if (l2.out_features < 1 || l2.out_features > 4) return false;
   g->in0 = l0.in_features; g->hid = l0.out_features; g->out = l2.out_features;
@@ -828,7 +917,7 @@ bool geometry(const hoir_mlp_desc* m, Geo* g) {
   g->off[1] = g->off[0] + (long long)g->in0 * 2 * g->outp * 32;
   g->off[2] = g->off[1] + (long long)g->hid * 2 * g->outp * 32;
   g->off[3] = g->off[2] + (((long long)g->hid * g->n2 * g->op2 + 3) & ~3LL);
-  if ((size_t)g->hid * g->n2 * g->op2 * 4 > 4096) return false;
+  if ((size_t)g->hid * g->n2 * g->op2 * 4 > 2048) return false;      // the output-layer table in shared memory
   return true;
 }
 
@@ -986,7 +1075,7 @@ int hoir_fourier_train(const hoir_mlp_desc* m, long long B, const float* x, cons
     p.woff[1] = p.woff[0] + (long long)g.hid * g.in0 * g.n0;
     p.woff[2] = p.woff[1] + (long long)g.hid * g.hid * g.n1;
     p.woff[3] = p.woff[2] + (long long)g.out * g.hid * g.n2;
-    p.n_params = p.woff[3];
+    p.n_params = (p.woff[3] + 3) & ~3LL;       // slab stride (16-byte rows); the pad entries stay zero
     void* sl = nullptr;
     if (int err = hoir_get_workspace(4, (size_t)grid * p.n_params * sizeof(float), &sl)) return err;   // zeroed when allocated
     p.slabs = static_cast<float*>(sl);
