@@ -50,8 +50,9 @@ def test_fused_matches_per_layer_kernels(name):
     net.use_fused = False
     y_layers = net(x.cuda())      # B >= 512: the hidden / output layers run on the tcgen05 per-layer kernels
     # two independent evaluation orders (FFMA chains vs tf32 x 3 tensor-core passes); a sample whose hidden
-    # activation lands within round-off of a segment boundary may take the other branch
-    assert rel_err(y_fused, y_layers) <= 1e-5
+    # activation lands within round-off of a segment boundary may take the other branch;
+    # Fourier: the fused kernel reduces the basis argument with sincospif, the per-layer kernels with sincosf
+    assert rel_err(y_fused, y_layers) <= (1e-4 if name == "C3f" else 1e-5)
 
 
 @pytest.mark.parametrize("name", ["C1", "C2", "C3d", "poly"])
