@@ -136,6 +136,7 @@ _EXPORTS = {
     "hoir_sparse_lion_step_dev": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
     "hoir_write_floats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "hoir_tf32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]),
     "hoir_ffma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double),
                                  C.c_void_p]),
 }

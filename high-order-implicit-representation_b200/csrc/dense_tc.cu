@@ -533,7 +533,72 @@ const DenseEntry kDense[] = {
 
 int dense_sms() { return hoir_num_sms(); }
 
+// ---- measured tensor-pipe roofline denominator: tcgen05.mma kind::tf32, M = 128, N = 256, K = 8 per instruction, both
+// operands resident in shared memory (SWIZZLE_128B_BASE32B, K-major), accumulator in TMEM; one CTA per SM issues
+// `iters` rounds of 4 back-to-back MMAs (one 32-column K atom) and commits once.
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+  extern __shared__ __align__(1024) uint8_t psm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  for (int k = tid; k < (128 + 256) * 128 / 4; k += 128) reinterpret_cast<float*>(psm)[k] = 1.0f + (float)(k & 7) * 0.125f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint64_t dA = make_desc(smem_u32(psm), 512), dB = make_desc(smem_u32(psm + 128 * 128), 512);
+      constexpr uint32_t ID = make_idesc(128, 256, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_ss(tmem, dA + (uint64_t)((j * 32) >> 4), dB + (uint64_t)((j * 32) >> 4), ID, (it | j) != 0);
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait_backoff(&bar, 0, 256);
+  fence_after();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
 }  // namespace
+
+// elapsed milliseconds and FLOPs of `iters` rounds of 4 tcgen05 tf32 MMAs (128 x 256 x 8) on every SM: the measured
+// tensor roofline denominator for the tf32 x 3 kernels (bench.py)
+extern "C" int hoir_tf32_peak(int iters, float* ms, double* flops, void* stream) {
+  if (iters < 1 || !ms || !flops) return hoir_set_error(HOIR_EINVAL, "bad arguments", "hoir_tf32_peak");
+  const int sms = dense_sms();
+  const size_t smem = (128 + 256) * 128 + 1024;
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  HOIR_CHECK_CUDA(cudaEventCreate(&e0));
+  HOIR_CHECK_CUDA(cudaEventCreate(&e1));
+  cudaStream_t s = (cudaStream_t)stream;
+  tf32_peak_kernel<<<sms, 128, smem, s>>>(iters / 8 + 1);      // warm-up
+  HOIR_CHECK_CUDA(cudaEventRecord(e0, s));
+  tf32_peak_kernel<<<sms, 128, smem, s>>>(iters);
+  HOIR_CHECK_CUDA(cudaEventRecord(e1, s));
+  HOIR_CHECK_CUDA(cudaEventSynchronize(e1));
+  HOIR_CHECK_CUDA(cudaEventElapsedTime(ms, e0, e1));
+  *flops = 2.0 * 128.0 * 256.0 * 8.0 * 4.0 * (double)iters * (double)sms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  HOIR_CHECK_CUDA(cudaGetLastError());
+  return HOIR_OK;
+}
 
 // nullptr: this layer is not a dense contraction (or too small to be worth the tensor path)
 const void* hoir_dense_tc_find(const hoir_layer_desc* d, long long B) {

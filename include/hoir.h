@@ -297,6 +297,9 @@ int hoir_write_floats(float* dst, int n, const float* values, void* stream);
  * roofline denominator of bench.py).  reg_form 1: FFMA with three register sources (what a
  * kernel whose weights come from shared memory issues); 0: constant-bank multiplier/addend. */
 int hoir_ffma_peak(int iters, int reg_form, float* ms, double* flops, void* stream);
+/* tcgen05.mma kind::tf32 micro-kernel (M = 128, N = 256, K = 8 per instruction, operands resident in shared memory,
+ * accumulator in TMEM, one CTA per SM): the measured tensor-pipe denominator for the tf32 x 3 kernels. */
+int hoir_tf32_peak(int iters, float* ms, double* flops, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,11 @@ def test_fused_supported_matrix():
     assert sup(layer_type="discontinuous")
     assert sup(in_width=2, hidden_width=10, hidden_layers=2)
     assert sup(in_segments=37)                      # layer-0 segments are a runtime value
-    assert not sup(layer_type="fourier")
+    assert sup(layer_type="fourier")                # the fused Fourier family (csrc/fused_fourier.cu)
+    assert sup(layer_type="fourier", n_in=31, n_hidden=31)
+    assert not sup(layer_type="fourier", hidden_width=41)
+    assert not sup(layer_type="fourier", hidden_layers=2)
+    assert not sup(layer_type="fourier", n_out=7)
     assert not sup(hidden_width=41)
     assert not sup(hidden_segments=3)
     assert not sup(periodicity=2.0)
@@ -87,10 +91,10 @@ def test_errors_map_to_python_exceptions():
     _lib.check(lib.hoir_maxabs_forward(0, 4, 1e-6, None, None, None))
     with pytest.raises(ValueError, match="not recognized"):
         H.high_order_fc_layers("no_such_layer", n=3, in_features=2, out_features=2)
-    fourier = H.HighOrderMLP(layer_type="fourier", n=3, in_width=4, out_width=3, hidden_layers=1,
+    unfused = H.HighOrderMLP(layer_type="fourier", n=3, in_width=4, out_width=3, hidden_layers=2,
                              hidden_width=40, normalization=H.MaxAbsNormalization)
     with pytest.raises(H.HoirUnsupported):
-        _lib.check(lib.hoir_mlp_forward(fourier.mlp_desc(), 0, None, None, None, None, 0, None))
+        _lib.check(lib.hoir_mlp_forward(unfused.mlp_desc(), 0, None, None, None, None, 0, None))
 
 
 def test_no_cpu_fallback():
