@@ -38,14 +38,28 @@ for l in lines.splitlines():
         continue
     if re.match(r"^\s+/\*[0-9a-f]{4,}\*/", l):
         per_inst.append(cur)
-agg = collections.defaultdict(lambda: [0, 0, 0])
-tot = [0, 0, 0]
+agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
+tot = [0, 0, 0, 0, 0]
+
+
+def num(r, key):
+    try:
+        return int(float(r[ci[key]] or 0)) if key in ci else 0
+    except ValueError:
+        return 0
+
+
 for r, loc in zip(inst, per_inst):
-    ex = int(r[ci["Instructions Executed"]] or 0)
-    smp = int(r[ci["Warp Stall Sampling (All Samples)"]] or 0)
-    agg[loc][0] += ex; agg[loc][1] += smp; agg[loc][2] += 1
-    tot[0] += ex; tot[1] += smp
-print(f"total warp-instructions {tot[0]}, stall samples {tot[1]}, SASS instructions {len(inst)}")
-print(f"{'file:line':32s} {'inst%':>7s} {'samples%':>9s} {'sass':>6s}")
-for loc, v in sorted(agg.items(), key=lambda kv: -(kv[1][0] if os.environ.get("BY_INST") else kv[1][1]))[:top]:
-    print(f"{loc[0]+':'+str(loc[1]):32s} {100*v[0]/max(tot[0],1):7.2f} {100*v[1]/max(tot[1],1):9.2f} {v[2]:6d}")
+    ex = num(r, "Instructions Executed")
+    smp = num(r, "Warp Stall Sampling (All Samples)")
+    wv = num(r, "L1 Wavefronts Shared")
+    wx = num(r, "L1 Wavefronts Shared Excessive")
+    agg[loc][0] += ex; agg[loc][1] += smp; agg[loc][2] += 1; agg[loc][3] += wv; agg[loc][4] += wx
+    tot[0] += ex; tot[1] += smp; tot[3] += wv; tot[4] += wx
+print(f"total warp-instructions {tot[0]}, stall samples {tot[1]}, SASS instructions {len(inst)}, "
+      f"shared wavefronts {tot[3]} (excessive = bank conflicts: {tot[4]})")
+# BY_INST=1: sort by executed instructions; BY_CONFLICT=1: by excessive shared-memory wavefronts; default: stall samples
+key = 0 if os.environ.get("BY_INST") else (4 if os.environ.get("BY_CONFLICT") else 1)
+print(f"{'file:line':32s} {'inst%':>7s} {'samples%':>9s} {'sass':>6s} {'smem wavefronts':>16s} {'excessive':>10s}")
+for loc, v in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
+    print(f"{loc[0]+':'+str(loc[1]):32s} {100*v[0]/max(tot[0],1):7.2f} {100*v[1]/max(tot[1],1):9.2f} {v[2]:6d} {v[3]:16d} {v[4]:10d}")
