@@ -521,9 +521,12 @@ def run_e2e(H, dist, trainer, img, dev, rank, world, args, barrier):
     barrier()
     t0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(e_steps + 1)]
     e0.record()
+    marks[0].record()
     for s in range(e_steps):
         stepper.step(hx[s % 4], hy[s % 4])      # H2D of this batch overlaps the previous step's compute
+        marks[s + 1].record()                   # (compute stream: the end of this step's kernel)
     e2e_loss = stepper.flush()                  # every step's loss has been read back by now
     e1.record()
     barrier()
@@ -534,6 +537,7 @@ def run_e2e(H, dist, trainer, img, dev, rank, world, args, barrier):
         dist.all_reduce(wall_ms, op=dist.ReduceOp.MAX)
     e2e = {"value": BATCH * world * e_steps / (wall_ms.item() * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes,
+           "ms_per_step_median": statistics.median(a.elapsed_time(b) for a, b in zip(marks[:-1], marks[1:])),
            "steps": e_steps, "api": "HostBatchStepper.step(x_host[B,4], y_host[B,3]) -> loss of the previous step (2-deep H2D/compute pipeline)",
            "batches": "shuffled pixels of the synthetic image (image_to_dataset rows, rotations=2), pinned host memory",
            "last_loss": e2e_loss}

@@ -14,7 +14,9 @@ from typing import List, Optional, Sequence
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libhoir_b200.so")
+# HOIR_LIB: load another build of the same sources instead (libhoir_b200_dbg.so = -DHOIR_DEBUG_BOUNDS, see csrc/Makefile)
+LIB_PATH = os.environ.get("HOIR_LIB") or os.path.join(_PKG_DIR, "libhoir_b200.so")
+DEBUG_LIB_PATH = os.path.join(_PKG_DIR, "libhoir_b200_dbg.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 HOIR_MAX_LAYERS = 8
@@ -150,7 +152,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force:
         subprocess.run(["make", "-C", CSRC_DIR, "clean"], check=True, capture_output=not verbose)
     subprocess.run(["make", "-C", CSRC_DIR, "-j8"], check=True, capture_output=not verbose)
-    return LIB_PATH
+    return os.path.join(_PKG_DIR, "libhoir_b200.so")
+
+
+def build_debug(verbose: bool = False) -> str:
+    """The same sources with -DHOIR_DEBUG_BOUNDS (asserts on the swizzled smem / TMEM addressing) -> libhoir_b200_dbg.so."""
+    subprocess.run(["make", "-C", CSRC_DIR, "-j8", "debug"], check=True, capture_output=not verbose)
+    return DEBUG_LIB_PATH
 
 
 def lib() -> C.CDLL:

@@ -670,6 +670,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
               const int it = tid + r * FT, sl = it % F_UNIT, o = it / F_UNIT;
               if (o < p.outp) {
                 const uint32_t off = chunk_off((uint32_t)o, (uint32_t)sl);
+                HOIR_DBG_ASSERT(off + 4u <= gh_bytes && 2 * gh_bytes + 2 * 16 * 128 <= F_G_BYTES);
                 *reinterpret_cast<float*>(gb + off) = cur.g[r];
                 *reinterpret_cast<float*>(gb + gh_bytes + off) = tf32_lo(cur.g[r]);
               }
@@ -735,6 +736,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
 #pragma unroll
                 for (int q4 = 0; q4 < 8; ++q4) {
                   const uint32_t off = rowoff + (((uint32_t)q4 << 4) ^ sw);
+                  HOIR_DBG_ASSERT(off + 16u <= F_U_BYTES);
                   *reinterpret_cast<float4*>(ur + off) = make_float4(val[4 * q4], val[4 * q4 + 1], val[4 * q4 + 2], val[4 * q4 + 3]);
                   *reinterpret_cast<float4*>(ul + off) = make_float4(tf32_lo(val[4 * q4]), tf32_lo(val[4 * q4 + 1]),
                                                                      tf32_lo(val[4 * q4 + 2]), tf32_lo(val[4 * q4 + 3]));
@@ -763,6 +765,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                 }
                 const uint32_t off = (uint32_t)(sl >> 2) * F_U_RS + (uint32_t)(sl & 3) * 128u + (uint32_t)ca * 512u +
                                      (((uint32_t)m << 4) ^ ((uint32_t)(sl & 3) << 5));
+                HOIR_DBG_ASSERT(off + 16u <= F_U_BYTES);
                 *reinterpret_cast<float4*>(ur + off) = make_float4(val[0], val[1], val[2], val[3]);
                 *reinterpret_cast<float4*>(ul + off) = make_float4(tf32_lo(val[0]), tf32_lo(val[1]), tf32_lo(val[2]), tf32_lo(val[3]));
               }

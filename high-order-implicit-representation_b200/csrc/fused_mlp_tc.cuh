@@ -314,6 +314,7 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
       const int o = k % HID, r = k / HID, i = r / ND, q = r - i * ND;
       const float v = __ldg(w1 + (size_t)r * HP + o);
       const uint32_t off = sw4_off(o, P::kbase(i) + q, P::W1_RS);
+      HOIR_DBG_ASSERT(off + 4u <= P::W1_BYTES);
       *reinterpret_cast<float*>(sW1R + off) = v;
       *reinterpret_cast<float*>(sW1L + off) = tf32_lo(v);
     }
@@ -504,6 +505,7 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
 #pragma unroll
             for (int k = 0; k < ND; ++k) {
               const uint32_t off = rowoff + ((coff[k] & 0xffffu) ^ ((uint32_t)(t & 3) << 5)) + (coff[k] >> 16) * 512u;
+              HOIR_DBG_ASSERT(off + 4u <= P::U_BYTES);
               *reinterpret_cast<float*>(ur + off) = c5[k];
               *reinterpret_cast<float*>(ul + off) = tf32_lo(c5[k]);
             }
@@ -766,6 +768,7 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
 #pragma unroll
         for (int j = 0; j < HH; ++j) {
           const uint32_t off = sw4_off(hf * HH + j, s, P::GT_RS);
+          HOIR_DBG_ASSERT(off + 4u <= P::GT_BYTES);
           *reinterpret_cast<float*>(sGTR + off) = g[j];
           *reinterpret_cast<float*>(sGTL + off) = lo[j];
         }

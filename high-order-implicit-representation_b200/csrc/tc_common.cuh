@@ -3,7 +3,23 @@
 // XOR-ed with row % 4): the one layout tcgen05 accepts for tf32 in BOTH majors (csrc/probe/umma_probe.cu).
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
 #include <cuda_runtime.h>
+
+// -DHOIR_DEBUG_BOUNDS (make debug -> libhoir_b200_dbg.so): asserts on the swizzled shared-memory offsets and the TMEM
+// column arithmetic of the tensor-core kernels.  compute-sanitizer is not available on the GPU pool, so a debug build
+// of the same sources, run by tests/test_gpu_debug_bounds.py, is what guards that addressing.
+#ifdef HOIR_DEBUG_BOUNDS
+#define HOIR_DBG_ASSERT(cond)                                                                  \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      printf("HOIR_DEBUG_BOUNDS violated at %s:%d: %s\n", __FILE__, __LINE__, #cond);          \
+      __trap();                                                                                \
+    }                                                                                          \
+  } while (0)
+#else
+#define HOIR_DBG_ASSERT(cond) ((void)0)
+#endif
 
 namespace tc {
 
@@ -70,6 +86,7 @@ __device__ __forceinline__ void bar_pair(int warp) {
 
 // shared-memory operand in the 128B_BASE32B layout: element (row r, column c), RS = bytes per 4 rows
 __device__ __forceinline__ uint32_t sw4_off(uint32_t r, uint32_t c, uint32_t RS) {
+  HOIR_DBG_ASSERT((c >> 5) * 512u + 512u <= RS);      // the column atom lies inside one 4-row group
   return (r & 3u) * 128u + ((((c & 31u) << 2)) ^ ((r & 3u) << 5)) + (c >> 5) * 512u + (r >> 2) * RS;
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo) {
@@ -96,17 +113,20 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
                ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const float* v) {
+  HOIR_DBG_ASSERT((addr & 0xffffu) + 8u <= 512u && (addr >> 16) < 128u);   // columns / lane base inside TMEM
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
                  "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
                  "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
 }
 __device__ __forceinline__ void tmem_st4(uint32_t addr, const float* v) {
+  HOIR_DBG_ASSERT((addr & 0xffffu) + 4u <= 512u && (addr >> 16) < 128u);   // columns / lane base inside TMEM
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                ::"r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
                  "r"(__float_as_uint(v[3])) : "memory");
 }
 __device__ __forceinline__ void tmem_ld4(uint32_t addr, float* v) {
+  HOIR_DBG_ASSERT((addr & 0xffffu) + 4u <= 512u && (addr >> 16) < 128u);   // columns / lane base inside TMEM
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -114,6 +134,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t addr, float* v) {
   for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j]);
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
+  HOIR_DBG_ASSERT((addr & 0xffffu) + 8u <= 512u && (addr >> 16) < 128u);   // columns / lane base inside TMEM
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -143,6 +164,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t addr, const float* v) {
+  HOIR_DBG_ASSERT((addr & 0xffffu) + 32u <= 512u && (addr >> 16) < 128u);   // columns / lane base inside TMEM
   asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
                "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
                ::"r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
@@ -155,6 +177,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t addr, const float* v) {
                  "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31])) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
+  HOIR_DBG_ASSERT((addr & 0xffffu) + 16u <= 512u && (addr >> 16) < 128u);   // columns / lane base inside TMEM
   uint32_t r[16];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),

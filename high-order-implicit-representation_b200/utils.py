@@ -14,10 +14,14 @@ def positions_from_mesh(width: int, height: int, device: str = "cpu", rotations:
                         normalize: bool = False) -> List[Tensor]:
     """List of ``2*rotations`` tensors ``[width, height]`` ("width" is the ROW count, Quirk Q10).
 
-    Host callers (``device="cpu"``, the reference's dataset code) get the tensors computed with
-    stock torch ops on the host -- this is dataset preparation, not the hot path.  With a CUDA
-    device the coordinates are produced by ``hoir_mesh_positions`` (bit-identical)."""
+    The coordinates are produced by ``hoir_mesh_positions`` (sm_100a kernel); a ``device="cpu"`` caller (the
+    reference's dataset code, single_image_dataset.py:39-45) gets the kernel's result copied to the host whenever a CUDA
+    device is present -- the same bits as the in-kernel mesh of the training step.  Only on a machine WITHOUT a GPU
+    (dataset preparation on a login node, the CPU test suite) are they computed with stock torch ops."""
     dev = torch.device(device)
+    if dev.type == "cpu" and torch.cuda.is_available():
+        return [t.cpu() for t in positions_from_mesh(width, height, device="cuda", rotations=rotations,
+                                                     normalize=normalize)]
     if dev.type == "cuda":
         lib = _lib.lib()
         mesh = _lib.make_mesh_desc(width, height, rotations, normalize)
