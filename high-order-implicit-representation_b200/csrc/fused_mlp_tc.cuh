@@ -444,7 +444,21 @@ __global__ void __launch_bounds__((TcPlan<S, NQ>::NT), 1) fused_mlp_tc_kernel(co
     // units of 16 samples, double-buffered.  Thread = (input i, half of the unit): its K-columns are fixed, the
     // row swizzle is a compile-time constant per step.  The sample warps never touch the units.
     const int ht = tid - (NSAMPLE_THREADS + 32);
-    const int i = ht % HID, sh = ht / HID;            // sh = 0, 1: samples 8 sh .. 8 sh + 7 of a unit; sh = 2: idle
+    // thread = (input i, sh): sh = 0, 1: samples 8 sh .. 8 sh + 7 of a unit; sh = 2: idle.
+    // continuous shape (pairs): a warp takes the 32 inputs of chunks 0-3 -- their K-columns kbase(i) + k fall into 32
+    // DIFFERENT banks, so a unit store is one wavefront (with inputs 0 .. 31 per warp, chunk 0 and chunk 4 collided:
+    // 10.5 M excess wavefronts per launch, 12 % of all shared-memory wavefronts); the third warp takes chunk 4.
+    int i = ht % HID, sh = ht / HID;
+    if constexpr (S::CONT && NQ == 2 && HID == 40) {
+      const int hw = ht >> 5, hl = ht & 31;
+      if (hw < 2) {
+        sh = hw;
+        i = hl < 16 ? hl : hl + 4;                    // inputs 0 .. 15 and 20 .. 35: chunks 0 - 3 of both halves
+      } else {
+        sh = hl < 16 ? (hl >> 3) : 2;
+        i = (hl & 7) < 4 ? 16 + (hl & 7) : 32 + (hl & 7);   // inputs 16 .. 19 and 36 .. 39: chunk 4
+      }
+    }
     const LagrangeTable& lag = p.lag;
     const int kb = P::kbase(i);
     uint32_t coff[ND];

@@ -173,3 +173,61 @@ def test_full_size_sorted_equals_two_pass_on_shuffled_pixels():
     l_p = tr.train_step_pixels(img, 2, idx.to(torch.int32)).item()
     assert abs(l_p - l_t) <= 2e-6 * abs(l_t)
     assert rel_err(tr.flat_g[:-1], g_t) <= 1e-4
+
+
+@pytest.mark.parametrize("seg0,in_width,B", [(300, 4, 9001), (129, 2, 8193), (1000, 2, 12345), (7, 4, 8200)])
+def test_sort_edge_geometries(seg0, in_width, B):
+    """Layer-0 segment counts that force coarser cells (more than 2^18 bins otherwise), two-input networks (no minor key),
+    ragged batch sizes, inputs outside [-1, 1] and non-finite inputs: the order is always a permutation and the sorted
+    step equals the unsorted one."""
+    import hoir_b200 as H
+    kw = dict(layer_type="continuous", n=3, in_width=in_width, out_width=3, hidden_layers=1, hidden_width=40,
+              in_segments=seg0, out_segments=2, hidden_segments=2)
+    torch.manual_seed(1)
+    net = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **kw)
+    H.initialize_network_polynomial_layers(net, 1.0, 0.0, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.2 * torch.randn(p.shape, generator=torch.Generator().manual_seed(2)) / p.shape[1] ** 0.5)
+    tr = H.FusedTrainer(net.cuda(), lr=0.0, keep_grads=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(B, in_width, generator=g) * 2.6 - 1.3                 # 13 % of the samples outside the domain
+    y = torch.rand(B, 3, generator=g) * 2 - 1
+    order = torch.empty(B, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().hoir_mlp_batch_sort(tr.desc, B, _lib.dptr(x.cuda()), None, None, _lib.dptr(order, torch.int32),
+                                              None, _lib.stream_ptr(torch.device("cuda"))))
+    assert torch.equal(order.long().sort().values.cpu(), torch.arange(B))
+    tr.sort_min_batch, tr.batch_order = 0, "sorted"
+    l_s = tr.train_step(x.cuda(), y.cuda()).item()
+    g_s = tr.flat_g[:-1].clone()
+    tr.batch_order = "two_pass"                                          # below 32768 samples: the unsorted in-kernel walk
+    l_u = tr.train_step(x.cuda(), y.cuda()).item()
+    assert abs(l_s - l_u) <= 2e-6 * abs(l_u)
+    assert rel_err(g_s, tr.flat_g[:-1]) <= 2e-5
+    # non-finite coordinates must not crash the sort (segment_index maps NaN to segment 0, +-inf to the end segments)
+    xb = x.clone()
+    xb[::97, 0] = float("nan")
+    xb[5::101, 1] = float("inf")
+    xb[7::103, 0] = float("-inf")
+    _lib.check(_lib.lib().hoir_mlp_batch_sort(tr.desc, B, _lib.dptr(xb.cuda()), None, None, _lib.dptr(order, torch.int32),
+                                              None, _lib.stream_ptr(torch.device("cuda"))))
+    assert torch.equal(order.long().sort().values.cpu(), torch.arange(B))
+
+
+def test_sort_rejects_bad_arguments():
+    _, net = make_pair("C2")
+    tr = H.FusedTrainer(net, lr=0.0)
+    lib = _lib.lib()
+    with pytest.raises(ValueError):
+        _lib.check(lib.hoir_mlp_batch_sort(tr.desc, 16, None, None, None, None, None, None))            # neither x nor mesh
+    _lib.check(lib.hoir_mlp_batch_sort(tr.desc, 0, None, _lib.make_mesh_desc(8, 8, 2, True, 0), None, None, None, None))   # B == 0
+    _, net10 = make_pair("C1")
+    tr10 = H.FusedTrainer(net10, lr=0.0)
+    assert not lib.hoir_mlp_order_supported(tr10.desc)                  # FFMA-only network: no *_order entries
+    x = torch.zeros(64, 2, device="cuda")
+    order = torch.zeros(64, dtype=torch.int32, device="cuda")
+    _lib.check(lib.hoir_mlp_batch_sort(tr10.desc, 64, _lib.dptr(x), None, None, _lib.dptr(order, torch.int32), None, None))
+    with pytest.raises(H.HoirUnsupported):
+        _lib.check(lib.hoir_mlp_train_step_order(tr10.desc, 64, _lib.dptr(x), None, _lib.dptr(order, torch.int32), 0,
+                                                 _lib.dptr(torch.zeros(64, 3, device="cuda")), None, _lib.dptr(tr10.packed),
+                                                 tr10._g_table, tr10._loss_ptr, 1.0, None))
