@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, no_peer):
+def _worker(rank, world, port, q, no_peer, name="C2"):
     if no_peer:
         os.environ["HOIR_NO_PEER"] = "1"
     import torch.distributed as dist
@@ -28,7 +28,7 @@ def _worker(rank, world, port, q, no_peer):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     torch.manual_seed(0)
-    net = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW["C2"])
+    net = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW[name])
     H.initialize_network_polynomial_layers(net, 1.0, 0.0, generator=torch.Generator().manual_seed(0))
     net = net.cuda()
     tr = H.FusedTrainer(net, optimizer="adam", lr=1e-3)
@@ -44,9 +44,9 @@ def _worker(rank, world, port, q, no_peer):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world,name", [(2, "C2"), (4, "C2"), (8, "C2"), (2, "C3f")])
 @pytest.mark.parametrize("no_peer", [False, True], ids=["nvlink-peer-exchange", "nccl-allreduce"])
-def test_data_parallel_matches_single_gpu(no_peer, world):
+def test_data_parallel_matches_single_gpu(no_peer, world, name):
     """2 / 4 / 8 ranks (skipped below that GPU count): the rank-ordered sum over N peers and the two-buffer reuse
     protocol of the in-kernel exchange (opt_tail.cuh) over three consecutive steps."""
     if torch.cuda.device_count() < world:
@@ -56,7 +56,7 @@ def test_data_parallel_matches_single_gpu(no_peer, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, no_peer)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, no_peer, name)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
@@ -71,16 +71,22 @@ def test_data_parallel_matches_single_gpu(no_peer, world):
     else:                                             # gradient exchange inside the kernel: one launch per step
         assert all(r[3] for r in res) and res[0][4] == 1, "peer-memory exchange was not active"
     torch.manual_seed(0)
-    net = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW["C2"])
+    net = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW[name])
     H.initialize_network_polynomial_layers(net, 1.0, 0.0, generator=torch.Generator().manual_seed(0))
     net = net.cuda()
     tr = H.FusedTrainer(net, optimizer="adam", lr=1e-3)
     g = torch.Generator().manual_seed(1)
     img = torch.randint(0, 256, (64, 128, 3), generator=g, dtype=torch.uint8).cuda()
     losses = [tr.train_step_mesh(img, 2, 0, 64 * 128).item() for _ in range(3)]
+    tol = 1e-4 if name == "C3f" else 1e-5          # (the fused Fourier kernel: tf32 x 3 tensor-core passes)
     for a, b in zip(losses, res[0][1]):
-        assert abs(a - b) <= 1e-5 * abs(a)
-    assert (tr.flat_w.cpu() - res[0][2]).abs().max().item() <= 5e-5
+        assert abs(a - b) <= tol * abs(a)
+    # Adam turns round-off-sized gradient differences into +-lr steps: compare the bulk, bound the worst
+    diff = (tr.flat_w.cpu() - res[0][2]).abs()
+    if name == "C3f":
+        assert diff.max().item() <= 3 * 2e-3 and (diff > 5e-5).float().mean().item() <= 2e-2
+    else:
+        assert diff.max().item() <= 5e-5
 
 
 def _trainer_worker(rank, world, port, q, no_peer, sampling):
