@@ -102,7 +102,7 @@ struct FourierParams {
   float* slabs;                    // [p2_ctas][n_params]: private gradient slabs (zero on entry, zero on exit)
   long long n_params, woff[4];     // boundary-layout float offsets of the layers in a slab / the flat gradient
   int p2_ctas;                     // CTAs that take a batch slice in phase 2
-  int dbg;                         // profiling switches (HOIR_FOURIER_DBG): 1 no basis evaluation, 2 no MMAs, 4 no Phi stores in phase 2
+  int dbg;                         // HOIR_FOURIER_DBG bit 5 (with -DHOIR_FOURIER_TIMERS=1): print CTA 0's cycle accounting
   OptTail tail;
 };
 
@@ -239,7 +239,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
         if (leader) {
           const uint32_t wbase = smem_u32(sW + st * F_STAGE_BYTES);
           const uint64_t dW[2] = {make_desc(wbase, 512), make_desc(wbase + (uint32_t)p.outp * 128u, 512)};
-          if (!(p.dbg & 16))
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
@@ -303,10 +302,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
       const uint32_t buf = qa & 1, ph = (qa >> 1) & 1;
       float v[32], lo[32];
       const long long c0 = FCLK();
-      if (p.dbg & 8) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = xv;
-      } else
       fourier_eval<32, NT, ODD_SIN, false>(p, n, xv, v, nullptr);
 #pragma unroll
       for (int k = 0; k < 32; ++k) lo[k] = tf32_lo(v[k]);
@@ -397,7 +392,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
           a2[i] = h[i];
           if (TRAIN) wsa2[(size_t)i * FT] = live ? h[i] : 0.f;
         }
-#pragma unroll 4
+#pragma unroll 8
       for (int i = 0; i < p.hid; ++i) {
         float val[4];
         fourier_eval<4, 0, ODD_SIN, false>(p, p.n2, a2[i], val, nullptr);
@@ -449,7 +444,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
       for (int o = 0; o < 4; ++o) wsgy[(size_t)o * FT] = gy[o];
       // ---- output layer backward: dL/da2_i = sum_j phi'_j(a2_i) sum_o W2[i][j][o] gy[o];  MaxAbs backward -> g1
       float dot = 0.f;
-#pragma unroll 4
+#pragma unroll 8
       for (int i = 0; i < p.hid; ++i) {
         const float xa = a2[i];
         float val[4], der[4];
@@ -596,7 +591,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
               const uint32_t glo = layer == 2 ? 16u * 128u : gh_bytes;
               const uint64_t dG[2] = {make_desc(gbase, 512), make_desc(gbase + glo, 512)};
               const uint32_t idesc = make_idesc(128, layer == 2 ? 16 : p.outp, 1, 0);   // A: Phi^T MN-major, B: G^T K-major
-              for (int h = 0; h < 2 && mb0 + h < nb && !(p.dbg & 2); ++h) {
+              for (int h = 0; h < 2 && mb0 + h < nb; ++h) {
                 const uint64_t dU[2] = {make_desc(ubase + h * 2048, F_U_RS), make_desc(ubase + F_U_BYTES + h * 2048, F_U_RS)};
                 const uint32_t d_col = tmem + acc_col(layer, mb0 + h);
 #pragma unroll
@@ -708,7 +703,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
 #pragma unroll
                 for (int r = 0; r < XV1; ++r) xv = r == st ? cur.x1[r] : xv;
                 float val[32];
-                if (on && !(p.dbg & 1)) {
+                if (on) {
                   fourier_eval<32, NT, ODD_SIN, false>(p, nterm, xv, val, nullptr);
                 } else {
 #pragma unroll
@@ -732,7 +727,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                 const long long e2 = FCLK();
                 t_ev += e1 - e0; t_uw += e2 - e1;
                 const long long e3 = FCLK();
-                if (!(p.dbg & 4)) {
 #pragma unroll
                 for (int q4 = 0; q4 < 8; ++q4) {
                   const uint32_t off = rowoff + (((uint32_t)q4 << 4) ^ sw);
@@ -740,7 +734,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) fourier_mlp_kernel(const Fourier
                   *reinterpret_cast<float4*>(ur + off) = make_float4(val[4 * q4], val[4 * q4 + 1], val[4 * q4 + 2], val[4 * q4 + 3]);
                   *reinterpret_cast<float4*>(ul + off) = make_float4(tf32_lo(val[4 * q4]), tf32_lo(val[4 * q4 + 1]),
                                                                      tf32_lo(val[4 * q4 + 2]), tf32_lo(val[4 * q4 + 3]));
-                }
                 }
                 t_l2 += FCLK() - e3;
               }
@@ -1072,7 +1065,6 @@ int hoir_fourier_train(const hoir_mlp_desc* m, long long B, const float* x, cons
     const long long units_all = tiles * (FT / F_UNIT);
     long long n2 = (units_all + 7) / 8;
     p.p2_ctas = (int)(n2 < 1 ? 1 : (n2 > grid ? grid : n2));
-    if (getenv("HOIR_FOURIER_SKIP_GW") != nullptr) p.p2_ctas = 0;      // (profiling only: phase 1 alone)
     if (getenv("HOIR_FOURIER_DBG") != nullptr) p.dbg = atoi(getenv("HOIR_FOURIER_DBG"));
     p.woff[0] = 0;
     p.woff[1] = p.woff[0] + (long long)g.hid * g.in0 * g.n0;
