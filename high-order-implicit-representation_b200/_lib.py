@@ -100,6 +100,9 @@ _EXPORTS = {
                                      C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "hoir_mlp_fused_supported": (C.c_int, [C.POINTER(MlpDesc)]),
+    "hoir_mlp_forward_supported": (C.c_int, [C.POINTER(MlpDesc)]),
+    "hoir_interp_frame": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hoir_mlp_packed_size": (C.c_longlong, [C.POINTER(MlpDesc)]),
     "hoir_mlp_packed_offset": (C.c_longlong, [C.POINTER(MlpDesc), C.c_int]),
     "hoir_mlp_pack": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
@@ -145,6 +148,15 @@ _EXPORTS = {
 EXPORTED_SYMBOLS = tuple(_EXPORTS)
 
 _lib: Optional[C.CDLL] = None
+
+#: bumped whenever a kernel of this library writes weights through raw pointers (optimizer steps, CUDA-graph replays):
+#: tensor version counters do not see those writes, caches of kernel-side weight copies key on this as well
+WEIGHT_EPOCH = 0
+
+
+def weights_changed() -> None:
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -1153,10 +1153,20 @@ int num_sms_fused() { return hoir_num_sms(); }
 extern "C" int hoir_mlp_fused_supported(const hoir_mlp_desc* m) {
   return find_entry(m) != nullptr || (mlp_desc_ok(m) && hoir_fourier_supported(m));
 }
+// 2: the whole training step is fused (hoir_mlp_fused_supported); 1: only the forward (hoir_mlp_forward / hoir_interp_frame:
+// the neighborhood-interpolator family, fused_interp.cu -- it trains through the per-layer kernels); 0: neither
+extern "C" int hoir_mlp_forward_supported(const hoir_mlp_desc* m) {
+  if (hoir_mlp_fused_supported(m)) return 2;
+  return mlp_desc_ok(m) && hoir_interp_supported(m) ? 1 : 0;
+}
+namespace {
+bool interp_only(const hoir_mlp_desc* m) { return mlp_desc_ok(m) && find_entry(m) == nullptr && !hoir_fourier_supported(m) && hoir_interp_supported(m); }
+}  // namespace
 
 extern "C" long long hoir_mlp_packed_offset(const hoir_mlp_desc* m, int layer) {
   if (!mlp_desc_ok(m) || layer < 0 || layer > m->num_layers) return -1;
   if (hoir_fourier_supported(m)) return hoir_fourier_packed_offset(m, layer);
+  if (interp_only(m)) return hoir_interp_packed_offset(m, layer);
   long long off = 0;
   for (int l = 0; l < layer; ++l) {
     const hoir_layer_desc& d = m->layers[l];
@@ -1178,6 +1188,11 @@ extern "C" int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, floa
     for (int l = 0; l < m->num_layers; ++l)
       if (!w[l]) return hoir_set_error(HOIR_EINVAL, "null weight pointer", "hoir_mlp_pack");
     return hoir_fourier_pack(m, w, packed, (cudaStream_t)stream);
+  }
+  if (interp_only(m)) {
+    for (int l = 0; l < m->num_layers; ++l)
+      if (!w[l]) return hoir_set_error(HOIR_EINVAL, "null weight pointer", "hoir_mlp_pack");
+    return hoir_interp_pack(m, w, packed, (cudaStream_t)stream);
   }
   for (int l = 0; l < m->num_layers; ++l) {
     const hoir_layer_desc& d = m->layers[l];
@@ -1201,6 +1216,10 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
                                 int post_scale, void* stream) {
   if (mlp_desc_ok(m) && hoir_fourier_supported(m))
     return hoir_fourier_forward(m, B, x, mesh, packed, y, post_scale, (cudaStream_t)stream);
+  if (interp_only(m)) {
+    if (mesh != nullptr) return hoir_set_error(HOIR_EUNSUPPORTED, "mesh coordinates: implicit-image networks only", "hoir_mlp_forward");
+    return hoir_interp_forward(m, B, x, packed, y, post_scale, (cudaStream_t)stream);
+  }
   const FusedEntry* e = find_entry(m);
   if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", "hoir_mlp_forward");
   FusedParams p;

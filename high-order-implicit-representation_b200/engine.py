@@ -181,6 +181,7 @@ class FusedTrainer:
         if self.keep_grads:
             self.flat_g.zero_()
         self.step_count += 1
+        _lib.weights_changed()
         scale = self._loss_scale(B, global_batch)
         ev = None
         if self.kernel_events is not None:
@@ -451,6 +452,7 @@ class GraphedStep:
         return loss
 
     def replay(self) -> Tensor:
+        _lib.weights_changed()
         self.optimizer.refresh_hyper()          # step count / lr -> device scalars, ordered before the replay
         self.graph.replay()
         return self.loss

@@ -131,10 +131,42 @@ class HighOrderMLP(nn.Module):
         desc = self.mlp_desc()
         return bool(desc is not None and _lib.lib().hoir_mlp_fused_supported(desc))
 
+    def forward_fused_supported(self) -> bool:
+        """The forward has a whole-network kernel (``hoir_mlp_forward``): every ``fused_supported`` network, plus the
+        neighborhood-interpolator family whose TRAINING stays on the per-layer kernels."""
+        desc = self.mlp_desc()
+        return bool(desc is not None and _lib.lib().hoir_mlp_forward_supported(desc))
+
+    def packed_weights(self) -> Tensor:
+        """Kernel-side weights of ``hoir_mlp_forward`` / ``hoir_interp_frame``, re-packed only when a ``w`` changed
+        (tensor version counters + the library's weight epoch, which the optimizers and graph replays of this package
+        bump; the 101 frames of a generate_sequence pack once).  After writing weights through raw pointers from
+        outside, call ``_lib.weights_changed()``."""
+        ws = [l.w for l in self.high_order_layers()]
+        key = (_lib.WEIGHT_EPOCH,) + tuple((w.data_ptr(), w._version) for w in ws)
+        if getattr(self, "_packed_key", None) != key:
+            lib, desc, dev = _lib.lib(), self.mlp_desc(), ws[0].device
+            packed = torch.empty(lib.hoir_mlp_packed_size(desc), device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                _lib.check(lib.hoir_mlp_pack(desc, _lib.ptr_table([w.detach().contiguous() for w in ws]), _lib.dptr(packed),
+                                             _lib.stream_ptr(dev)))
+            self._packed, self._packed_key = packed, key
+        return self._packed
+
     def forward(self, x: Tensor) -> Tensor:
-        if self.use_fused and x.is_cuda and not (x.requires_grad and torch.is_grad_enabled()) \
-                and x.dim() == 2 and self.fused_supported():
-            return _FusedMLPFunction.apply(x, self.mlp_desc(), *[l.w for l in self.high_order_layers()])
+        if self.use_fused and x.is_cuda and x.dim() == 2 and not (x.requires_grad and torch.is_grad_enabled()):
+            if self.fused_supported():
+                return _FusedMLPFunction.apply(x, self.mlp_desc(), *[l.w for l in self.high_order_layers()])
+            if not torch.is_grad_enabled() and x.dtype == torch.float32 and self.forward_fused_supported():
+                # inference of a network whose forward alone is fused (the interpolators): one launch, no autograd
+                desc = self.mlp_desc()
+                x2 = x.contiguous()
+                y = torch.empty((x2.shape[0], desc.layers[desc.num_layers - 1].out_features), device=x2.device)
+                with torch.cuda.device(x2.device):
+                    _lib.check(_lib.lib().hoir_mlp_forward(desc, x2.shape[0], _lib.dptr(x2), None,
+                                                           _lib.dptr(self.packed_weights()), _lib.dptr(y), 0,
+                                                           _lib.stream_ptr(x2.device)))
+                return y
         return self.model(x)
 
 
@@ -213,6 +245,7 @@ class Adam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.lib()
+        _lib.weights_changed()               # (raw-pointer writes: invisible to the tensors' version counters)
         if self.capturable and not torch.cuda.is_current_stream_capturing():
             self.refresh_hyper()
         for group in self.param_groups:

@@ -55,6 +55,21 @@ def neighborhood_sample_generator(model: nn.Module, image: Tensor, width: int, o
         img = image.contiguous().float()
         Cc, Hh, Ww = img.shape
         pad = 2 * outside + width
+        from .networks import HighOrderMLP
+        mlp = model if isinstance(model, HighOrderMLP) else getattr(model, "model", None)     # Net(cfg).model
+        total = width + 2 * outside
+        if (isinstance(mlp, HighOrderMLP) and mlp.use_fused and mlp.forward_fused_supported() and not mlp.fused_supported()
+                and mlp.high_order_layers()[0].in_features == Cc * (total * total - width * width)
+                and mlp.high_order_layers()[-1].out_features == Cc * width * width and pad < min(Hh, Ww)
+                and next(mlp.parameters()).device == img.device):
+            # ONE launch per frame: reflection pad + stride-w gather + whole-network forward + fold + crop + blend
+            out = torch.empty_like(img)
+            prev_c = prev.contiguous().float() if prev is not None else None
+            with torch.cuda.device(img.device):
+                _lib.check(_lib.lib().hoir_interp_frame(mlp.mlp_desc(), _lib.dptr(img), Cc, Hh, Ww, width, outside,
+                                                        _lib.dptr(mlp.packed_weights()), float(alpha), _lib.dptr(prev_c),
+                                                        _lib.dptr(out), _lib.stream_ptr(img.device)))
+            return out
         feat, _, _ = neighborhood_gather(img, width, outside, stride=width, pad=pad, want_targets=False)
         outs = [model(feat[b * batch_size:(b + 1) * batch_size])
                 for b in range((len(feat) + batch_size) // batch_size)]

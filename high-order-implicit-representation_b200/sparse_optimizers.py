@@ -34,6 +34,7 @@ class SparseLion(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.lib()
+        _lib.weights_changed()               # (raw-pointer writes: invisible to the tensors' version counters)
         if self.capturable and not torch.cuda.is_current_stream_capturing():
             self.refresh_hyper()
         for group in self.param_groups:

@@ -165,6 +165,11 @@ int hoir_radial_sample(const float* images, const float* stripes, int M, int C, 
  * rows are then one contiguous run): hoir_mlp_packed_size includes it, hoir_mlp_pack and the optimizer tail
  * write both. */
 int hoir_mlp_fused_supported(const hoir_mlp_desc* m);           /* 1 / 0 */
+/* 2: forward AND training step are fused (== hoir_mlp_fused_supported); 1: the forward only -- the neighborhood
+ * interpolator family (many-segment input layer + 2-segment hidden / output layers, <= 64 wide, <= 32 outputs; e.g.
+ * 216 -> 50 -> 50 -> 50 -> 27 of /root/reference/config/neighborhood_config.yaml): hoir_mlp_pack / hoir_mlp_forward /
+ * hoir_interp_frame apply, training goes through the per-layer entry points; 0: neither */
+int hoir_mlp_forward_supported(const hoir_mlp_desc* m);
 long long hoir_mlp_packed_size(const hoir_mlp_desc* m);         /* floats, or -1 */
 long long hoir_mlp_packed_offset(const hoir_mlp_desc* m, int layer);
 int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, float* packed, void* stream);
@@ -174,6 +179,16 @@ int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, float* packed, 
 int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float* x,
                      const hoir_mesh_desc* mesh, const float* packed, float* y, int post_scale,
                      void* stream);
+
+/* One pass of the neighborhood interpolator over an image in ONE launch: reflection pad by 2*outside + width,
+ * stride-width donut patches, model forward, fold, crop and blend
+ *   out = alpha * prev + (1 - alpha) * new        (prev NULL: out = new)
+ * -- neighborhood_sample_generator + the blend of generate_sequence,
+ * /root/reference/high_order_implicit_representation/rendering.py:28-95, 119.  image / prev / out are [C][H][W];
+ * the network must map C*((w+2o)^2 - w^2) features to C*w*w outputs; out must not alias image.  No feature tensor and
+ * no activation touches HBM. */
+int hoir_interp_frame(const hoir_mlp_desc* m, const float* image, int C, int H, int W, int width, int outside,
+                      const float* packed, float alpha, const float* prev_image, float* out_image, void* stream);
 
 /* One fused forward + MSE + backward pass (Net.eval_step + loss.backward(),
  * /root/reference/high_order_implicit_representation/networks.py:64-70):

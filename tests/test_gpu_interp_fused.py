@@ -1,0 +1,228 @@
+"""The fused FORWARD of the neighborhood-interpolator family (csrc/fused_interp.cu): hoir_mlp_forward on explicit
+feature rows and hoir_interp_frame (reflection pad + stride-w donut gather + network + fold + crop + blend in ONE launch;
+/root/reference/high_order_implicit_representation/rendering.py:28-95, 119) against the CPU oracle and against this
+package's own gather -> per-layer kernels -> fold path.  Tolerance 1e-5 relative (BASELINE.json: piecewise layers)."""
+import pytest
+import torch
+
+import hoir_b200 as H
+from hoir_b200 import _lib
+from oracle import hol_oracle as O
+from helpers import MLP_KW, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+VARIANTS = {
+    # BASELINE config C4: 216 -> 50 -> 50 -> 50 -> 27 (/root/reference/config/neighborhood_config.yaml:25-31)
+    "C4": dict(layer_type="continuous", n=3, in_width=216, out_width=27, hidden_layers=2, hidden_width=50,
+               in_segments=50, out_segments=2, hidden_segments=2),
+    "C4s": MLP_KW["C4s"],                                             # width 3, outside 1 (the reference's tests)
+    "disc3": dict(layer_type="discontinuous", n=3, in_width=48, out_width=27, hidden_layers=2, hidden_width=50,
+                  in_segments=20, out_segments=2, hidden_segments=2),
+    "disc2": dict(layer_type="discontinuous", n=2, in_width=24, out_width=3, hidden_layers=1, hidden_width=10,
+                  in_segments=100, out_segments=2, hidden_segments=2),
+    "deep": dict(layer_type="continuous", n=2, in_width=24, out_width=3, hidden_layers=3, hidden_width=64,
+                 in_segments=7, out_segments=2, hidden_segments=2),
+    "odd": dict(layer_type="continuous", n=3, in_width=9, out_width=32, hidden_layers=1, hidden_width=33,
+                in_segments=16, out_segments=2, hidden_segments=2),
+}
+
+
+def pair(name, normalization=True, seed=0):
+    kw = VARIANTS[name]
+    torch.manual_seed(seed)
+    ref = O.HighOrderMLP(normalization=O.MaxAbsNormalization if normalization else None, **kw)
+    O.initialize_network_polynomial_layers(ref, max_slope=1.0, max_offset=0.0)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.add_(0.3 * torch.randn_like(p) / p.shape[1] ** 0.5)
+        if not normalization:
+            # keep every activation inside [-1, 1] on a probe batch: three layers of quadratic extrapolation otherwise
+            # reach 1e10, where no fp32 path (this kernel, the per-layer kernels, the oracle against fp64) holds 1e-5
+            x = torch.rand(2048, kw["in_width"], generator=torch.Generator().manual_seed(99)) * 2.2 - 1.1
+            for layer in ref.model:
+                y = layer(x)
+                layer.w.div_(1.05 * y.abs().max())
+                x = layer(x)
+    net = H.HighOrderMLP(normalization=H.MaxAbsNormalization if normalization else None, **kw)
+    net.load_state_dict(ref.state_dict())
+    return ref, net.cuda()
+
+
+def test_support_matrix():
+    def sup(**kw):
+        base = dict(VARIANTS["C4"], normalization=H.MaxAbsNormalization)
+        base.update(kw)
+        return _lib.lib().hoir_mlp_forward_supported(H.HighOrderMLP(**base).mlp_desc())
+    assert sup() == 1 and sup(layer_type="discontinuous", in_segments=32) == 1 and sup(n=2) == 1 and sup(hidden_layers=3) == 1
+    assert sup(hidden_width=64) == 1 and sup(out_width=32) == 1 and sup(in_segments=3) == 1
+    assert sup(hidden_width=65) == 0 and sup(out_width=33) == 0 and sup(hidden_layers=4) == 0
+    assert sup(hidden_segments=3) == 0 and sup(n=4) == 0 and sup(layer_type="fourier") == 0
+    assert sup(in_segments=200) == 0                         # one input's node rows no longer fit a ring stage
+    c2 = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW["C2"])
+    assert _lib.lib().hoir_mlp_forward_supported(c2.mlp_desc()) == 2        # whole training step fused
+    c4 = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **VARIANTS["C4"])
+    assert c4.forward_fused_supported() and not c4.fused_supported()
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+@pytest.mark.parametrize("norm", [True, False])
+def test_forward_matches_oracle(name, norm):
+    ref, net = pair(name, norm)
+    assert net.forward_fused_supported() and not net.fused_supported()
+    kw = VARIANTS[name]
+    for B in (1, 31, 255, 256, 257, 2000):
+        g = torch.Generator().manual_seed(B)
+        x = torch.rand(B, kw["in_width"], generator=g) * 2.2 - 1.1
+        with torch.no_grad():
+            want = ref(x)
+            got = net(x.cuda())
+        assert got.shape == want.shape
+        assert rel_err(got, want) <= TOL, (name, norm, B)
+    with torch.no_grad():
+        assert net(torch.empty(0, kw["in_width"], device="cuda")).shape == (0, kw["out_width"])
+
+
+def test_forward_adversarial_inputs():
+    """Exact segment boundaries, +-1 and values just outside on every layer-0 input (first-segment-wins rounding)."""
+    from helpers import adversarial_inputs
+    ref, net = pair("C4s")
+    v = adversarial_inputs(50)
+    g = torch.Generator().manual_seed(5)
+    x = v[torch.randint(len(v), (1500, 48), generator=g)]
+    with torch.no_grad():
+        assert rel_err(net(x.cuda()), ref(x)) <= TOL
+
+
+def test_forward_matches_per_layer_kernels_and_autograd_still_works():
+    ref, net = pair("C4")
+    x = torch.rand(3000, 216, generator=torch.Generator().manual_seed(1)).cuda() * 2 - 1
+    with torch.no_grad():
+        fused = net(x)
+        net.use_fused = False
+        layered = net(x)
+        net.use_fused = True
+    assert rel_err(fused, layered) <= TOL
+    # with grad enabled the forward stays on the per-layer autograd kernels (training of this family)
+    y = net(x)
+    assert y.requires_grad
+    y.square().mean().backward()
+    assert all(p.grad is not None for p in net.parameters())
+
+
+def test_packed_weights_follow_the_optimizer():
+    """The packed copy is keyed on tensor versions AND the library's weight epoch: raw-pointer optimizer steps
+    (hoir_b200.Adam) invalidate it."""
+    ref, net = pair("C4s")
+    x = torch.rand(500, 48, generator=torch.Generator().manual_seed(2)).cuda() * 2 - 1
+    with torch.no_grad():
+        before = net(x)
+    p0 = net.packed_weights()
+    assert net.packed_weights() is p0                       # cached
+    opt = H.Adam(net.parameters(), lr=1e-2)
+    net(x).square().mean().backward()
+    opt.step()
+    with torch.no_grad():
+        after = net(x)
+        net.use_fused = False
+        layered = net(x)
+    assert net.packed_weights() is not p0
+    assert rel_err(after, layered) <= TOL and rel_err(after, before) > 1e-4
+    net.use_fused = True
+    with torch.no_grad():                                    # in-place torch update: the version counter moves
+        net.high_order_layers()[0].w.mul_(0.5)
+        a2 = net(x)
+        net.use_fused = False
+        assert rel_err(a2, net(x)) <= TOL
+
+
+@pytest.mark.parametrize("name,width,outside", [("C4", 3, 3), ("C4s", 3, 1), ("disc2", 1, 1)])
+@pytest.mark.parametrize("h,w", [(21, 21), (40, 57), (99, 64)])
+def test_frame_matches_oracle_and_unfused_path(name, width, outside, h, w):
+    ref, net = pair(name)
+    if 2 * outside + width >= min(h, w):
+        pytest.skip("reflection padding needs a larger image")
+    img = torch.rand(3, h, w, generator=torch.Generator().manual_seed(h * w)) * 2 - 1
+    want = O.neighborhood_sample_generator(ref, img, width=width, outside=outside, batch_size=1 << 14)
+    got = H.neighborhood_sample_generator(net, img.cuda(), width=width, outside=outside)
+    assert got.shape == img.shape
+    assert rel_err(got, want) <= TOL
+    net.use_fused = False
+    unfused = H.neighborhood_sample_generator(net, img.cuda(), width=width, outside=outside)
+    assert rel_err(got, unfused) <= TOL
+    # blend with a previous frame (generate_sequence, rendering.py:119)
+    net.use_fused = True
+    prev = torch.rand(3, h, w, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    got_b = H.neighborhood_sample_generator(net, img.cuda(), width=width, outside=outside, alpha=0.75, prev=prev.cuda())
+    assert rel_err(got_b, 0.75 * prev + 0.25 * want) <= TOL
+
+
+def test_frame_is_one_launch_and_sequence_matches(monkeypatch):
+    ref, net = pair("C4")
+    calls = []
+    lib = _lib.lib()
+    real = lib.hoir_interp_frame
+
+    class Spy:
+        def __getattr__(self, k):
+            if k == "hoir_interp_frame":
+                def f(*a):
+                    calls.append(k)
+                    return real(*a)
+                return f
+            if k in ("hoir_neighborhood_gather", "hoir_neighborhood_fold", "hoir_layer_forward"):
+                raise AssertionError(f"{k} called: the frame did not take the one-launch path")
+            return getattr(lib, k)
+    monkeypatch.setattr(_lib, "lib", lambda: Spy())
+    img = torch.rand(3, 48, 48, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    seq = H.generate_sequence(net, img.cuda(), frames=3, width=3, outside=3, alpha=0.75)
+    monkeypatch.undo()
+    assert calls == ["hoir_interp_frame"] * 3 and seq.shape == (4, 3, 48, 48)
+    this = img.clone()
+    for _ in range(3):
+        this = 0.75 * this + 0.25 * O.neighborhood_sample_generator(ref, this, 3, 3, 1 << 14)
+    assert rel_err(seq[-1], 0.5 * (this + 1)) <= 3 * TOL          # three iterated frames
+
+
+def test_frame_argument_errors():
+    _, net = pair("C4")
+    lib = _lib.lib()
+    img = torch.zeros(3, 32, 32, device="cuda")
+    out = torch.empty_like(img)
+    st = _lib.stream_ptr(img.device)
+    pk = net.packed_weights()
+
+    def call(image=img, C=3, Hh=32, Ww=32, width=3, outside=3, o=out):
+        return lib.hoir_interp_frame(net.mlp_desc(), _lib.dptr(image), C, Hh, Ww, width, outside, _lib.dptr(pk), 0.0, None,
+                                     _lib.dptr(o), st)
+    _lib.check(call())
+    with pytest.raises(ValueError):
+        _lib.check(call(width=3, outside=1))                  # 48 features expected by the geometry, network has 216
+    with pytest.raises(ValueError):
+        _lib.check(call(Hh=8, Ww=8))                          # pad 9 >= image
+    with pytest.raises(ValueError):
+        _lib.check(call(o=img))                               # aliasing
+    c2 = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW["C2"]).cuda()
+    with pytest.raises(H.HoirUnsupported):
+        _lib.check(lib.hoir_interp_frame(c2.mlp_desc(), _lib.dptr(img), 3, 32, 32, 3, 3, _lib.dptr(pk), 0.0, None,
+                                         _lib.dptr(out), st))
+    torch.cuda.synchronize()
+
+
+def test_frame_full_size_properties():
+    """1024 x 1024 frame (BASELINE C4 geometry, 118k patches): fused frame == this package's unfused path, alpha = 1
+    returns prev exactly, and a constant image maps to a constant image."""
+    _, net = pair("C4")
+    img = torch.rand(3, 1024, 1024, generator=torch.Generator().manual_seed(9)).cuda() * 2 - 1
+    got = H.neighborhood_sample_generator(net, img, width=3, outside=3)
+    net.use_fused = False
+    unfused = H.neighborhood_sample_generator(net, img, width=3, outside=3)
+    net.use_fused = True
+    assert rel_err(got, unfused) <= TOL
+    same = H.neighborhood_sample_generator(net, img, width=3, outside=3, alpha=1.0, prev=img)
+    assert torch.equal(same, img)
+    const = torch.full((3, 256, 256), 0.25, device="cuda")
+    oc = H.neighborhood_sample_generator(net, const, width=3, outside=3)
+    per_block = oc[:, :3, :3]
+    assert torch.equal(oc, per_block.repeat(1, 86, 86)[:, :256, :256])
