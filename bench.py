@@ -285,9 +285,15 @@ def run_secondary(H, dev, trainer, img, flush, peak_tf, rank, world, dist, which
         ms = _timeit(step, 10)
         entry("c4_train", B, ms, C4_FLOP, "patches/s",
               workload="C4: interpolator continuous n=2, 216->50->50->50->27, 2048^2 image, 2^16 patches/step (gather + step)")
-        ms = _timeit(lambda: H.neighborhood_sample_generator(net, im, 3, 3), 3, warm=1)
-        out["c4_frame"] = {"value": ms, "unit": "ms/frame", "workload": "one generate_sequence frame on 2048^2 "
-                           "(reflect-pad + stride-3 gather + forward + fold + crop)"}
+        ms = _timeit(lambda: H.neighborhood_sample_generator(net, im, 3, 3), 10, warm=2)
+        net.use_fused = False
+        ms_layers = _timeit(lambda: H.neighborhood_sample_generator(net, im, 3, 3), 3, warm=1)
+        net.use_fused = True
+        patches = ((2048 + 9) // 3 + 1) ** 2
+        out["c4_frame"] = {"value": ms, "unit": "ms/frame", "patches_per_s": patches / (ms * 1e-3), "launches": 1,
+                           "per_layer_path_ms": ms_layers,
+                           "workload": "one generate_sequence frame on 2048^2 in ONE launch (hoir_interp_frame: reflect-pad + "
+                                       "stride-3 gather + 216->50->50->50->27 forward + fold + crop + blend)"}
 
     def c1_b256():
         kw = dict(layer_type="continuous", n=3, in_width=2, out_width=3, hidden_layers=2, hidden_width=10,

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
         const int nch = p.tc_nch[l];
         for (int c = 0; c < nch; ++c, ++qw, ++qa) {
           const uint32_t st = qw % I_WSTAGES, wph = (qw / I_WSTAGES) & 1, buf = qa & 1, ph = (qa >> 1) & 1;
-          mbar_wait(&bars[IB_AFULL0 + buf], ph);
+          if (l == 0 && c == 0) mbar_wait_backoff(&bars[IB_AFULL0 + buf], ph, 256);   // the tile's whole layer 0 away
+          else mbar_wait(&bars[IB_AFULL0 + buf], ph);
           mbar_wait(&bars[IB_WFULL0 + st], wph);
           fence_after();
           if (leader) {
@@ -220,8 +221,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
     const int blk = warp >> 2;
     const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float4* myrec = sRec + warp * 32;
-    const int qtr = lane >> 3, l8 = lane & 7;
-    const bool act = 4 * l8 < p.op4, act1 = 32 + 4 * l8 < p.op4;
+    const int qtr = lane >> 3, l8 = lane & 7, rowb = p.op4 * 4;   // bytes per node row of the layer-0 table
     const LagrangeTable& lag = p.lag;
     uint32_t ql = 0, qa = 0, qd = 0;
     const int fg = p.width + p.outside, WW = p.width * p.width;
@@ -248,35 +248,43 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
         for (int k = 0; k < 8; ++k)
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[k][c] = 0.f;
-        // the 4 (or fewer) input values of group g of this lane's sample; issued one group ahead of their use
-        auto load_x = [&](int g, float* xv) {
+        // the 4 (or fewer) input values of group g of this lane's sample, issued one group ahead of their use; patch mode
+        // reads its donut-cell table entries one group earlier still (no LDS -> address -> LDG chain on the issue path)
+        auto load_tab = [&](int g, int* t) {
+          const int i0 = g * p.gi;
+#pragma unroll
+          for (int il = 0; il < 4; ++il) t[il] = (p.x == nullptr && il < p.gi && i0 + il < p.in0) ? sTab[i0 + il] : 0;
+        };
+        auto load_x = [&](int g, const int* t, float* xv) {
           const int i0 = g * p.gi, gi = min(p.gi, p.in0 - i0);
 #pragma unroll
           for (int il = 0; il < 4; ++il) {
             xv[il] = 0.f;
             if (live && il < gi) {
-              if (p.x != nullptr) {
+              if (p.x != nullptr)
                 xv[il] = __ldg(p.x + bl * p.in0 + i0 + il);
-              } else {
-                const int t = sTab[i0 + il];
-                xv[il] = __ldg(p.image + ((size_t)(t >> 16) * p.H + reflect(y0 + ((t >> 8) & 255), p.H)) * p.W +
-                               reflect(x0 + (t & 255), p.W));
-              }
+              else
+                xv[il] = __ldg(p.image + ((size_t)(t[il] >> 16) * p.H + reflect(y0 + ((t[il] >> 8) & 255), p.H)) * p.W +
+                               reflect(x0 + (t[il] & 255), p.W));
             }
           }
         };
-        // basis record of (this lane's sample, input il of a group): first node row (floats from the slab) + N values
+        // basis record of (this lane's sample, input il of a group): first node row (bytes from the slab) + N values
         auto make_record = [&](float xval, int il, float4* dst) {
           const int id = hoir::segment_index(xval, 1.f, 2.f, p.segf0, p.seg0);
           const float xi = p.pow2_0 ? hoir::local_coordinate<true>(xval, id, 1.f, 2.f, p.segf0, p.inv_segf0)
                                     : hoir::local_coordinate<false>(xval, id, 1.f, 2.f, p.segf0, p.inv_segf0);
           float l[N];
           hoir::lagrange<N>(lag.X, lag.D, xi, l);
-          dst[lane] = make_float4(__int_as_float((il * p.nodes0 + id * p.stride0) * p.op4), l[0], N > 1 ? l[1] : 0.f,
+          HOIR_DBG_ASSERT(id >= 0 && il < p.gi && (uint32_t)((il * p.nodes0 + id * p.stride0 + N) * rowb) <= p.stage_bytes0);
+          dst[lane] = make_float4(__int_as_float((il * p.nodes0 + id * p.stride0) * rowb), l[0], N > 1 ? l[1] : 0.f,
                                   N > 2 ? l[2] : 0.f);
         };
         float xv[4], xn[4];
-        load_x(0, xv);
+        int tb[4];
+        load_tab(0, tb);
+        load_x(0, tb, xv);
+        load_tab(1, tb);
         uint32_t cnt = 0;                                      // records are double-buffered: input k lives in buffer k & 1
         make_record(xv[0], 0, myrec);
         __syncwarp();
@@ -288,13 +296,14 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
 #pragma unroll
           for (int il = 0; il < 4; ++il) xn[il] = 0.f;
           const long long cx0 = ICLK();
-          if (more) load_x(g + 1, xn);
+          if (more) load_x(g + 1, tb, xn);
+          load_tab(g + 2, tb);
           const long long c0 = ICLK();
           tm_ldx += c0 - cx0;
           mbar_wait(&bars[IB_LFULL0 + st], ph);
           const long long c1 = ICLK();
           tm_lwait += c1 - c0;
-          const float* slab = reinterpret_cast<const float*>(sLRing + (size_t)st * p.stage_bytes0) + 4 * l8;
+          const uint8_t* slab = sLRing + (size_t)st * p.stage_bytes0 + 16 * l8;
 #pragma unroll
           for (int il = 0; il < 4; ++il) {
             if (il < gi) {
@@ -307,12 +316,13 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
               for (int k = 0; k < 8; ++k) {
                 const float4 rc = cur[4 * k];               // 4 distinct records per instruction (one per quarter-warp)
                 const float lj[3] = {rc.y, rc.z, rc.w};
-                const float* row = slab + __float_as_int(rc.x);
+                const uint8_t* row = slab + __float_as_int(rc.x);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-                  if (act) a = *reinterpret_cast<const float4*>(row + j * p.op4);
-                  if (act1) c = *reinterpret_cast<const float4*>(row + j * p.op4 + 32);
+                  // every lane loads (lanes past the row's last output read the next row / stage: in bounds of the ring,
+                  // never stored) -- no predicates, no zero fills in the inner loop
+                  const float4 a = *reinterpret_cast<const float4*>(row + j * rowb);
+                  const float4 c = *reinterpret_cast<const float4*>(row + j * rowb + 128);
                   acc[k][0] = fmaf(lj[j], a.x, acc[k][0]); acc[k][1] = fmaf(lj[j], a.y, acc[k][1]);
                   acc[k][2] = fmaf(lj[j], a.z, acc[k][2]); acc[k][3] = fmaf(lj[j], a.w, acc[k][3]);
                   acc[k][4] = fmaf(lj[j], c.x, acc[k][4]); acc[k][5] = fmaf(lj[j], c.y, acc[k][5]);
@@ -336,6 +346,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int o = (c < 4 ? 0 : 28) + 4 * l8 + c;
+            HOIR_DBG_ASSERT(o >= p.hid || (warp * 32 + 4 * k + qtr) * I_PITCH + o < IT * I_PITCH);
             if (o < p.hid) rows[(4 * k + qtr) * I_PITCH + o] = acc[k][c];
           }
         __syncwarp();

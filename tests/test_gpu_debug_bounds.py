@@ -58,6 +58,16 @@ assert torch.isfinite(tr.forward(x.cuda())).all()
 net2 = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW["C4s"]).cuda()
 xs = (torch.rand(5000, 48, generator=g) * 2 - 1).cuda()
 net2(xs).square().mean().backward()
+# fused interpolator forward (layer-0 ring + tcgen05 layers, csrc/fused_interp.cu): explicit rows and the one-launch frame
+with torch.no_grad():
+    fused = net2(xs)
+    net2.use_fused = False
+    assert rel_err(fused, net2(xs)) <= 1e-5
+    net2.use_fused = True
+    img = (torch.rand(3, 70, 45, generator=g) * 2 - 1).cuda()
+    fr = H.neighborhood_sample_generator(net2, img, 3, 1, alpha=0.5, prev=img)
+    net2.use_fused = False
+    assert rel_err(fr, H.neighborhood_sample_generator(net2, img, 3, 1, alpha=0.5, prev=img)) <= 1e-5
 torch.cuda.synchronize()
 print("DEBUG_BOUNDS_OK")
 '''
