@@ -6,22 +6,28 @@
 //
 // One launch = the inference pass of /root/reference/high_order_implicit_representation/rendering.py:28-95:
 // ReflectionPad2d + stride-w donut patches + model forward + F.fold + crop + alpha blend (generate_sequence, :98-126),
-// or the plain forward y = MLP(x) of an explicit batch.  Per 256-sample tile (8 sample warps + MMA warp + loader warp):
+// or the plain forward y = MLP(x) of an explicit batch.  Per 256-sample tile (16 compute warps + MMA warp + loader warp):
 //
 //   layer 0   a gather (2.2 MB of weights for 216 x 51 x 50): the packed table [in][node][out] streams through a 3-stage
-//             shared-memory ring (cp.async.bulk + mbarrier tx count); a warp owns 32 samples, lanes = outputs (two per
-//             lane, conflict-free LDS.64 of the node rows), the 32 x 2 partial sums stay in registers across all input
-//             groups (the ring never waits for the tensor-core layers: their weight chunks have a ring of their own).
+//             shared-memory ring (cp.async.bulk + mbarrier tx count), one or two inputs per stage.  Warps w and w + 8
+//             share a group of 32 samples (16 each).  Lanes = (sample, input of the stage) evaluate segment index, local
+//             coordinate and basis values once and leave a 16-byte record in shared memory; for the contraction a
+//             quarter-warp owns one sample (8 lanes x 2 x 4 outputs), so one LDS.128 fetches 128 contiguous bytes of
+//             the node rows of FOUR samples, conflict-free; the partial sums stay in registers across all inputs.
+//             The layer is bound by those shared-memory reads: 200 bytes per (sample, input, node) for 50 FMAs.
 //             Patch mode: the input value of (sample, feature) is read straight from the image (reflection and
 //             donut order computed in-kernel) -- no [B, 216] feature tensor in HBM.
-//   hidden /  the tile's layer-0 output goes through shared memory to thread-per-sample form; MaxAbs in registers; every
-//   output    2-segment layer is a dense contraction over its densified basis (ND = 3 .. 6 node slots per input, 32 / ND
-//   layers    inputs per 32-column chunk) on tcgen05 (kind::tf32, 3 passes A*B + A_lo*B + A*B_lo): the sample threads write
-//             the basis chunks straight into TMEM, the pre-swizzled hi | lo weight-chunk images stream through the same
-//             ring region, accumulators in TMEM.
+//   hidden /  the tile's layer-0 output goes to shared memory rows; the main warp of each pair (thread = sample) runs
+//   output    MaxAbs and every 2-segment layer as a dense contraction over its densified basis (ND = 3 .. 6 node slots
+//   layers    per input, 32 / ND inputs per 32-column chunk) on tcgen05 (kind::tf32, 3 passes A*B + A_lo*B + A*B_lo):
+//             basis chunks are written straight into TMEM, the pre-swizzled hi | lo weight-chunk images stream through
+//             a ring of their own, accumulators in TMEM, results back to the shared-memory row.  The helper warp of
+//             the pair meanwhile gathers the next tile (two mbarriers per pair hand the rows back and forth).
 //   output    y[b][out], or the fold: pixel (c, ph*w + kh - (w+o), pw*w + kw - (w+o)) = alpha*prev + (1-alpha)*value.
 //
 // Activations never touch HBM.  Training of this family stays on the per-layer kernels (slab_kernels.cu, dense_tc.cu).
+// The layer-0 loop is kept small on purpose: an earlier version with the four inputs of a group unrolled (7.7 k SASS
+// instructions) lost 25 % to instruction-cache misses.
 #include <stdlib.h>
 #include <string.h>
 #include "hoir_common.cuh"
@@ -41,15 +47,16 @@
 namespace {
 using namespace tc;
 
-constexpr int IT = 256, I_THREADS = 320, I_LSTAGES = 3, I_WSTAGES = 4;
-constexpr uint32_t I_LRING_BYTES = 81920, I_WSTAGE_BYTES = 16384;     // layer-0 slab ring (3 stages); weight-chunk ring (4 x 16 KB)
+constexpr int IT = 256, I_CWARPS = 16, I_MMA_WARP = 16, I_LOAD_WARP = 17, I_THREADS = 576, I_LSTAGES = 3, I_WSTAGES = 4;
+constexpr uint32_t I_LRING_BYTES = 77824, I_WSTAGE_BYTES = 16384;     // layer-0 slab ring (3 stages); weight-chunk ring (4 x 16 KB)
 constexpr int I_PITCH = 65, I_MAXW = 64, I_MAXTC = 4;        // activation row pitch; widest row; tensor-core layers
 constexpr int I_A_COL = 0, I_D_COL = 256;
 enum { IB_LFULL0 = 0, IB_LEMPTY0 = IB_LFULL0 + I_LSTAGES, IB_WFULL0 = IB_LEMPTY0 + I_LSTAGES, IB_WEMPTY0 = IB_WFULL0 + I_WSTAGES,
-       IB_AFULL0 = IB_WEMPTY0 + I_WSTAGES, IB_AFULL1, IB_AEMPTY0, IB_AEMPTY1, IB_DFULL, IB_DEMPTY, IB_COUNT };
+       IB_AFULL0 = IB_WEMPTY0 + I_WSTAGES, IB_AFULL1, IB_AEMPTY0, IB_AEMPTY1, IB_DFULL, IB_DEMPTY,
+       IB_ROWS_FULL0, IB_ROWS_FREE0 = IB_ROWS_FULL0 + 8, IB_COUNT = IB_ROWS_FREE0 + 8 };   // per (main, helper) pair: rows written / rows read
 constexpr int I_MAXIN = 1024;                                          // features of a patch (donut-cell table)
 constexpr uint32_t IS_LRING = 0, IS_WRING = I_LRING_BYTES, IS_ACT = IS_WRING + I_WSTAGES * I_WSTAGE_BYTES,
-                   IS_REC = IS_ACT + IT * I_PITCH * 4, IS_TAB = IS_REC + 2 * 8 * 32 * 16, IS_BAR = IS_TAB + I_MAXIN * 4,
+                   IS_REC = IS_ACT + IT * I_PITCH * 4, IS_TAB = IS_REC + I_CWARPS * 64 * 16, IS_BAR = IS_TAB + I_MAXIN * 4,
                    IS_TOTAL = IS_BAR + 512;
 static_assert(IS_TOTAL <= 227 * 1024, "shared-memory plan");
 
@@ -104,19 +111,6 @@ __device__ __forceinline__ void donut_cell(int f, int width, int outside, int& c
   }
 }
 
-template <int W>
-__device__ __forceinline__ void maxabs_row(float* v, int width, float eps) {   // first index wins ties
-  float m = -1.f;
-#pragma unroll
-  for (int i = 0; i < W; ++i) {
-    const float a = fabsf(v[i]);
-    if (i < width && a > m) m = a;
-  }
-  const float inv_d = __fdiv_rn(1.f, __fadd_rn(m, eps));
-#pragma unroll
-  for (int i = 0; i < W; ++i) v[i] *= inv_d;
-}
-
 template <int N, bool CONT>
 __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpParams p) {
   constexpr int STRIDE = CONT ? N - 1 : N, ND = STRIDE * 2 + (CONT ? 1 : 0), IPC = 32 / ND;
@@ -131,16 +125,17 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-  if (warp == 8) {
+  if (warp == I_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s = 0; s < I_LSTAGES; ++s) { mbar_init(&bars[IB_LFULL0 + s], 1); mbar_init(&bars[IB_LEMPTY0 + s], 8); }
+    for (int s = 0; s < I_LSTAGES; ++s) { mbar_init(&bars[IB_LFULL0 + s], 1); mbar_init(&bars[IB_LEMPTY0 + s], I_CWARPS); }
     for (int s = 0; s < I_WSTAGES; ++s) { mbar_init(&bars[IB_WFULL0 + s], 1); mbar_init(&bars[IB_WEMPTY0 + s], 1); }
     mbar_init(&bars[IB_AFULL0], IT); mbar_init(&bars[IB_AFULL1], IT);
     mbar_init(&bars[IB_AEMPTY0], 1); mbar_init(&bars[IB_AEMPTY1], 1);
     mbar_init(&bars[IB_DFULL], 1); mbar_init(&bars[IB_DEMPTY], IT);
+    for (int g = 0; g < 8; ++g) { mbar_init(&bars[IB_ROWS_FULL0 + g], 1); mbar_init(&bars[IB_ROWS_FREE0 + g], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (p.x == nullptr) {
@@ -157,7 +152,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
   const long long tiles = (p.B + IT - 1) / IT;
   const size_t per_input0 = (size_t)p.nodes0 * p.op4;           // floats
 
-  if (warp == 9) {
+  if (warp == I_LOAD_WARP) {
     // =========================== loader: layer-0 groups, then the weight chunks of the tensor-core layers ========
     if (elect_one()) {
       uint32_t ql = 0, qw = 0;
@@ -181,7 +176,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == I_MMA_WARP) {
     // =========================== MMA warp ===================================================================
     const uint32_t leader = elect_one();
     uint32_t qw = 0, qa = 0, qd = 0;
@@ -217,21 +212,25 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
       }
     }
   } else {
-    // =========================== sample warps ===============================================================
-    const int blk = warp >> 2;
-    const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float4* myrec = sRec + warp * 32;
-    const int qtr = lane >> 3, l8 = lane & 7, rowb = p.op4 * 4;   // bytes per node row of the layer-0 table
+    // =========================== compute warps ==============================================================
+    // warps w and w + 8 share the 32 samples of group w & 7 in layer 0 (16 each: four warps per scheduler keep the
+    // shared-memory pipe busy); the tensor-core layers and the output belong to the main warp (w < 8, thread = sample),
+    // while its helper already gathers the next tile
+    const int grp = warp & 7, hf = warp >> 3;
+    const bool main_w = hf == 0;
+    const int blk = grp >> 2;
+    const uint32_t tm_lane = tmem + ((uint32_t)((grp & 3) * 32) << 16);
+    float4* myrec = sRec + warp * 64;                                // [2 buffers][2 inputs][16 samples]
+    const int qtr = lane >> 3, l8 = lane & 7, rowb = p.op4 * 4;       // bytes per node row of the layer-0 table
     const LagrangeTable& lag = p.lag;
     uint32_t ql = 0, qa = 0, qd = 0;
-    const int fg = p.width + p.outside, WW = p.width * p.width;
-    long long tm_all = ICLK(), tm_lwait = 0, tm_l0 = 0, tm_tc = 0, tm_awt = 0, tm_dwt = 0, tm_out = 0, tm_pre = 0, tm_ldx = 0, tm_post = 0;
+    const int fg = p.width + p.outside;
+    long long tm_all = ICLK(), tm_lwait = 0, tm_l0 = 0, tm_tc = 0, tm_awt = 0, tm_dwt = 0, tm_out = 0, tm_rec = 0, tm_ldx = 0, tm_rows = 0, tm_pre = 0;
+    uint32_t nt = 0;                                                 // tiles this CTA has started
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      // ---- layer 0: warp = 32 samples (lane = sample for the basis records, lanes = outputs for the contraction)
-      long long cq0 = 0;
+      // ---- layer 0: lanes = (sample, input parity) for the basis records, lanes = outputs for the contraction
       {
-        const long long cp0 = ICLK();
-        const long long bl = tile * IT + warp * 32 + lane;
+        const long long bl = tile * IT + grp * 32 + 16 * hf + (lane & 15);
         const bool live = bl < p.B;
         int y0 = 0, x0 = 0;
         if (p.x == nullptr) {
@@ -240,132 +239,135 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
           y0 = ph * p.stride - p.pad;
           x0 = pw * p.stride - p.pad;
         }
-        // a quarter-warp owns the samples 4k + qtr (k = 0..7) of the warp's 32; its 8 lanes hold outputs 4*l8 .. +3 and
+        // a quarter-warp owns the samples 4k + qtr (k = 0..3) of the warp's 16; its 8 lanes hold outputs 4*l8 .. +3 and
         // 32 + 4*l8 .. +3: one LDS.128 fetches 128 contiguous bytes of FOUR samples' node rows (conflict-free), and the
-        // broadcast of a basis record costs one wavefront per sample instead of four
-        float acc[8][8];
+        // broadcast of a basis record costs half a wavefront per sample
+        float acc[4][8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[k][c] = 0.f;
-        // the 4 (or fewer) input values of group g of this lane's sample, issued one group ahead of their use; patch mode
-        // reads its donut-cell table entries one group earlier still (no LDS -> address -> LDG chain on the issue path)
-        auto load_tab = [&](int g, int* t) {
-          const int i0 = g * p.gi;
-#pragma unroll
-          for (int il = 0; il < 4; ++il) t[il] = (p.x == nullptr && il < p.gi && i0 + il < p.in0) ? sTab[i0 + il] : 0;
+        // Software pipeline over the groups of the ring (gi <= 2 inputs each).  Lane = (sample s = lane & 15 of the warp's
+        // 16, input h = lane >> 4 of the group): one pass of the record code serves both inputs.  At the top of group g:
+        // the records of group g + 1 are computed from values loaded a group earlier, the values of group g + 2 are
+        // requested, their donut-cell table entries (patch mode) one group earlier still.
+        const int hsel = lane >> 4;
+        auto load_tab = [&](int g) {
+          const int i = g * p.gi + hsel;
+          return (p.x == nullptr && hsel < p.gi && i < p.in0) ? sTab[i] : 0;
         };
-        auto load_x = [&](int g, const int* t, float* xv) {
-          const int i0 = g * p.gi, gi = min(p.gi, p.in0 - i0);
-#pragma unroll
-          for (int il = 0; il < 4; ++il) {
-            xv[il] = 0.f;
-            if (live && il < gi) {
-              if (p.x != nullptr)
-                xv[il] = __ldg(p.x + bl * p.in0 + i0 + il);
-              else
-                xv[il] = __ldg(p.image + ((size_t)(t[il] >> 16) * p.H + reflect(y0 + ((t[il] >> 8) & 255), p.H)) * p.W +
-                               reflect(x0 + (t[il] & 255), p.W));
-            }
+        auto load_x = [&](int g, int t) {
+          const int i = g * p.gi + hsel;
+          float v = 0.f;
+          if (live && hsel < p.gi && i < p.in0) {
+            if (p.x != nullptr)
+              v = __ldg(p.x + bl * p.in0 + i);
+            else
+              v = __ldg(p.image + ((size_t)(t >> 16) * p.H + reflect(y0 + ((t >> 8) & 255), p.H)) * p.W +
+                        reflect(x0 + (t & 255), p.W));
+          }
+          return v;
+        };
+        // basis records of a group: rec[il][s] = (first node row in bytes from the slab, N basis values)
+        auto make_records = [&](float xval, float4* dst) {
+          if (hsel < p.gi) {
+            const int id = hoir::segment_index(xval, 1.f, 2.f, p.segf0, p.seg0);
+            const float xi = p.pow2_0 ? hoir::local_coordinate<true>(xval, id, 1.f, 2.f, p.segf0, p.inv_segf0)
+                                      : hoir::local_coordinate<false>(xval, id, 1.f, 2.f, p.segf0, p.inv_segf0);
+            float l[N];
+            hoir::lagrange<N>(lag.X, lag.D, xi, l);
+            HOIR_DBG_ASSERT(id >= 0 && (uint32_t)((hsel * p.nodes0 + id * p.stride0 + N) * rowb) <= p.stage_bytes0);
+            dst[lane] = make_float4(__int_as_float((hsel * p.nodes0 + id * p.stride0) * rowb), l[0], N > 1 ? l[1] : 0.f,
+                                    N > 2 ? l[2] : 0.f);
           }
         };
-        // basis record of (this lane's sample, input il of a group): first node row (bytes from the slab) + N values
-        auto make_record = [&](float xval, int il, float4* dst) {
-          const int id = hoir::segment_index(xval, 1.f, 2.f, p.segf0, p.seg0);
-          const float xi = p.pow2_0 ? hoir::local_coordinate<true>(xval, id, 1.f, 2.f, p.segf0, p.inv_segf0)
-                                    : hoir::local_coordinate<false>(xval, id, 1.f, 2.f, p.segf0, p.inv_segf0);
-          float l[N];
-          hoir::lagrange<N>(lag.X, lag.D, xi, l);
-          HOIR_DBG_ASSERT(id >= 0 && il < p.gi && (uint32_t)((il * p.nodes0 + id * p.stride0 + N) * rowb) <= p.stage_bytes0);
-          dst[lane] = make_float4(__int_as_float((il * p.nodes0 + id * p.stride0) * rowb), l[0], N > 1 ? l[1] : 0.f,
-                                  N > 2 ? l[2] : 0.f);
-        };
-        float xv[4], xn[4];
-        int tb[4];
-        load_tab(0, tb);
-        load_x(0, tb, xv);
-        load_tab(1, tb);
-        uint32_t cnt = 0;                                      // records are double-buffered: input k lives in buffer k & 1
-        make_record(xv[0], 0, myrec);
+        const long long cp0 = ICLK();
+        int tb = load_tab(0);
+        float xc = load_x(0, tb), xn;
+        make_records(xc, myrec);
+        tb = load_tab(1);
+        xc = load_x(1, tb);                      // (groups past the last one: every lane predicated off)
+        tb = load_tab(2);
         __syncwarp();
         tm_pre += ICLK() - cp0;
         for (int g = 0; g < p.ngroups; ++g, ++ql) {
           const uint32_t st = ql % I_LSTAGES, ph = (ql / I_LSTAGES) & 1;
           const int gi = min(p.gi, p.in0 - g * p.gi);
-          const bool more = g + 1 < p.ngroups;
-#pragma unroll
-          for (int il = 0; il < 4; ++il) xn[il] = 0.f;
-          const long long cx0 = ICLK();
-          if (more) load_x(g + 1, tb, xn);
-          load_tab(g + 2, tb);
+          const long long cr0 = ICLK();
+          make_records(xc, myrec + ((g + 1) & 1) * 32);
+          const long long cr1 = ICLK();
+          xn = load_x(g + 2, tb);
+          tb = load_tab(g + 3);
           const long long c0 = ICLK();
-          tm_ldx += c0 - cx0;
+          tm_rec += cr1 - cr0;
+          tm_ldx += c0 - cr1;
           mbar_wait(&bars[IB_LFULL0 + st], ph);
           const long long c1 = ICLK();
           tm_lwait += c1 - c0;
           const uint8_t* slab = sLRing + (size_t)st * p.stage_bytes0 + 16 * l8;
+          const float4* cur = myrec + (g & 1) * 32 + qtr;
+#pragma unroll 1
+          for (int il = 0; il < gi; ++il, cur += 16) {
 #pragma unroll
-          for (int il = 0; il < 4; ++il) {
-            if (il < gi) {
-              // the next input's record is written while this one is consumed (other buffer)
-              float4* nxt = myrec + ((cnt + 1) & 1) * 32 * 8;
-              if (il + 1 < gi) make_record(xv[(il + 1) & 3], il + 1, nxt);
-              else if (more) make_record(xn[0], 0, nxt);
-              const float4* cur = myrec + (cnt & 1) * 32 * 8 + qtr;
+            for (int k = 0; k < 4; ++k) {
+              const float4 rc = cur[4 * k];                 // 4 distinct records per instruction (one per quarter-warp)
+              const float lj[3] = {rc.y, rc.z, rc.w};
+              const uint8_t* row = slab + __float_as_int(rc.x);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float4 rc = cur[4 * k];               // 4 distinct records per instruction (one per quarter-warp)
-                const float lj[3] = {rc.y, rc.z, rc.w};
-                const uint8_t* row = slab + __float_as_int(rc.x);
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                  // every lane loads (lanes past the row's last output read the next row / stage: in bounds of the ring,
-                  // never stored) -- no predicates, no zero fills in the inner loop
-                  const float4 a = *reinterpret_cast<const float4*>(row + j * rowb);
-                  const float4 c = *reinterpret_cast<const float4*>(row + j * rowb + 128);
-                  acc[k][0] = fmaf(lj[j], a.x, acc[k][0]); acc[k][1] = fmaf(lj[j], a.y, acc[k][1]);
-                  acc[k][2] = fmaf(lj[j], a.z, acc[k][2]); acc[k][3] = fmaf(lj[j], a.w, acc[k][3]);
-                  acc[k][4] = fmaf(lj[j], c.x, acc[k][4]); acc[k][5] = fmaf(lj[j], c.y, acc[k][5]);
-                  acc[k][6] = fmaf(lj[j], c.z, acc[k][6]); acc[k][7] = fmaf(lj[j], c.w, acc[k][7]);
-                }
+              for (int j = 0; j < N; ++j) {
+                // every lane loads (lanes past the row's last output read the next row / stage: in bounds of the ring,
+                // never stored) -- no predicates, no zero fills in the inner loop
+                const float4 a = *reinterpret_cast<const float4*>(row + j * rowb);
+                const float4 c = *reinterpret_cast<const float4*>(row + j * rowb + 128);
+                acc[k][0] = fmaf(lj[j], a.x, acc[k][0]); acc[k][1] = fmaf(lj[j], a.y, acc[k][1]);
+                acc[k][2] = fmaf(lj[j], a.z, acc[k][2]); acc[k][3] = fmaf(lj[j], a.w, acc[k][3]);
+                acc[k][4] = fmaf(lj[j], c.x, acc[k][4]); acc[k][5] = fmaf(lj[j], c.y, acc[k][5]);
+                acc[k][6] = fmaf(lj[j], c.z, acc[k][6]); acc[k][7] = fmaf(lj[j], c.w, acc[k][7]);
               }
-              __syncwarp();
-              ++cnt;
             }
           }
+          __syncwarp();
           if (lane == 0) mbar_arrive(&bars[IB_LEMPTY0 + st]);
           tm_l0 += ICLK() - c1;
-#pragma unroll
-          for (int il = 0; il < 4; ++il) xv[il] = xn[il];
+          xc = xn;
         }
-        cq0 = ICLK();
-        // the tile's layer-0 output -> shared memory rows (thread-per-sample form for the tensor-core layers)
-        float* rows = sAct + (size_t)(warp * 32) * I_PITCH;
+        // the layer-0 output of the warp's 16 samples -> shared memory rows (thread-per-sample form for the
+        // tensor-core layers); a helper first waits until its main warp is done with the previous tile's rows
+        const long long cw0 = ICLK();
+        if (!main_w && nt > 0) mbar_wait(&bars[IB_ROWS_FREE0 + grp], (nt - 1) & 1);
+        float* rows = sAct + (size_t)(grp * 32 + 16 * hf) * I_PITCH;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int o = (c < 4 ? 0 : 28) + 4 * l8 + c;
-            HOIR_DBG_ASSERT(o >= p.hid || (warp * 32 + 4 * k + qtr) * I_PITCH + o < IT * I_PITCH);
+            HOIR_DBG_ASSERT(o >= p.hid || (grp * 32 + 16 * hf + 4 * k + qtr) * I_PITCH + o < IT * I_PITCH);
             if (o < p.hid) rows[(4 * k + qtr) * I_PITCH + o] = acc[k][c];
           }
+        ++nt;
+        if (!main_w) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[IB_ROWS_FULL0 + grp]);
+          continue;                                            // on to the next tile's layer 0
+        }
+        mbar_wait(&bars[IB_ROWS_FULL0 + grp], (nt - 1) & 1);
         __syncwarp();
+        tm_rows += ICLK() - cw0;
       }
-      // ---- tensor-core layers: thread = sample
+      // ---- tensor-core layers (main warps): thread = sample, its activation row stays in shared memory
       const long long ct0 = ICLK();
-      tm_post += ct0 - cq0;
-      const long long b = tile * IT + tid;
+      const long long b = tile * IT + grp * 32 + lane;
       const bool live = b < p.B;
-      float* row = sAct + (size_t)tid * I_PITCH;
-      float h[I_MAXW];
-#pragma unroll
-      for (int i = 0; i < I_MAXW; ++i) h[i] = i < p.hid ? row[i] : 0.f;
+      float* row = sAct + (size_t)(grp * 32 + lane) * I_PITCH;
       for (int l = 0; l < p.ntc; ++l) {
         const int in_f = p.tc_in[l];
-        if (p.normalize) maxabs_row<I_MAXW>(h, in_f, p.norm_eps);
-#pragma unroll
-        for (int i = 0; i < I_MAXW; ++i)
-          if (i < in_f) row[i] = h[i];
+        float inv_d = 1.f;
+        if (p.normalize) {                                   // MaxAbsNormalization: x / (max |x| + eps)
+          float m = 0.f;
+#pragma unroll 10
+          for (int i = 0; i < in_f; ++i) m = fmaxf(m, fabsf(row[i]));
+          inv_d = __fdiv_rn(1.f, __fadd_rn(m, p.norm_eps));
+        }
         const int nch = p.tc_nch[l];
 #pragma unroll 1
         for (int c = 0; c < nch; ++c, ++qa) {
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
 #pragma unroll
           for (int m = 0; m < IPC; ++m) {
             const int i = c * IPC + m;
-            const float xa = i < in_f ? row[i] : 0.f;
+            const float xa = i < in_f ? row[i] * inv_d : 0.f;
             // two segments on [-1, 1]: the same roundings as the generic index / local coordinate (fused_mlp.cu: locate2)
             const float t = __fadd_rn(xa, 1.f);
             const int id = t >= 1.f ? 1 : 0;
@@ -411,8 +413,13 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
         fence_after();
 #pragma unroll
         for (int g = 0; g < I_MAXW; g += 16)
-          if (g < p.tc_outp[l]) tmem_ld16(tm_lane + I_D_COL + blk * 64 + g, h + g);
-        tmem_wait_ld();
+          if (g < p.tc_outp[l]) {
+            float t16[16];
+            tmem_ld16(tm_lane + I_D_COL + blk * 64 + g, t16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) row[g + j] = t16[j];
+          }
         fence_before();
         mbar_arrive(&bars[IB_DEMPTY]);
         ++qd;
@@ -422,33 +429,33 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
       tm_tc += co0 - ct0;
       if (live) {
         if (p.fold_out == nullptr) {
-#pragma unroll
-          for (int o = 0; o < 32; ++o)
-            if (o < p.out) p.y[b * p.out + o] = p.post_scale ? 0.5f * (h[o] + 1.f) : h[o];
+          for (int o = 0; o < p.out; ++o) p.y[b * p.out + o] = p.post_scale ? 0.5f * (row[o] + 1.f) : row[o];
         } else {
           const int ph = (int)(b / p.nW), pw = (int)(b - (long long)ph * p.nW);
-#pragma unroll
-          for (int o = 0; o < 32; ++o) {
-            if (o < p.out) {
-              const int c = o / WW, e = o - c * WW, kh = e / p.width, kw = e - kh * p.width;
-              const int r = ph * p.width + kh - fg, cc = pw * p.width + kw - fg;
-              if (r >= 0 && r < p.H && cc >= 0 && cc < p.W) {
-                const size_t k = ((size_t)c * p.H + r) * p.W + cc;
-                p.fold_out[k] = p.fold_prev ? p.alpha * __ldg(p.fold_prev + k) + (1.f - p.alpha) * h[o] : h[o];
-              }
+          int c = 0, kh = 0, kw = 0;
+          for (int o = 0; o < p.out; ++o) {
+            const int r = ph * p.width + kh - fg, cc = pw * p.width + kw - fg;
+            if (r >= 0 && r < p.H && cc >= 0 && cc < p.W) {
+              const size_t k = ((size_t)c * p.H + r) * p.W + cc;
+              const float hv = row[o];
+              p.fold_out[k] = p.fold_prev ? p.alpha * __ldg(p.fold_prev + k) + (1.f - p.alpha) * hv : hv;
             }
+            if (++kw == p.width) { kw = 0; if (++kh == p.width) { kh = 0; ++c; } }
           }
         }
       }
       tm_out += ICLK() - co0;
+      // the helper may overwrite the rows of this group now
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[IB_ROWS_FREE0 + grp]);
     }
-    if (HOIR_INTERP_TIMERS && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7))
-      printf("warp %d all %lld  layer0: pre %lld ldx %lld wait %lld work %lld post %lld  tc %lld (a-wait %lld d-wait %lld)  out %lld\n", warp,
-             ICLK() - tm_all, tm_pre, tm_ldx, tm_lwait, tm_l0, tm_post, tm_tc, tm_awt, tm_dwt, tm_out);
+    if (HOIR_INTERP_TIMERS && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 15))
+      printf("warp %d all %lld  layer0: pre %lld rec %lld ldx %lld wait %lld work %lld rows %lld  tc %lld (a-wait %lld d-wait %lld)  out %lld\n",
+             warp, ICLK() - tm_all, tm_pre, tm_rec, tm_ldx, tm_lwait, tm_l0, tm_rows, tm_tc, tm_awt, tm_dwt, tm_out);
   }
   fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (warp == I_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 // ---- packing ---------------------------------------------------------------------------------------------------
@@ -515,7 +522,7 @@ bool igeometry(const hoir_mlp_desc* m, IGeo* g) {
   const size_t per_input = (size_t)g->nodes0 * g->op4 * sizeof(float);
   int gi = (int)((I_LRING_BYTES / I_LSTAGES) / per_input);
   if (gi < 1 || (per_input % 16) != 0) return false;
-  g->gi = gi > 4 ? 4 : gi;
+  g->gi = gi > 2 ? 2 : gi;                              // lanes = 16 samples x 2 inputs for the basis records
   g->ngroups = (g->in0 + g->gi - 1) / g->gi;
   g->stage_bytes0 = (uint32_t)((g->gi * per_input + 127) / 128 * 128);
   if ((size_t)I_LSTAGES * g->stage_bytes0 > I_LRING_BYTES) return false;
