@@ -1,6 +1,6 @@
 // fused_interp.cu -- whole-network FORWARD kernel for the neighborhood interpolator family
-//   in0 -> hid -> ... -> hid -> out,  piecewise-Lagrange layers (continuous / discontinuous, n = 2 or 3), a many-segment
-//   input layer and 2-segment hidden / output layers with MaxAbsNormalization in between -- Net(cfg) as built by
+//   in0 -> hid -> ... -> hid -> out,  piecewise-Lagrange layers (continuous / discontinuous, n = 2 or 3), an input layer
+//   with any number of segments and 1- or 2-segment hidden / output layers with MaxAbsNormalization in between -- Net(cfg) as built by
 //   /root/reference/examples/implicit_neighborhood.py:37-41 from /root/reference/config/neighborhood_config.yaml:25-31
 //   (216 -> 50 -> 50 -> 50 -> 27 for width = outside = 3).
 //
@@ -18,7 +18,7 @@
 //             Patch mode: the input value of (sample, feature) is read straight from the image (reflection and
 //             donut order computed in-kernel) -- no [B, 216] feature tensor in HBM.
 //   hidden /  the tile's layer-0 output goes to shared memory rows; the main warp of each pair (thread = sample) runs
-//   output    MaxAbs and every 2-segment layer as a dense contraction over its densified basis (ND = 3 .. 6 node slots
+//   output    MaxAbs and every 1- / 2-segment layer as a dense contraction over its densified basis (ND = 2 .. 6 node slots
 //   layers    per input, 32 / ND inputs per 32-column chunk) on tcgen05 (kind::tf32, 3 passes A*B + A_lo*B + A*B_lo):
 //             basis chunks are written straight into TMEM, the pre-swizzled hi | lo weight-chunk images stream through
 //             a ring of their own, accumulators in TMEM, results back to the shared-memory row.  The helper warp of
@@ -73,7 +73,7 @@ struct InterpParams {
   int pow2_0;
   int gi, ngroups;
   uint32_t stage_bytes0;
-  int tc_in[I_MAXTC], tc_out[I_MAXTC], tc_outp[I_MAXTC], tc_nch[I_MAXTC];
+  int tc_in[I_MAXTC], tc_out[I_MAXTC], tc_outp[I_MAXTC], tc_nch[I_MAXTC], tc_seg[I_MAXTC];
   const float* tc_img[I_MAXTC];    // [chunk][hi | lo][outp x 32] pre-swizzled chunk images
   int normalize;
   float norm_eps;
@@ -111,9 +111,36 @@ __device__ __forceinline__ void donut_cell(int f, int width, int outside, int& c
   }
 }
 
+// One 32-column chunk of the densified basis of a 1- or 2-segment layer for this thread's sample: ND node slots per input,
+// 32 / ND inputs per chunk (inputs c * IPC ...), zero elsewhere.  Segment index and local coordinate with the roundings of
+// the generic code (hoir_common.cuh: for 1 or 2 segments on [-1, 1] every scaling is exact).
+template <int N, bool CONT, int SEG>
+__device__ __forceinline__ void basis_chunk(const float* row, float inv_d, int c, int in_f, const LagrangeTable& lag, float* v) {
+  constexpr int STRIDE = CONT ? N - 1 : N, ND = STRIDE * SEG + (CONT ? 1 : 0), IPC = 32 / ND;
+#pragma unroll
+  for (int k = IPC * ND; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+  for (int m = 0; m < IPC; ++m) {
+    const int i = c * IPC + m;
+    const float xa = i < in_f ? row[i] * inv_d : 0.f;
+    const float t = __fadd_rn(xa, 1.f);
+    const int id = SEG == 2 && t >= 1.f ? 1 : 0;
+    const float xi = __fmaf_rn(2.f, SEG == 2 ? (id ? xa : t) : t * 0.5f, -1.f);
+    float lv[N];
+    hoir::lagrange<N>(lag.X, lag.D, xi, lv);
+    const int base = id * STRIDE;
+#pragma unroll
+    for (int q = 0; q < ND; ++q) {
+      float vq = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) vq = (q == base + j) ? lv[j] : vq;
+      v[m * ND + q] = i < in_f ? vq : 0.f;
+    }
+  }
+}
+
 template <int N, bool CONT>
 __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpParams p) {
-  constexpr int STRIDE = CONT ? N - 1 : N, ND = STRIDE * 2 + (CONT ? 1 : 0), IPC = 32 / ND;
   extern __shared__ __align__(1024) uint8_t ism[];
   uint8_t* sLRing = ism + IS_LRING;
   uint8_t* sWRing = ism + IS_WRING;
@@ -373,27 +400,8 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
         for (int c = 0; c < nch; ++c, ++qa) {
           const uint32_t buf = qa & 1, ph = (qa >> 1) & 1;
           float v[32], lo[32];
-#pragma unroll
-          for (int k = IPC * ND; k < 32; ++k) v[k] = 0.f;
-#pragma unroll
-          for (int m = 0; m < IPC; ++m) {
-            const int i = c * IPC + m;
-            const float xa = i < in_f ? row[i] * inv_d : 0.f;
-            // two segments on [-1, 1]: the same roundings as the generic index / local coordinate (fused_mlp.cu: locate2)
-            const float t = __fadd_rn(xa, 1.f);
-            const int id = t >= 1.f ? 1 : 0;
-            const float xi = __fmaf_rn(2.f, id ? xa : t, -1.f);
-            float lv[N];
-            hoir::lagrange<N>(lag.X, lag.D, xi, lv);
-            const int base = id * STRIDE;
-#pragma unroll
-            for (int q = 0; q < ND; ++q) {
-              float vq = 0.f;
-#pragma unroll
-              for (int j = 0; j < N; ++j) vq = (q == base + j) ? lv[j] : vq;
-              v[m * ND + q] = i < in_f ? vq : 0.f;
-            }
-          }
+          if (p.tc_seg[l] == 2) basis_chunk<N, CONT, 2>(row, inv_d, c, in_f, lag, v);
+          else basis_chunk<N, CONT, 1>(row, inv_d, c, in_f, lag, v);
 #pragma unroll
           for (int k = 0; k < 32; ++k) lo[k] = tf32_lo(v[k]);
           const long long ca0 = ICLK();
@@ -488,10 +496,10 @@ __global__ void interp_pack_image_kernel(const float* __restrict__ w, float* __r
 }
 
 struct IGeo {
-  int kind, n, L, in0, hid, out, ntc, nd, ipc;
+  int kind, n, L, in0, hid, out, ntc;
   int nodes0, op4, gi, ngroups;
   uint32_t stage_bytes0;
-  int tc_in[I_MAXTC], tc_out[I_MAXTC], tc_outp[I_MAXTC], tc_nch[I_MAXTC];
+  int tc_in[I_MAXTC], tc_out[I_MAXTC], tc_outp[I_MAXTC], tc_nch[I_MAXTC], tc_seg[I_MAXTC], tc_nd[I_MAXTC], tc_ipc[I_MAXTC];
   long long off[HOIR_MAX_LAYERS + 1];          // packed float offsets per layer, then the total
 };
 
@@ -507,7 +515,7 @@ bool igeometry(const hoir_mlp_desc* m, IGeo* g) {
     if (d.kind != l0.kind || d.n != l0.n || d.length != 2.f || d.periodicity > 0.f) return false;
     if (d.rescale != 1.f) return false;
     if (l > 0 && d.in_features != m->layers[l - 1].out_features) return false;
-    if (l > 0 && d.segments != 2) return false;
+    if (l > 0 && d.segments != 1 && d.segments != 2) return false;
     if (l < L - 1 && d.out_features != l0.out_features) return false;
   }
   const int hid = l0.out_features, out = m->layers[L - 1].out_features;
@@ -515,8 +523,6 @@ bool igeometry(const hoir_mlp_desc* m, IGeo* g) {
   g->kind = l0.kind; g->n = l0.n; g->L = L;
   g->in0 = l0.in_features; g->hid = hid; g->out = out; g->ntc = L - 1;
   const int stride = hoir::piecewise_stride(l0.kind, l0.n);
-  g->nd = stride * 2 + (l0.kind == HOIR_CONTINUOUS ? 1 : 0);
-  g->ipc = 32 / g->nd;
   g->nodes0 = hoir_layer_nodes(&l0);
   g->op4 = (hid + 3) & ~3;
   const size_t per_input = (size_t)g->nodes0 * g->op4 * sizeof(float);
@@ -534,7 +540,10 @@ bool igeometry(const hoir_mlp_desc* m, IGeo* g) {
     g->tc_in[k] = m->layers[l].in_features;
     g->tc_out[k] = m->layers[l].out_features;
     g->tc_outp[k] = (m->layers[l].out_features + 15) & ~15;
-    g->tc_nch[k] = (m->layers[l].in_features + g->ipc - 1) / g->ipc;
+    g->tc_seg[k] = m->layers[l].segments;
+    g->tc_nd[k] = stride * g->tc_seg[k] + (l0.kind == HOIR_CONTINUOUS ? 1 : 0);        // == hoir_layer_nodes
+    g->tc_ipc[k] = 32 / g->tc_nd[k];
+    g->tc_nch[k] = (m->layers[l].in_features + g->tc_ipc[k] - 1) / g->tc_ipc[k];
     g->off[l] = o;
     o += (long long)g->tc_nch[k] * 2 * g->tc_outp[k] * 32;
   }
@@ -555,6 +564,7 @@ int ifill(const hoir_mlp_desc* m, const IGeo& g, const float* packed, InterpPara
   p->gi = g.gi; p->ngroups = g.ngroups; p->stage_bytes0 = g.stage_bytes0;
   for (int k = 0; k < g.ntc; ++k) {
     p->tc_in[k] = g.tc_in[k]; p->tc_out[k] = g.tc_out[k]; p->tc_outp[k] = g.tc_outp[k]; p->tc_nch[k] = g.tc_nch[k];
+    p->tc_seg[k] = g.tc_seg[k];
     p->tc_img[k] = packed + g.off[k + 1];
   }
   p->normalize = m->normalize;
@@ -595,7 +605,7 @@ int hoir_interp_pack(const hoir_mlp_desc* m, const float* const* w, float* packe
   for (int l = 1; l < g.L; ++l) {
     const int k = l - 1;
     interp_pack_image_kernel<<<sms, 256, 0, st>>>(w[l], packed + g.off[l], g.tc_in[k], g.tc_out[k], hoir_layer_nodes(&m->layers[l]),
-                                                  g.nd, g.ipc, g.tc_nch[k], g.tc_outp[k]);
+                                                  g.tc_nd[k], g.tc_ipc[k], g.tc_nch[k], g.tc_outp[k]);
   }
   HOIR_CHECK_CUDA(cudaGetLastError());
   return HOIR_OK;

@@ -166,8 +166,9 @@ int hoir_radial_sample(const float* images, const float* stripes, int M, int C, 
  * write both. */
 int hoir_mlp_fused_supported(const hoir_mlp_desc* m);           /* 1 / 0 */
 /* 2: forward AND training step are fused (== hoir_mlp_fused_supported); 1: the forward only -- the neighborhood
- * interpolator family (many-segment input layer + 2-segment hidden / output layers, <= 64 wide, <= 32 outputs; e.g.
- * 216 -> 50 -> 50 -> 50 -> 27 of /root/reference/config/neighborhood_config.yaml): hoir_mlp_pack / hoir_mlp_forward /
+ * interpolator family (3-5 piecewise layers, n = 2 or 3, 1- or 2-segment hidden / output layers, <= 64 wide, <= 32
+ * outputs: the stock /root/reference/config/neighborhood_config.yaml and the 216 -> 50 -> 50 -> 50 -> 27 network of
+ * /root/reference/README.md:57): hoir_mlp_pack / hoir_mlp_forward /
  * hoir_interp_frame apply, training goes through the per-layer entry points; 0: neither */
 int hoir_mlp_forward_supported(const hoir_mlp_desc* m);
 long long hoir_mlp_packed_size(const hoir_mlp_desc* m);         /* floats, or -1 */

@@ -37,14 +37,14 @@ def main():
         net.use_fused = False
         u = timeit(lambda: H.neighborhood_sample_generator(net, im, 3, 3), 5)
         net.use_fused = True
-        print(f"n={n} frame {size}^2 ({patches} patches): fused {f:.3f} ms ({patches / f * 1e-6:.1f} Mpatch/s), unfused {u:.3f} ms")
+        print(f"n={n} frame {size}^2 ({patches} patches): fused {f:.3f} ms ({patches / f * 1e-3:.1f} Mpatch/s), unfused {u:.3f} ms")
     B = 1 << 18
     x = torch.rand(B, 216, device=dev) * 2 - 1
     with torch.no_grad():
         f = timeit(lambda: net(x), 10)
         net.use_fused = False
         u = timeit(lambda: net(x), 5)
-    print(f"n={n} forward B=2^18 rows: fused {f:.3f} ms ({B / f * 1e-6:.1f} Msample/s), per-layer {u:.3f} ms")
+    print(f"n={n} forward B=2^18 rows: fused {f:.3f} ms ({B / f * 1e-3:.1f} Msample/s), per-layer {u:.3f} ms")
 
 
 if __name__ == "__main__":

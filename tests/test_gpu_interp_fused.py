@@ -24,6 +24,11 @@ VARIANTS = {
                   in_segments=100, out_segments=2, hidden_segments=2),
     "deep": dict(layer_type="continuous", n=2, in_width=24, out_width=3, hidden_layers=3, hidden_width=64,
                  in_segments=7, out_segments=2, hidden_segments=2),
+    # the stock /root/reference/config/neighborhood_config.yaml: one input / output segment, one 10-wide hidden layer
+    "stock": dict(layer_type="continuous", n=3, in_width=216, out_width=27, hidden_layers=1, hidden_width=10,
+                  in_segments=1, out_segments=1, hidden_segments=2),
+    "disc1": dict(layer_type="discontinuous", n=2, in_width=48, out_width=27, hidden_layers=2, hidden_width=20,
+                  in_segments=5, out_segments=2, hidden_segments=1),
     "odd": dict(layer_type="continuous", n=3, in_width=9, out_width=32, hidden_layers=1, hidden_width=33,
                 in_segments=16, out_segments=2, hidden_segments=2),
 }
@@ -58,6 +63,7 @@ def test_support_matrix():
     assert sup() == 1 and sup(layer_type="discontinuous", in_segments=32) == 1 and sup(n=2) == 1 and sup(hidden_layers=3) == 1
     assert sup(hidden_width=64) == 1 and sup(out_width=32) == 1 and sup(in_segments=3) == 1
     assert sup(hidden_width=65) == 0 and sup(out_width=33) == 0 and sup(hidden_layers=4) == 0
+    assert sup(hidden_segments=1) == 1 and sup(out_segments=1, in_segments=1, hidden_width=10, hidden_layers=1) == 1
     assert sup(hidden_segments=3) == 0 and sup(n=4) == 0 and sup(layer_type="fourier") == 0
     assert sup(in_segments=200) == 0                         # one input's node rows no longer fit a ring stage
     c2 = H.HighOrderMLP(normalization=H.MaxAbsNormalization, **MLP_KW["C2"])
@@ -137,7 +143,7 @@ def test_packed_weights_follow_the_optimizer():
         assert rel_err(a2, net(x)) <= TOL
 
 
-@pytest.mark.parametrize("name,width,outside", [("C4", 3, 3), ("C4s", 3, 1), ("disc2", 1, 1)])
+@pytest.mark.parametrize("name,width,outside", [("C4", 3, 3), ("C4s", 3, 1), ("disc2", 1, 1), ("stock", 3, 3)])
 @pytest.mark.parametrize("h,w", [(21, 21), (40, 57), (99, 64)])
 def test_frame_matches_oracle_and_unfused_path(name, width, outside, h, w):
     ref, net = pair(name)
