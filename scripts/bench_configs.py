@@ -139,7 +139,7 @@ def c4():
     ms = timeit(gstep, 20)
     report("C4 same, gather + the whole step replayed from ONE CUDA graph (GraphedStep)", B, ms, 162600, "")
     ms = timeit(lambda: H.neighborhood_sample_generator(net, img, 3, 3), 3)
-    report("C4 inference: one generate_sequence frame on 2048^2 (gather + forward + fold)", 2048 * 2048, ms, 68600 / 9, "per output pixel")
+    report("C4 inference: one generate_sequence frame on 2048^2 (hoir_interp_frame: pad + gather + forward + fold + blend in ONE launch)", 2048 * 2048, ms, 68600 / 9, "per output pixel")
 
 
 def c5(tr):
