@@ -394,8 +394,13 @@ bool hoir_slab_eligible(const hoir_layer_desc* d, long long B) {
   return per_input <= kSlabBudget;
 }
 
+// gw0_tc.cu: the same sum as a tcgen05 contraction (node slots of an input <= 128, <= 64 outputs)
+bool hoir_gw0_tc_eligible(const hoir_layer_desc* d, long long B);
+int hoir_gw0_tc(const hoir_layer_desc* d, long long B, const float* x, const float* gy, int ldo, float* gw, cudaStream_t stream);
+
 int hoir_slab_grad_w(const hoir_layer_desc* d, long long B, const float* x, const float* gy, int ldo, float* gw,
                      cudaStream_t stream) {
+  if (hoir_gw0_tc_eligible(d, B)) return hoir_gw0_tc(d, B, x, gy, ldo, gw, stream);
   SlabParams p;
   slab_fill(d, B, &p, SLAB_THREADS / 32);
   p.x = x;

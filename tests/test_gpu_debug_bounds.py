@@ -68,6 +68,11 @@ with torch.no_grad():
     fr = H.neighborhood_sample_generator(net2, img, 3, 1, alpha=0.5, prev=img)
     net2.use_fused = False
     assert rel_err(fr, H.neighborhood_sample_generator(net2, img, 3, 1, alpha=0.5, prev=img)) <= 1e-5
+# dL/dw of a many-segment layer at large batch on the tensor cores (csrc/gw0_tc.cu)
+lay = H.high_order_fc_layers("continuous", n=2, in_features=48, out_features=27, segments=50).cuda()
+xg = (torch.rand(9000, 48, generator=g) * 2.2 - 1.1).cuda().requires_grad_(True)
+lay(xg).square().mean().backward()
+assert torch.isfinite(lay.w.grad).all()
 torch.cuda.synchronize()
 print("DEBUG_BOUNDS_OK")
 '''
