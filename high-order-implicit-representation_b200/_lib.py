@@ -101,6 +101,8 @@ _EXPORTS = {
                                      C.c_void_p, C.c_void_p]),
     "hoir_mlp_fused_supported": (C.c_int, [C.POINTER(MlpDesc)]),
     "hoir_mlp_forward_supported": (C.c_int, [C.POINTER(MlpDesc)]),
+    "hoir_mlp_forward_acts": (C.c_int, [C.POINTER(MlpDesc), C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "hoir_interp_frame": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hoir_mlp_packed_size": (C.c_longlong, [C.POINTER(MlpDesc)]),

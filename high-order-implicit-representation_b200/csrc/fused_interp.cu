@@ -79,6 +79,7 @@ struct InterpParams {
   float norm_eps;
   const float* w0;
   // output
+  float* acts;                     // training: [tc layer][pre-norm | normalized][B][hid] inputs of the tensor-core layers, or nullptr
   float* y;                        // [B][out]
   int post_scale;
   float* fold_out;                 // [C][H][W] (fold mode) or nullptr
@@ -395,6 +396,27 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
           for (int i = 0; i < in_f; ++i) m = fmaxf(m, fabsf(row[i]));
           inv_d = __fdiv_rn(1.f, __fadd_rn(m, p.norm_eps));
         }
+        if (p.acts != nullptr) {
+          // training: the layer's input rows (as they arrive, and as the layer sees them) for the backward kernels;
+          // the warp writes its 32 rows cooperatively (lanes = consecutive features)
+          __syncwarp();                                      // (every lane's row of the previous layer is written)
+          const float* grows = sAct + (size_t)(grp * 32) * I_PITCH;
+          const long long bw = tile * IT + grp * 32;
+          float* ah = p.acts + ((size_t)(2 * l) * p.B + bw) * in_f;
+          float* au = p.acts + ((size_t)(2 * l + 1) * p.B + bw) * in_f;
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const float sc = __shfl_sync(0xffffffffu, inv_d, r);
+            if (bw + r < p.B) {
+              for (int i = lane; i < in_f; i += 32) {
+                const float hv = grows[r * I_PITCH + i];
+                ah[(size_t)r * in_f + i] = hv;
+                if (p.normalize) au[(size_t)r * in_f + i] = hv * sc;
+              }
+            }
+          }
+          __syncwarp();
+        }
         const int nch = p.tc_nch[l];
 #pragma unroll 1
         for (int c = 0; c < nch; ++c, ++qa) {
@@ -611,7 +633,7 @@ int hoir_interp_pack(const hoir_mlp_desc* m, const float* const* w, float* packe
   return HOIR_OK;
 }
 int hoir_interp_forward(const hoir_mlp_desc* m, long long B, const float* x, const float* packed, float* y, int post_scale,
-                        cudaStream_t st) {
+                        float* acts, cudaStream_t st) {
   IGeo g;
   if (!igeometry(m, &g)) return hoir_set_error(HOIR_EUNSUPPORTED, "not a fused interpolator network", "hoir_mlp_forward");
   if (B < 0) return hoir_set_error(HOIR_EINVAL, "negative batch", "hoir_mlp_forward");
@@ -623,6 +645,7 @@ int hoir_interp_forward(const hoir_mlp_desc* m, long long B, const float* x, con
   p.x = x;
   p.y = y;
   p.post_scale = post_scale;
+  p.acts = acts;
   return ilaunch(g, p, st);
 }
 

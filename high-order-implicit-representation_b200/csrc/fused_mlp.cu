@@ -1218,7 +1218,7 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
     return hoir_fourier_forward(m, B, x, mesh, packed, y, post_scale, (cudaStream_t)stream);
   if (interp_only(m)) {
     if (mesh != nullptr) return hoir_set_error(HOIR_EUNSUPPORTED, "mesh coordinates: implicit-image networks only", "hoir_mlp_forward");
-    return hoir_interp_forward(m, B, x, packed, y, post_scale, (cudaStream_t)stream);
+    return hoir_interp_forward(m, B, x, packed, y, post_scale, nullptr, (cudaStream_t)stream);
   }
   const FusedEntry* e = find_entry(m);
   if (!e) return hoir_set_error(HOIR_EUNSUPPORTED, "no fused instantiation for this network", "hoir_mlp_forward");
@@ -1248,6 +1248,16 @@ extern "C" int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float
   e->fwd<<<grid, BT, e->smem_fwd, (cudaStream_t)stream>>>(p);
   HOIR_CHECK_CUDA(cudaGetLastError());
   return HOIR_OK;
+}
+
+// Forward of a forward-only-fused network (hoir_mlp_forward_supported == 1) that also stores what the per-layer backward
+// kernels need: acts[(2 * (l - 1) + k) * B * hid ...] = input rows of layer l >= 1, k = 0 as the previous layer produced them
+// (the input of MaxAbsNormalization), k = 1 normalized (the input of the layer; only written when the network normalizes).
+extern "C" int hoir_mlp_forward_acts(const hoir_mlp_desc* m, long long B, const float* x, const float* packed, float* y,
+                                     float* acts, void* stream) {
+  if (!interp_only(m)) return hoir_set_error(HOIR_EUNSUPPORTED, "not a forward-only-fused network", "hoir_mlp_forward_acts");
+  if (B > 0 && !acts) return hoir_set_error(HOIR_EINVAL, "null device pointer", "hoir_mlp_forward_acts");
+  return hoir_interp_forward(m, B, x, packed, y, 0, acts, (cudaStream_t)stream);
 }
 
 namespace {

@@ -217,7 +217,7 @@ bool hoir_interp_supported(const hoir_mlp_desc* m);
 long long hoir_interp_packed_offset(const hoir_mlp_desc* m, int layer);      // layer == num_layers: total floats
 int hoir_interp_pack(const hoir_mlp_desc* m, const float* const* w, float* packed, cudaStream_t st);
 int hoir_interp_forward(const hoir_mlp_desc* m, long long B, const float* x, const float* packed, float* y, int post_scale,
-                        cudaStream_t st);
+                        float* acts, cudaStream_t st);      // acts: [layer - 1][pre-norm | normalized][B][hid] or nullptr
 
 // fused Fourier-network family (fused_fourier.cu), dispatched from the C ABI entry points of fused_mlp.cu
 bool hoir_fourier_supported(const hoir_mlp_desc* m);

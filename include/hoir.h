@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HOIR_VERSION 105
+#define HOIR_VERSION 106
 #define HOIR_MAX_LAYERS 8
 #define HOIR_MAX_N 32          /* max basis functions per segment / Fourier terms          */
 #define HOIR_MAX_ROTATIONS 8
@@ -180,6 +180,15 @@ int hoir_mlp_pack(const hoir_mlp_desc* m, const float* const* w, float* packed, 
 int hoir_mlp_forward(const hoir_mlp_desc* m, long long B, const float* x,
                      const hoir_mesh_desc* mesh, const float* packed, float* y, int post_scale,
                      void* stream);
+
+/* The same forward for TRAINING a forward-only-fused network (hoir_mlp_forward_supported == 1): additionally stores the
+ * inputs of the layers l = 1 .. L-1 for the per-layer backward entry points (hoir_layer_backward,
+ * hoir_maxabs_backward): acts is [L-1][2][B][hidden width]; [l-1][0] = the rows as layer l-1 produced them (input of
+ * MaxAbsNormalization), [l-1][1] = the normalized rows (input of layer l; not written when normalize == 0).
+ * Replaces the forward half of Net.eval_step for the interpolator
+ * (/root/reference/high_order_implicit_representation/networks.py:64-70). */
+int hoir_mlp_forward_acts(const hoir_mlp_desc* m, long long B, const float* x, const float* packed, float* y,
+                          float* acts, void* stream);
 
 /* One pass of the neighborhood interpolator over an image in ONE launch: reflection pad by 2*outside + width,
  * stride-width donut patches, model forward, fold, crop and blend

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"libhoir_b200.so does not export {name}"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS)
-    assert lib.hoir_version() == 105
+    assert lib.hoir_version() == 106
 
 
 def test_struct_layouts_match_header():
