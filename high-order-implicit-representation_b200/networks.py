@@ -201,13 +201,19 @@ class HighOrderMLP(nn.Module):
         outside, call ``_lib.weights_changed()``."""
         ws = [l.w for l in self.high_order_layers()]
         key = (_lib.WEIGHT_EPOCH,) + tuple((w.data_ptr(), w._version) for w in ws)
-        if getattr(self, "_packed_key", None) != key:
-            lib, desc, dev = _lib.lib(), self.mlp_desc(), ws[0].device
-            packed = torch.empty(lib.hoir_mlp_packed_size(desc), device=dev, dtype=torch.float32)
-            with torch.cuda.device(dev):
-                _lib.check(lib.hoir_mlp_pack(desc, _lib.ptr_table([w.detach().contiguous() for w in ws]), _lib.dptr(packed),
-                                             _lib.stream_ptr(dev)))
-            self._packed, self._packed_key = packed, key
+        capturing = torch.cuda.is_current_stream_capturing()
+        if getattr(self, "_packed_key", None) == key and not capturing:
+            return self._packed
+        lib, desc, dev = _lib.lib(), self.mlp_desc(), ws[0].device
+        packed = torch.empty(lib.hoir_mlp_packed_size(desc), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hoir_mlp_pack(desc, _lib.ptr_table([w.detach().contiguous() for w in ws]), _lib.dptr(packed),
+                                         _lib.stream_ptr(dev)))
+        if capturing:
+            # a CUDA graph records the pack: every replay re-packs the weights it then holds; the copy lives in the
+            # graph's memory pool and is not valid outside a replay, so it never enters the cache
+            return packed
+        self._packed, self._packed_key = packed, key
         return self._packed
 
     def forward(self, x: Tensor) -> Tensor:

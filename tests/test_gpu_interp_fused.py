@@ -278,3 +278,30 @@ def test_frame_full_size_properties():
     oc = H.neighborhood_sample_generator(net, const, width=3, outside=3)
     per_block = oc[:, :3, :3]
     assert torch.equal(oc, per_block.repeat(1, 86, 86)[:, :256, :256])
+
+
+def test_graphed_training_step_repacks_every_replay():
+    """GraphedStep over the fused-forward training function: the weight pack is recorded in the graph (never served from
+    the cache), so replays follow the weights; eager evaluation after replays sees the trained weights."""
+    _, a = pair("C4s")
+    _, b = pair("C4s")
+    g = torch.Generator().manual_seed(11)
+    x = (torch.rand(4096, 48, generator=g) * 2 - 1).cuda()
+    t = (torch.rand(4096, 27, generator=g) * 2 - 1).cuda()
+    with torch.no_grad():
+        y0 = a(x)
+    gs = H.GraphedStep(a, H.Adam(a.parameters(), lr=1e-3, capturable=True), x, t, warmup=1)   # (restores the weights)
+    opt = H.Adam(b.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(3):
+        l_graph = gs.replay().item()
+        opt.zero_grad()
+        l = torch.nn.functional.mse_loss(b(x).flatten(), t.flatten())
+        l.backward()
+        opt.step()
+        losses.append((l_graph, l.item()))
+    for lg, le in losses:
+        assert abs(lg - le) <= 1e-5 * abs(le), losses
+    assert losses[0][1] > losses[-1][1]
+    with torch.no_grad():                               # (Adam turns last-bit gradient differences into +-lr steps)
+        assert rel_err(a(x), b(x)) <= 5e-3 and rel_err(a(x), y0) > 2e-2
