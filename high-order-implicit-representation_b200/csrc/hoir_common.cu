@@ -20,7 +20,7 @@ struct Workspace {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-constexpr int kSlots = 5;
+constexpr int kSlots = 6;
 Workspace g_ws[16][kSlots];
 // forward calls arrive on the caller's thread, backward calls on autograd's device thread: the table is shared
 std::mutex g_ws_mutex;
