@@ -34,7 +34,7 @@ namespace {
 using namespace tc;
 
 constexpr int Z_UNIT = 64, Z_WORKERS = 256, Z_THREADS = Z_WORKERS + 32, Z_MMAW = Z_WORKERS / 32;
-constexpr int Z_IB = 4, Z_NBLK = 2, Z_NB = Z_IB * 64;    // inputs per block, blocks per CTA, B rows (= MMA N) per block
+constexpr int Z_NBLK = 2, Z_NB = 256;                    // blocks per CTA, B rows (= MMA N) per block: 4 inputs x 64 node slots or 2 x 128
 constexpr int Z_D_COL = 0;                               // D: 2 blocks x 256 columns = all of TMEM
 constexpr uint32_t Z_B_BYTES = Z_NB * 128;               // one Phi^T tile (hi or lo): 256 rows x 64 samples (fp16)
 constexpr uint32_t Z_A_BYTES = 128 * 128;                // one (dL/dy)^T tile: 128 rows (hi | lo halves) x 64 samples (fp16)
@@ -95,8 +95,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {     // D f
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int N>
+template <int N, int SPS>                                // SPS: log2 of the node slots per input (6 or 7)
 __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p) {
+  constexpr int Z_IB = Z_NB >> SPS;                        // inputs per block
   extern __shared__ __align__(1024) uint8_t zsm[];
   uint8_t* sB = zsm + ZS_B;                                // [block][hi | lo] Phi^T tiles
   uint8_t* sA = zsm + ZS_G;                                // [2] (dL/dy)^T tiles: rows 0..63 hi halves, 64..127 lo halves
@@ -209,10 +210,10 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
     // warp 4 + w takes the tasks w and w + 4 (task t: block t / 3, input t % 3 of the block)
     const int wq = warp - 4;
     int prev[2][2] = {{-1, -1}, {-1, -1}};                  // [task][sample half]: first row of the cells set for the last unit
-    float xpre[2][2];
+    float xpre[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     auto prefetch = [&](int u) {
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
+      for (int r = 0; r < Z_NBLK * Z_IB / 4; ++r) {
         const int t = wq + 4 * r, i = i0 + t;
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs) {
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
       float xv[2][2] = {{xpre[0][0], xpre[0][1]}, {xpre[1][0], xpre[1][1]}};
       prefetch(u + 1);
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
+      for (int r = 0; r < Z_NBLK * Z_IB / 4; ++r) {
         const int t = wq + 4 * r;
         const int blk = t / Z_IB, m = t - blk * Z_IB, i = i0 + t;
         uint8_t* th = sB + blk * 2 * Z_B_BYTES;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
           const float sc = (i < p.in_f && b < b_hi) ? p.rescale : 0.f;      // rows past the slice / inputs past the layer: nothing
 #pragma unroll
           for (int j = 0; j < N; ++j) l[hs][j] *= sc;
-          row[hs] = m * 64 + id * p.stride;
+          row[hs] = (m << SPS) + id * p.stride;
           HOIR_DBG_ASSERT(row[hs] >= 0 && row[hs] + N <= Z_NB);
         }
         mbar_wait(&bars[ZB_BEMPTY0 + blk], (u & 1) ^ 1);                    // the MMAs of unit u - 1 are done with the tiles
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
     // items (output o, column n of the pass), n fastest
     for (int it = tid; it < 64 * Z_FC; it += Z_THREADS) {
       const int o = it / Z_FC, n = it - o * Z_FC, col = hb * Z_FC + n;
-      const int t = col >> 6, q = col & 63, i = i0 + t;
+      const int t = col >> SPS, q = col & ((1 << SPS) - 1), i = i0 + t;
       if (o < p.out_f && i < p.in_f && q < p.nodes) {
         const float v = (sF[o * Z_FP + n] + sF[(64 + o) * Z_FP + n]) * inv_S;
         if (v != 0.f) hoir::red_add(p.gw + ((size_t)o * p.in_f + i) * p.nodes + q, v);
@@ -314,14 +315,14 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
 
 }  // namespace
 
-// many-segment piecewise layer whose node slots fit 64 rows of a Phi^T block and whose outputs fit 64 accumulator lanes
+// many-segment piecewise layer whose node slots fit 64 or 128 rows of a Phi^T block and whose outputs fit 64 accumulator lanes
 bool hoir_gw0_tc_eligible(const hoir_layer_desc* d, long long B) {
   static const bool off = getenv("HOIR_NO_GW0_TC") != nullptr;
   if (off || d == nullptr || B < 8192) return false;
   if (d->kind != HOIR_CONTINUOUS && d->kind != HOIR_DISCONTINUOUS) return false;
   if (d->length != 2.f || d->periodicity > 0.f || d->segments <= 8 || d->n < 2 || d->n > 3) return false;
   if (d->out_features > 64 || d->in_features < 12) return false;
-  return hoir_layer_nodes(d) <= 64;
+  return hoir_layer_nodes(d) <= 128;
 }
 
 int hoir_gw0_tc(const hoir_layer_desc* d, long long B, const float* x, const float* gy, int ldo, float* gw, cudaStream_t stream) {
@@ -342,14 +343,16 @@ int hoir_gw0_tc(const hoir_layer_desc* d, long long B, const float* x, const flo
   p.rescale = d->rescale == 0.f ? 1.f : d->rescale;
   p.pow2 = hoir::is_pow2(d->segments);
   hoir_make_lagrange_table(d->n, 1.f, &p.lag);
-  const int per_cta = Z_NBLK * Z_IB;
+  const int sps = p.nodes <= 64 ? 6 : 7;
+  const int per_cta = Z_NBLK * (Z_NB >> sps);
   const int groups = (p.in_f + per_cta - 1) / per_cta;
   // a slice = what one CTA accumulates in TMEM before its single flush.  The tensor core TRUNCATES its fp32 accumulator
   // (measured in fused_fourier.cu), a bias that grows with the number of non-zero terms per element: at most 2048 samples
   // per slice (~80 non-zero terms per node at 50 segments) keeps dL/dw within 6e-6 of the fp64 oracle at any batch; the
   // slices then add up in fp32 atomics (round to nearest).
   long long slices = hoir_num_sms() / groups;
-  const long long min_slices = (B + 2047) / 2048, max_slices = (B + 1023) / 1024;
+  static const long long cap = getenv("HOIR_GW0_SLICE") ? atoll(getenv("HOIR_GW0_SLICE")) : 2048;   // (experiments)
+  const long long min_slices = (B + cap - 1) / cap, max_slices = (B + 1023) / 1024;
   if (slices < min_slices) slices = min_slices;
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
@@ -365,7 +368,7 @@ int hoir_gw0_tc(const hoir_layer_desc* d, long long B, const float* x, const flo
     if (grid > 4LL * hoir_num_sms()) grid = 4LL * hoir_num_sms();
     gy_maxabs_kernel<<<(unsigned)grid, 256, 0, stream>>>(gy, B, p.out_f, ldo, reinterpret_cast<unsigned*>(ws));
   }
-  auto kern = d->n == 2 ? gw0_tc_kernel<2> : gw0_tc_kernel<3>;
+  auto kern = sps == 6 ? (d->n == 2 ? gw0_tc_kernel<2, 6> : gw0_tc_kernel<3, 6>) : (d->n == 2 ? gw0_tc_kernel<2, 7> : gw0_tc_kernel<3, 7>);
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZS_TOTAL));
   kern<<<dim3((unsigned)groups, (unsigned)slices), Z_THREADS, ZS_TOTAL, stream>>>(p);
   HOIR_CHECK_CUDA(cudaGetLastError());

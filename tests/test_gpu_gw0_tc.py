@@ -1,5 +1,5 @@
 """dL/dw of many-segment piecewise layers at large batch through the tensor-core kernel (csrc/gw0_tc.cu: node slots of an
-input <= 64, <= 64 outputs, B >= 8192 -- the input layer of the neighborhood interpolator,
+input <= 128, <= 64 outputs, B >= 8192 -- the input layer of the neighborhood interpolator,
 /root/reference/examples/implicit_neighborhood.py:37-41) against the CPU oracle in fp64.  Tolerance 1e-5 relative
 (BASELINE.json: piecewise layers), tf32 x 3 tensor-core passes."""
 import pytest
@@ -18,6 +18,8 @@ CASES = [  # kind, n, in, out, segments
     ("continuous", 3, 37, 64, 20),         # 41 nodes, 64 outputs, inputs not a multiple of the 8 per CTA
     ("discontinuous", 3, 13, 5, 21),       # 63 nodes, odd everything
     ("continuous", 2, 100, 33, 63),        # 64 nodes exactly
+    ("continuous", 3, 216, 50, 50),        # 101 nodes: 128 slots per input, 4 inputs per CTA (the n = 3 interpolator)
+    ("discontinuous", 2, 30, 27, 64),      # 128 nodes exactly
 ]
 
 
@@ -34,7 +36,7 @@ def _want(kind, n, in_f, out_f, seg, x, gy, w):
 def test_gw_matches_oracle(kind, n, in_f, out_f, seg, B):
     torch.manual_seed(1)
     layer = H.high_order_fc_layers(kind, n=n, in_features=in_f, out_features=out_f, segments=seg).cuda()
-    assert _lib.lib().hoir_layer_nodes(layer.desc) <= 64
+    assert _lib.lib().hoir_layer_nodes(layer.desc) <= 128
     g = torch.Generator().manual_seed(B + in_f)
     x = torch.rand(B, in_f, generator=g) * 2.2 - 1.1
     gy = torch.randn(B, out_f, generator=g)
