@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
 // many-segment piecewise layer whose node slots fit 64 or 128 rows of a Phi^T block and whose outputs fit 64 accumulator lanes
 bool hoir_gw0_tc_eligible(const hoir_layer_desc* d, long long B) {
   static const bool off = getenv("HOIR_NO_GW0_TC") != nullptr;
-  if (off || d == nullptr || B < 8192) return false;
+  static const long long min_b = getenv("HOIR_GW0_MIN_B") ? atoll(getenv("HOIR_GW0_MIN_B")) : 4096;
+  if (off || d == nullptr || B < min_b) return false;
   if (d->kind != HOIR_CONTINUOUS && d->kind != HOIR_DISCONTINUOUS) return false;
   if (d->length != 2.f || d->periodicity > 0.f || d->segments <= 8 || d->n < 2 || d->n > 3) return false;
   if (d->out_features > 64 || d->in_features < 12) return false;

@@ -386,7 +386,10 @@ int slab_launch(K kern, SlabParams& p, cudaStream_t stream, size_t extra_smem = 
 // many-segment piecewise layer, big batch: the shared-memory slab kernels apply
 bool hoir_slab_eligible(const hoir_layer_desc* d, long long B) {
   static const bool off = getenv("HOIR_NO_SLAB") != nullptr;
-  if (off || d == nullptr || B < 4096) return false;
+  // measured on the interpolator's input layer (216 x 51 x 50): 36 us at batch 256 (the reference's batch size), where the
+  // generic tile kernel -- 18-sample tiles on 15 CTAs -- takes 450 us; 70 us at 4096, from where gw0_tc.cu (53 us) takes over
+  static const long long min_b = getenv("HOIR_SLAB_MIN_B") ? atoll(getenv("HOIR_SLAB_MIN_B")) : 128;
+  if (off || d == nullptr || B < min_b) return false;
   if (d->kind != HOIR_CONTINUOUS && d->kind != HOIR_DISCONTINUOUS) return false;
   if (d->length != 2.f || d->periodicity > 0.f || d->segments <= 8 || d->n < 2 || d->n > 3) return false;
   if (d->out_features > 64) return false;

@@ -155,10 +155,14 @@ class HighOrderMLP(nn.Module):
             segments=out_segments, **common))
         self.model = nn.Sequential(*layers)
         self.use_fused = use_fused
-        # batch sizes from which the forward-only-fused kernel is used (it streams the whole input-layer table once per
-        # 256-sample tile, yet measured faster than the 7 per-layer launches from batch 256 up: 0.17 against 0.38 ms)
-        self.fused_train_min_batch = 1
-        self.fused_infer_min_batch = 1
+        # batch sizes from which the forward-only-fused kernel is used.  It streams the whole input-layer table once per
+        # 256-sample tile, yet measured faster than the 7 per-layer launches from batch 256 up when that table is the bulk
+        # of the work (216 x 51 x 50: 0.17 against 0.38 ms eager, 0.38 against 0.40 ms per graphed training step at batch
+        # 256); for a small input layer (the stock neighborhood_config.yaml: 3 nodes x 10 outputs per input) the tile's
+        # 108 ring hand-offs cost more than the per-layer launches until the batch fills the GPU (65536: 0.42 / 1.11 ms).
+        big_table = (in_segments or 1) * n_in * hidden_width >= 1024
+        self.fused_train_min_batch = 1 if big_table else 16384
+        self.fused_infer_min_batch = 1 if big_table else 16384
         self._mlp_desc: Optional[_lib.MlpDesc] = None
         self._desc_checked = False
 

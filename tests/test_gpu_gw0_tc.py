@@ -1,5 +1,5 @@
 """dL/dw of many-segment piecewise layers at large batch through the tensor-core kernel (csrc/gw0_tc.cu: node slots of an
-input <= 128, <= 64 outputs, B >= 8192 -- the input layer of the neighborhood interpolator,
+input <= 128, <= 64 outputs, B >= 4096 -- the input layer of the neighborhood interpolator,
 /root/reference/examples/implicit_neighborhood.py:37-41) against the CPU oracle in fp64.  Tolerance 1e-5 relative
 (BASELINE.json: piecewise layers), tf32 x 3 tensor-core passes."""
 import pytest
@@ -32,7 +32,7 @@ def _want(kind, n, in_f, out_f, seg, x, gy, w):
 
 
 @pytest.mark.parametrize("kind,n,in_f,out_f,seg", CASES)
-@pytest.mark.parametrize("B", [8192, 8192 + 1234])
+@pytest.mark.parametrize("B", [4096, 8192 + 1234])
 def test_gw_matches_oracle(kind, n, in_f, out_f, seg, B):
     torch.manual_seed(1)
     layer = H.high_order_fc_layers(kind, n=n, in_features=in_f, out_features=out_f, segments=seg).cuda()

@@ -52,6 +52,7 @@ def pair(name, normalization=True, seed=0):
                 x = layer(x)
     net = H.HighOrderMLP(normalization=H.MaxAbsNormalization if normalization else None, **kw)
     net.load_state_dict(ref.state_dict())
+    net.fused_train_min_batch = net.fused_infer_min_batch = 1      # (every variant through the fused kernels, at every batch)
     return ref, net.cuda()
 
 
