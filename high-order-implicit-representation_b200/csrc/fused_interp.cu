@@ -78,6 +78,7 @@ struct InterpParams {
   int normalize;
   float norm_eps;
   const float* w0;
+  int gpc;                         // 32-sample groups per CTA tile (1, 2, 4, 8): small batches spread over more SMs
   // output
   float* acts;                     // training: [tc layer][pre-norm | normalized][B][hid] inputs of the tensor-core layers, or nullptr
   float* y;                        // [B][out]
@@ -158,11 +159,11 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s = 0; s < I_LSTAGES; ++s) { mbar_init(&bars[IB_LFULL0 + s], 1); mbar_init(&bars[IB_LEMPTY0 + s], I_CWARPS); }
+    for (int s = 0; s < I_LSTAGES; ++s) { mbar_init(&bars[IB_LFULL0 + s], 1); mbar_init(&bars[IB_LEMPTY0 + s], 2 * p.gpc); }
     for (int s = 0; s < I_WSTAGES; ++s) { mbar_init(&bars[IB_WFULL0 + s], 1); mbar_init(&bars[IB_WEMPTY0 + s], 1); }
-    mbar_init(&bars[IB_AFULL0], IT); mbar_init(&bars[IB_AFULL1], IT);
+    mbar_init(&bars[IB_AFULL0], 32 * p.gpc); mbar_init(&bars[IB_AFULL1], 32 * p.gpc);
     mbar_init(&bars[IB_AEMPTY0], 1); mbar_init(&bars[IB_AEMPTY1], 1);
-    mbar_init(&bars[IB_DFULL], 1); mbar_init(&bars[IB_DEMPTY], IT);
+    mbar_init(&bars[IB_DFULL], 1); mbar_init(&bars[IB_DEMPTY], 32 * p.gpc);
     for (int g = 0; g < 8; ++g) { mbar_init(&bars[IB_ROWS_FULL0 + g], 1); mbar_init(&bars[IB_ROWS_FREE0 + g], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_base_s;
-  const long long tiles = (p.B + IT - 1) / IT;
+  const int TS = 32 * p.gpc;                                     // samples per tile (the groups >= gpc of the CTA idle)
+  const long long tiles = (p.B + TS - 1) / TS;
   const size_t per_input0 = (size_t)p.nodes0 * p.op4;           // floats
 
   if (warp == I_LOAD_WARP) {
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
             const uint64_t dW[2] = {make_desc(wbase, 512), make_desc(wbase + (uint32_t)p.tc_outp[l] * 128u, 512)};
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk)
+              if (blk * 4 < p.gpc)
 #pragma unroll
               for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
@@ -239,6 +242,8 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
         ++qd;
       }
     }
+  } else if ((warp & 7) >= p.gpc) {
+    // (a 32-sample group beyond the tile: small batches run fewer groups per CTA on more SMs)
   } else {
     // =========================== compute warps ==============================================================
     // warps w and w + 8 share the 32 samples of group w & 7 in layer 0 (16 each: four warps per scheduler keep the
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       // ---- layer 0: lanes = (sample, input parity) for the basis records, lanes = outputs for the contraction
       {
-        const long long bl = tile * IT + grp * 32 + 16 * hf + (lane & 15);
+        const long long bl = tile * TS + grp * 32 + 16 * hf + (lane & 15);
         const bool live = bl < p.B;
         int y0 = 0, x0 = 0;
         if (p.x == nullptr) {
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
       }
       // ---- tensor-core layers (main warps): thread = sample, its activation row stays in shared memory
       const long long ct0 = ICLK();
-      const long long b = tile * IT + grp * 32 + lane;
+      const long long b = tile * TS + grp * 32 + lane;
       const bool live = b < p.B;
       float* row = sAct + (size_t)(grp * 32 + lane) * I_PITCH;
       for (int l = 0; l < p.ntc; ++l) {
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
           // the warp writes its 32 rows cooperatively (lanes = consecutive features)
           __syncwarp();                                      // (every lane's row of the previous layer is written)
           const float* grows = sAct + (size_t)(grp * 32) * I_PITCH;
-          const long long bw = tile * IT + grp * 32;
+          const long long bw = tile * TS + grp * 32;
           float* ah = p.acts + ((size_t)(2 * l) * p.B + bw) * in_f;
           float* au = p.acts + ((size_t)(2 * l + 1) * p.B + bw) * in_f;
 #pragma unroll 4
@@ -600,8 +605,11 @@ int ilaunch(const IGeo& g, InterpParams& p, cudaStream_t st) {
   const void* kern = g.n == 2 ? (g.kind == HOIR_CONTINUOUS ? (const void*)interp_fwd_kernel<2, true> : (const void*)interp_fwd_kernel<2, false>)
                               : (g.kind == HOIR_CONTINUOUS ? (const void*)interp_fwd_kernel<3, true> : (const void*)interp_fwd_kernel<3, false>);
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IS_TOTAL));
-  const long long tiles = (p.B + IT - 1) / IT;
   const int sms = hoir_num_sms();
+  int gpc = 8;                                                  // halve the tile while that puts more SMs to work
+  while (gpc > 1 && (p.B + 16 * gpc - 1) / (16 * gpc) <= sms) gpc >>= 1;
+  p.gpc = gpc;
+  const long long tiles = (p.B + 32 * gpc - 1) / (32 * gpc);
   void* args[] = {&p};
   HOIR_CHECK_CUDA(cudaLaunchKernel(kern, dim3((unsigned)(tiles < sms ? tiles : sms)), dim3(I_THREADS), args, IS_TOTAL, st));
   HOIR_CHECK_CUDA(cudaGetLastError());
