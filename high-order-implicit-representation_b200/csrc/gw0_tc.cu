@@ -95,7 +95,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {     // D f
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int N, int SPS>                                // SPS: log2 of the node slots per input (6 or 7)
+template <int N, int SPS>                                // SPS: log2 of the node slots per input (6, 7 or 8)
 __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p) {
   constexpr int Z_IB = Z_NB >> SPS;                        // inputs per block
   extern __shared__ __align__(1024) uint8_t zsm[];
@@ -213,8 +213,9 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
     float xpre[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     auto prefetch = [&](int u) {
 #pragma unroll
-      for (int r = 0; r < Z_NBLK * Z_IB / 4; ++r) {
+      for (int r = 0; r < (Z_NBLK * Z_IB + 3) / 4; ++r) {
         const int t = wq + 4 * r, i = i0 + t;
+        if (t >= Z_NBLK * Z_IB) continue;
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs) {
           const long long b = b_lo + (long long)u * Z_UNIT + hs * 32 + lane;
@@ -227,8 +228,9 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
       float xv[2][2] = {{xpre[0][0], xpre[0][1]}, {xpre[1][0], xpre[1][1]}};
       prefetch(u + 1);
 #pragma unroll
-      for (int r = 0; r < Z_NBLK * Z_IB / 4; ++r) {
+      for (int r = 0; r < (Z_NBLK * Z_IB + 3) / 4; ++r) {
         const int t = wq + 4 * r;
+        if (t >= Z_NBLK * Z_IB) continue;
         const int blk = t / Z_IB, m = t - blk * Z_IB, i = i0 + t;
         uint8_t* th = sB + blk * 2 * Z_B_BYTES;
         uint8_t* tl = th + Z_B_BYTES;
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) gw0_tc_kernel(const Gw0Params p)
 
 }  // namespace
 
-// many-segment piecewise layer whose node slots fit 64 or 128 rows of a Phi^T block and whose outputs fit 64 accumulator lanes
+// many-segment piecewise layer whose node slots fit 64, 128 or 256 rows of a Phi^T block and whose outputs fit 64 accumulator lanes
 bool hoir_gw0_tc_eligible(const hoir_layer_desc* d, long long B) {
   static const bool off = getenv("HOIR_NO_GW0_TC") != nullptr;
   static const long long min_b = getenv("HOIR_GW0_MIN_B") ? atoll(getenv("HOIR_GW0_MIN_B")) : 4096;
@@ -323,7 +325,7 @@ bool hoir_gw0_tc_eligible(const hoir_layer_desc* d, long long B) {
   if (d->kind != HOIR_CONTINUOUS && d->kind != HOIR_DISCONTINUOUS) return false;
   if (d->length != 2.f || d->periodicity > 0.f || d->segments <= 8 || d->n < 2 || d->n > 3) return false;
   if (d->out_features > 64 || d->in_features < 12) return false;
-  return hoir_layer_nodes(d) <= 128;
+  return hoir_layer_nodes(d) <= 256;
 }
 
 int hoir_gw0_tc(const hoir_layer_desc* d, long long B, const float* x, const float* gy, int ldo, float* gw, cudaStream_t stream) {
@@ -344,7 +346,7 @@ int hoir_gw0_tc(const hoir_layer_desc* d, long long B, const float* x, const flo
   p.rescale = d->rescale == 0.f ? 1.f : d->rescale;
   p.pow2 = hoir::is_pow2(d->segments);
   hoir_make_lagrange_table(d->n, 1.f, &p.lag);
-  const int sps = p.nodes <= 64 ? 6 : 7;
+  const int sps = p.nodes <= 64 ? 6 : (p.nodes <= 128 ? 7 : 8);
   const int per_cta = Z_NBLK * (Z_NB >> sps);
   const int groups = (p.in_f + per_cta - 1) / per_cta;
   // a slice = what one CTA accumulates in TMEM before its single flush.  The tensor core TRUNCATES its fp32 accumulator
@@ -369,7 +371,9 @@ int hoir_gw0_tc(const hoir_layer_desc* d, long long B, const float* x, const flo
     if (grid > 4LL * hoir_num_sms()) grid = 4LL * hoir_num_sms();
     gy_maxabs_kernel<<<(unsigned)grid, 256, 0, stream>>>(gy, B, p.out_f, ldo, reinterpret_cast<unsigned*>(ws));
   }
-  auto kern = sps == 6 ? (d->n == 2 ? gw0_tc_kernel<2, 6> : gw0_tc_kernel<3, 6>) : (d->n == 2 ? gw0_tc_kernel<2, 7> : gw0_tc_kernel<3, 7>);
+  auto kern = sps == 6 ? (d->n == 2 ? gw0_tc_kernel<2, 6> : gw0_tc_kernel<3, 6>)
+            : sps == 7 ? (d->n == 2 ? gw0_tc_kernel<2, 7> : gw0_tc_kernel<3, 7>)
+                       : (d->n == 2 ? gw0_tc_kernel<2, 8> : gw0_tc_kernel<3, 8>);
   HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZS_TOTAL));
   kern<<<dim3((unsigned)groups, (unsigned)slices), Z_THREADS, ZS_TOTAL, stream>>>(p);
   HOIR_CHECK_CUDA(cudaGetLastError());
