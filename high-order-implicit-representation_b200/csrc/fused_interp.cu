@@ -25,7 +25,9 @@
 //             the pair meanwhile gathers the next tile (two mbarriers per pair hand the rows back and forth).
 //   output    y[b][out], or the fold: pixel (c, ph*w + kh - (w+o), pw*w + kw - (w+o)) = alpha*prev + (1-alpha)*value.
 //
-// Activations never touch HBM.  Training of this family stays on the per-layer kernels (slab_kernels.cu, dense_tc.cu).
+// Activations never touch HBM in inference.  For training (hoir_mlp_forward_acts) the same kernel also stores the inputs of
+// the layers 1 .. L-1 for the per-layer backward kernels (gw0_tc.cu / slab_kernels.cu for the input layer, dense_tc.cu).
+// Small batches run 1, 2 or 4 of the eight 32-sample groups per CTA, so that more SMs stream the table in parallel.
 // The layer-0 loop is kept small on purpose: an earlier version with the four inputs of a group unrolled (7.7 k SASS
 // instructions) lost 25 % to instruction-cache misses.
 #include <stdlib.h>

@@ -169,7 +169,7 @@ int hoir_mlp_fused_supported(const hoir_mlp_desc* m);           /* 1 / 0 */
  * interpolator family (3-5 piecewise layers, n = 2 or 3, 1- or 2-segment hidden / output layers, <= 64 wide, <= 32
  * outputs: the stock /root/reference/config/neighborhood_config.yaml and the 216 -> 50 -> 50 -> 50 -> 27 network of
  * /root/reference/README.md:57): hoir_mlp_pack / hoir_mlp_forward /
- * hoir_interp_frame apply, training goes through the per-layer entry points; 0: neither */
+ * hoir_interp_frame apply; a training step = hoir_mlp_forward_acts + the per-layer backward entry points; 0: neither */
 int hoir_mlp_forward_supported(const hoir_mlp_desc* m);
 long long hoir_mlp_packed_size(const hoir_mlp_desc* m);         /* floats, or -1 */
 long long hoir_mlp_packed_offset(const hoir_mlp_desc* m, int layer);
