@@ -295,6 +295,14 @@ def run_secondary(H, dev, trainer, img, flush, peak_tf, rank, world, dist, which
                            "workload": "one generate_sequence frame on 2048^2 in ONE launch (hoir_interp_frame: reflect-pad + "
                                        "stride-3 gather + 216->50->50->50->27 forward + fold + crop + blend)"}
 
+        # the reference's own operating point for this example: batch_size=256 (/root/reference/README.md:57)
+        xs, ys = gs.x[:256].clone(), gs.y[:256].clone()
+        net_s = _mlp(H, dev, **kw)
+        gss = H.GraphedStep(net_s, H.Adam(net_s.parameters(), lr=1e-4, capturable=True), xs, ys)
+        ms = _timeit(gss.replay, 100)
+        out["c4_b256"] = {"value": 256 / (ms * 1e-3), "unit": "patches/s", "us_per_step": ms * 1e3,
+                          "workload": "C4 network, batch 256 (the reference's batch size), whole step replayed from one CUDA graph"}
+
     def c1_b256():
         kw = dict(layer_type="continuous", n=3, in_width=2, out_width=3, hidden_layers=2, hidden_width=10,
                   in_segments=100, out_segments=2, hidden_segments=2)
