@@ -77,6 +77,33 @@ def test_fused_supported_matrix():
     assert not sup(periodicity=2.0)
 
 
+def test_forward_supported_matrix():
+    """hoir_mlp_forward_supported: 2 = whole training step fused, 1 = forward only (the neighborhood-interpolator family,
+    csrc/fused_interp.cu), 0 = per-layer kernels.  Host logic: no GPU needed."""
+    lib = _lib.lib()
+
+    def sup(**kw):
+        base = dict(layer_type="continuous", n=3, in_width=216, out_width=27, hidden_layers=2, hidden_width=50,
+                    in_segments=50, out_segments=2, hidden_segments=2, normalization=H.MaxAbsNormalization)
+        base.update(kw)
+        return lib.hoir_mlp_forward_supported(H.HighOrderMLP(**base).mlp_desc())
+    assert sup() == 1 and sup(n=2) == 1 and sup(layer_type="discontinuous", in_segments=32) == 1
+    assert sup(hidden_layers=3) == 1 and sup(hidden_width=64) == 1 and sup(out_width=32) == 1
+    assert sup(hidden_segments=1) == 1 and sup(in_segments=1, out_segments=1, hidden_width=10, hidden_layers=1) == 1   # stock yaml
+    assert sup(hidden_width=65) == 0 and sup(out_width=33) == 0 and sup(hidden_layers=4) == 0
+    assert sup(hidden_segments=3) == 0 and sup(n=4) == 0 and sup(layer_type="fourier") == 0 and sup(in_segments=200) == 0
+    assert sup(in_width=4, out_width=3, hidden_layers=1, hidden_width=40, in_segments=100) == 2                  # C2
+    # the thresholds of the fused forward follow the size of the input-layer table
+    big = H.HighOrderMLP(layer_type="continuous", n=2, in_width=216, out_width=27, hidden_layers=2, hidden_width=50,
+                         in_segments=50, out_segments=2, hidden_segments=2)
+    stock = H.HighOrderMLP(layer_type="continuous", n=3, in_width=216, out_width=27, hidden_layers=1, hidden_width=10,
+                           in_segments=1, out_segments=1, hidden_segments=2)
+    assert big.fused_train_min_batch == 1 and stock.fused_train_min_batch == 16384
+    e0 = _lib.WEIGHT_EPOCH
+    _lib.weights_changed()
+    assert _lib.WEIGHT_EPOCH == e0 + 1
+
+
 def test_errors_map_to_python_exceptions():
     lib = _lib.lib()
     bad = _lib.LayerDesc(7, 3, 2, 4, 4, 2.0, 1.0, 0.0, 2.0, 1)
