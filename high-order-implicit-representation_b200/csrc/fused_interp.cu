@@ -143,8 +143,11 @@ __device__ __forceinline__ void basis_chunk(const float* row, float inv_d, int c
   }
 }
 
-template <int N, bool CONT>
+// GPC: 32-sample groups per CTA tile -- 8 (full tiles, the constant lets ptxas keep the schedule of the large-batch case:
+// a run-time count cost 9 % there) or 0 = p.gpc (1, 2 or 4: small batches spread over more SMs)
+template <int N, bool CONT, int GPC>
 __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpParams p) {
+  const int gpc = GPC ? GPC : p.gpc;
   extern __shared__ __align__(1024) uint8_t ism[];
   uint8_t* sLRing = ism + IS_LRING;
   uint8_t* sWRing = ism + IS_WRING;
@@ -161,11 +164,11 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s = 0; s < I_LSTAGES; ++s) { mbar_init(&bars[IB_LFULL0 + s], 1); mbar_init(&bars[IB_LEMPTY0 + s], 2 * p.gpc); }
+    for (int s = 0; s < I_LSTAGES; ++s) { mbar_init(&bars[IB_LFULL0 + s], 1); mbar_init(&bars[IB_LEMPTY0 + s], 2 * gpc); }
     for (int s = 0; s < I_WSTAGES; ++s) { mbar_init(&bars[IB_WFULL0 + s], 1); mbar_init(&bars[IB_WEMPTY0 + s], 1); }
-    mbar_init(&bars[IB_AFULL0], 32 * p.gpc); mbar_init(&bars[IB_AFULL1], 32 * p.gpc);
+    mbar_init(&bars[IB_AFULL0], 32 * gpc); mbar_init(&bars[IB_AFULL1], 32 * gpc);
     mbar_init(&bars[IB_AEMPTY0], 1); mbar_init(&bars[IB_AEMPTY1], 1);
-    mbar_init(&bars[IB_DFULL], 1); mbar_init(&bars[IB_DEMPTY], 32 * p.gpc);
+    mbar_init(&bars[IB_DFULL], 1); mbar_init(&bars[IB_DEMPTY], 32 * gpc);
     for (int g = 0; g < 8; ++g) { mbar_init(&bars[IB_ROWS_FULL0 + g], 1); mbar_init(&bars[IB_ROWS_FREE0 + g], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_base_s;
-  const int TS = 32 * p.gpc;                                     // samples per tile (the groups >= gpc of the CTA idle)
+  const int TS = 32 * gpc;                                     // samples per tile (the groups >= gpc of the CTA idle)
   const long long tiles = (p.B + TS - 1) / TS;
   const size_t per_input0 = (size_t)p.nodes0 * p.op4;           // floats
 
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
             const uint64_t dW[2] = {make_desc(wbase, 512), make_desc(wbase + (uint32_t)p.tc_outp[l] * 128u, 512)};
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk)
-              if (blk * 4 < p.gpc)
+              if (blk * 4 < gpc)
 #pragma unroll
               for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
         ++qd;
       }
     }
-  } else if ((warp & 7) >= p.gpc) {
+  } else if ((warp & 7) >= gpc) {
     // (a 32-sample group beyond the tile: small batches run fewer groups per CTA on more SMs)
   } else {
     // =========================== compute warps ==============================================================
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
     const uint32_t tm_lane = tmem + ((uint32_t)((grp & 3) * 32) << 16);
     float4* myrec = sRec + warp * 64;                                // [2 buffers][2 inputs][16 samples]
     const int qtr = lane >> 3, l8 = lane & 7, rowb = p.op4 * 4;       // bytes per node row of the layer-0 table
+    const bool wide = p.op4 > 32;                                     // more than 32 outputs: two 128-byte reads per row
     const LagrangeTable& lag = p.lag;
     uint32_t ql = 0, qa = 0, qd = 0;
     const int fg = p.width + p.outside;
@@ -353,11 +357,13 @@ __global__ void __launch_bounds__(I_THREADS, 1) interp_fwd_kernel(const InterpPa
                 // every lane loads (lanes past the row's last output read the next row / stage: in bounds of the ring,
                 // never stored) -- no predicates, no zero fills in the inner loop
                 const float4 a = *reinterpret_cast<const float4*>(row + j * rowb);
-                const float4 c = *reinterpret_cast<const float4*>(row + j * rowb + 128);
                 acc[k][0] = fmaf(lj[j], a.x, acc[k][0]); acc[k][1] = fmaf(lj[j], a.y, acc[k][1]);
                 acc[k][2] = fmaf(lj[j], a.z, acc[k][2]); acc[k][3] = fmaf(lj[j], a.w, acc[k][3]);
-                acc[k][4] = fmaf(lj[j], c.x, acc[k][4]); acc[k][5] = fmaf(lj[j], c.y, acc[k][5]);
-                acc[k][6] = fmaf(lj[j], c.z, acc[k][6]); acc[k][7] = fmaf(lj[j], c.w, acc[k][7]);
+                if (wide) {                                   // (outputs 32 .. 63: a second wavefront per sample and row)
+                  const float4 c = *reinterpret_cast<const float4*>(row + j * rowb + 128);
+                  acc[k][4] = fmaf(lj[j], c.x, acc[k][4]); acc[k][5] = fmaf(lj[j], c.y, acc[k][5]);
+                  acc[k][6] = fmaf(lj[j], c.z, acc[k][6]); acc[k][7] = fmaf(lj[j], c.w, acc[k][7]);
+                }
               }
             }
           }
@@ -604,13 +610,19 @@ int ifill(const hoir_mlp_desc* m, const IGeo& g, const float* packed, InterpPara
 }
 
 int ilaunch(const IGeo& g, InterpParams& p, cudaStream_t st) {
-  const void* kern = g.n == 2 ? (g.kind == HOIR_CONTINUOUS ? (const void*)interp_fwd_kernel<2, true> : (const void*)interp_fwd_kernel<2, false>)
-                              : (g.kind == HOIR_CONTINUOUS ? (const void*)interp_fwd_kernel<3, true> : (const void*)interp_fwd_kernel<3, false>);
-  HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IS_TOTAL));
   const int sms = hoir_num_sms();
   int gpc = 8;                                                  // halve the tile while that puts more SMs to work
   while (gpc > 1 && (p.B + 16 * gpc - 1) / (16 * gpc) <= sms) gpc >>= 1;
   p.gpc = gpc;
+  const bool cont = g.kind == HOIR_CONTINUOUS;
+  const void* kern;
+  if (gpc == 8)
+    kern = g.n == 2 ? (cont ? (const void*)interp_fwd_kernel<2, true, 8> : (const void*)interp_fwd_kernel<2, false, 8>)
+                    : (cont ? (const void*)interp_fwd_kernel<3, true, 8> : (const void*)interp_fwd_kernel<3, false, 8>);
+  else
+    kern = g.n == 2 ? (cont ? (const void*)interp_fwd_kernel<2, true, 0> : (const void*)interp_fwd_kernel<2, false, 0>)
+                    : (cont ? (const void*)interp_fwd_kernel<3, true, 0> : (const void*)interp_fwd_kernel<3, false, 0>);
+  HOIR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IS_TOTAL));
   const long long tiles = (p.B + 32 * gpc - 1) / (32 * gpc);
   void* args[] = {&p};
   HOIR_CHECK_CUDA(cudaLaunchKernel(kern, dim3((unsigned)(tiles < sms ? tiles : sms)), dim3(I_THREADS), args, IS_TOTAL, st));
